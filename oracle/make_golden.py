@@ -1,0 +1,251 @@
+"""Generate ``tests/golden/*.npz`` by running the REAL reference (authoring container only).
+
+    PYNEAPPLE_QUIET=1 python oracle/make_golden.py [case ...]
+
+Imports Pyneapple from ``/root/reference/src`` (read-only mount; it does not
+exist on the GPU box), runs its own solvers / fitters on seeded synthetic
+inputs from ``pyneapple_b200.synth`` and stores inputs + outputs.  The
+fixtures are the parity pins for the oracle port (``oracle/ref_port.py``),
+the C restatement (``oracle/pnb_oracle.c``) and the CUDA path.
+"""
+
+from __future__ import annotations
+
+import os
+import sys
+import time
+
+os.environ.setdefault("PYNEAPPLE_QUIET", "1")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference/src")
+
+import numpy as np  # noqa: E402
+
+from pyneapple.models import BiExpModel, MonoExpModel, NNLSModel, TriExpModel  # noqa: E402
+from pyneapple.solvers import (  # noqa: E402
+    ConstrainedCurveFitSolver,
+    CurveFitSolver,
+    NNLSSolver,
+)
+
+from pyneapple_b200 import synth  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+MODELS = {"monoexp": MonoExpModel, "biexp": BiExpModel, "triexp": TriExpModel}
+
+
+def _save(name, **arrays):
+    path = os.path.join(GOLD, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print(f"  wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)")
+
+
+def _curvefit_outputs(solver, n_free):
+    prs = solver.pixel_results_
+    return dict(
+        params=np.array([pr.params for pr in prs]).T,
+        pcov=np.array([pr.covariance for pr in prs]),
+        success=np.array([pr.success for pr in prs]),
+        messages=np.array([pr.message or "" for pr in prs]),
+    )
+
+
+def _run_curvefit(name, model_kind, model_kwargs, b, y, p0, bounds, pixel_fixed=None,
+                  p0_arr=None, bounds_arr=None, cls=CurveFitSolver, **solver_kwargs):
+    model = MODELS[model_kind](**model_kwargs)
+    kw = dict(max_iter=250, tol=1e-8)
+    kw.update(solver_kwargs)
+    solver = cls(model=model, p0=p0, bounds=bounds, **kw)
+    t = time.time()
+    solver.fit(b, y, p0=p0_arr, bounds=bounds_arr, pixel_fixed_params=pixel_fixed)
+    dt = time.time() - t
+    out = _curvefit_outputs(solver, None)
+    if cls is ConstrainedCurveFitSolver:
+        out["nit"] = np.array(
+            [pr.n_iterations if pr.n_iterations is not None else -1 for pr in solver.pixel_results_]
+        )
+    print(f"  {name}: {y.shape[0]} voxels in {dt:.1f}s, success {out['success'].mean():.3f}")
+    extra = {}
+    if pixel_fixed:
+        for k, v in pixel_fixed.items():
+            extra["fixed_" + k] = v
+    if p0_arr is not None:
+        extra.update(p0_arr=p0_arr, lb_arr=bounds_arr[0], ub_arr=bounds_arr[1])
+    _save(
+        name, b=b, y=y, param_names=np.array(model.param_names),
+        all_names=np.array(model._all_param_names),
+        p0=np.array([p0[n] for n in model.param_names], float),
+        lb=np.array([bounds[n][0] for n in model.param_names], float),
+        ub=np.array([bounds[n][1] for n in model.param_names], float),
+        max_iter=kw["max_iter"], tol=kw["tol"], **out, **extra,
+    )
+    return solver
+
+
+def _cfg_args(c):
+    cfg = synth.CONFIGS[c]
+    return cfg, cfg.p0, cfg.bounds
+
+
+def case_mono_c1():
+    cfg, p0, bounds = _cfg_args("C1")
+    b, y, _ = synth.sample_voxels(cfg, 512)
+    _run_curvefit("trf_mono_c1", "monoexp", {}, b, y, p0, bounds)
+
+
+def case_biexp_c2():
+    cfg, p0, bounds = _cfg_args("C2")
+    b, y, _ = synth.sample_voxels(cfg, 2048)
+    _run_curvefit("trf_biexp_s0_c2", "biexp", {"fit_s0": True}, b, y, p0, bounds)
+
+
+def case_biexp_modes():
+    cfg, p0, bounds = _cfg_args("C2")
+    b, y, _ = synth.sample_voxels(cfg, 256, z=5)
+    yn = y / y[:, :1]  # normalised signals for the S0-free modes
+    p0r = {k: p0[k] for k in ("f1", "D1", "D2")}
+    br = {k: bounds[k] for k in ("f1", "D1", "D2")}
+    _run_curvefit("trf_biexp_reduced", "biexp", {}, b, yn, p0r, br)
+    p0f = {"f1": 0.2, "D1": 0.001, "f2": 0.8, "D2": 0.02}
+    bf = {"f1": (0.0, 1.5), "D1": (1e-5, 0.003), "f2": (0.0, 1.5), "D2": (0.003, 0.3)}
+    _run_curvefit("trf_biexp_full", "biexp", {"fit_reduced": False}, b, yn, p0f, bf)
+
+
+def case_triexp():
+    cfg, p0, bounds = _cfg_args("C5")
+    b, y, _ = synth.sample_voxels(cfg, 256)
+    _run_curvefit("trf_triexp_reduced", "triexp", {}, b, y, p0, bounds)
+    p0s = dict(p0, S0=900.0)
+    bs = dict(bounds, S0=(1.0, 5000.0))
+    _run_curvefit("trf_triexp_s0", "triexp", {"fit_s0": True}, b, y[:128] * 1000.0, p0s, bs)
+    p0f = {"f1": 0.15, "D1": 0.1, "f2": 0.25, "D2": 0.01, "f3": 0.6, "D3": 0.001}
+    bf = {"f1": (0.0, 1.0), "D1": (0.03, 0.5), "f2": (0.0, 1.0), "D2": (0.003, 0.03),
+          "f3": (0.0, 1.0), "D3": (1e-4, 0.003)}
+    _run_curvefit("trf_triexp_full", "triexp", {"fit_reduced": False}, b, y[:128], p0f, bf)
+
+
+def case_constrained_c5():
+    cfg, p0, bounds = _cfg_args("C5")
+    b, y, _ = synth.sample_voxels(cfg, 256)
+    _run_curvefit("slsqp_triexp_c5", "triexp", {}, b, y, p0, bounds,
+                  cls=ConstrainedCurveFitSolver, fraction_constraint=True)
+
+
+def case_fixed():
+    cfg, p0, bounds = _cfg_args("C2")
+    b, y, _ = synth.sample_voxels(cfg, 256, z=9)
+    # segmented step 2: per-voxel fixed slow diffusion (analytic-Jacobian path)
+    rng = np.random.default_rng(77)
+    d1 = rng.uniform(8e-4, 2e-3, size=y.shape[0])
+    _run_curvefit("trf_biexp_s0_pixfixed_D1", "biexp", {"fit_s0": True}, b, y, p0, bounds,
+                  pixel_fixed={"D1": d1})
+    # model-level scalar fixed parameter
+    p0m = {k: v for k, v in p0.items() if k != "D2"}
+    bm = {k: v for k, v in bounds.items() if k != "D2"}
+    _run_curvefit("trf_biexp_s0_modelfixed_D2", "biexp",
+                  {"fit_s0": True, "fixed_params": {"D2": 0.03}}, b, y, p0m, bm)
+
+
+def case_per_voxel_p0():
+    """IDEAL-style call: per-voxel p0 and bounds arrays (fitters/ideal.py:240-242)."""
+    cfg, p0, bounds = _cfg_args("C2")
+    b, y, _ = synth.sample_voxels(cfg, 256, z=12)
+    names = ["f1", "D1", "D2", "S0"]
+    rng = np.random.default_rng(5)
+    lo = np.array([bounds[n][0] for n in names])[:, None]
+    hi = np.array([bounds[n][1] for n in names])[:, None]
+    centre = np.array([p0[n] for n in names])[:, None] * rng.uniform(0.7, 1.3, size=(4, y.shape[0]))
+    centre = np.clip(centre, lo, hi)
+    tol = np.array([0.2, 0.2, 0.2, 0.5])[:, None]
+    lb = np.clip(centre * (1 - tol), lo, hi)
+    ub = np.clip(centre * (1 + tol), lo, hi)
+    _run_curvefit("trf_biexp_s0_pervoxel", "biexp", {"fit_s0": True}, b, y, p0, bounds,
+                  p0_arr=centre, bounds_arr=(lb, ub))
+
+
+def case_degenerate():
+    """Appendix A.12 voxels + failure modes (max_iter exhaustion, lb == ub, x0 outside)."""
+    cfg, p0, bounds = _cfg_args("C2")
+    b = cfg.bvalues
+    good = synth.sample_voxels(cfg, 4, z=3)[1]
+    y = np.stack([
+        np.zeros(16), np.full(16, -5.0), np.full(16, 1e-12), np.full(16, 300.0),
+        np.r_[np.nan, good[0][1:]], np.r_[good[1][:5], np.inf, good[1][6:]],
+        good[2], good[3], 1e6 * good[2] / good[2][0], 1e-3 * good[3],
+    ])
+    _run_curvefit("trf_biexp_s0_degenerate", "biexp", {"fit_s0": True}, b, y, p0, bounds)
+    c1, p01, b1 = _cfg_args("C1")
+    _run_curvefit("trf_mono_degenerate", "monoexp", {}, b, y, p01, b1)
+    # nfev exhaustion -> status 0 -> failure -> p0
+    y2 = synth.sample_voxels(cfg, 64, z=3)[1]
+    for mi in (1, 2, 3, 5):
+        _run_curvefit(f"trf_biexp_s0_maxiter{mi}", "biexp", {"fit_s0": True}, b, y2, p0, bounds,
+                      max_iter=mi)
+    # invalid per-voxel bounds / p0
+    names = ["f1", "D1", "D2", "S0"]
+    n = 8
+    P0 = np.tile(np.array([p0[k] for k in names])[:, None], (1, n))
+    LB = np.tile(np.array([bounds[k][0] for k in names])[:, None], (1, n))
+    UB = np.tile(np.array([bounds[k][1] for k in names])[:, None], (1, n))
+    UB[1, 0] = LB[1, 0]            # lb == ub
+    LB[2, 1] = 0.5; UB[2, 1] = 0.4  # lb > ub
+    P0[0, 2] = 1.5                  # x0 above ub
+    P0[3, 3] = 0.0                  # x0 below lb
+    P0[0, 4] = 0.01                 # x0 on the lower bound -> make_strictly_feasible
+    P0[1, 5] = 0.003                # x0 on the upper bound
+    LB[3, 6] = -np.inf              # half-open
+    UB[3, 7] = np.inf
+    _run_curvefit("trf_biexp_s0_badbounds", "biexp", {"fit_s0": True}, b, y2[:n], p0, bounds,
+                  p0_arr=P0, bounds_arr=(LB, UB))
+
+
+def case_nnls_c3():
+    cfg = synth.CONFIGS["C3"]
+    b, y, _ = synth.sample_voxels(cfg, 256)
+    for order, n_vox in ((2, 256), (0, 64), (1, 64), (3, 64)):
+        model = NNLSModel(d_range=(0.0008, 0.5), n_bins=250)
+        solver = NNLSSolver(model=model, reg_order=order, mu=0.02, max_iter=250)
+        t = time.time()
+        solver.fit(b, y[:n_vox])
+        print(f"  nnls reg{order}: {n_vox} voxels in {time.time() - t:.1f}s")
+        _save(
+            f"nnls_c3_reg{order}", b=b, y=y[:n_vox], d_range=np.array([0.0008, 0.5]), n_bins=250,
+            reg_order=order, mu=0.02, max_iter=250,
+            coefficients=solver.params_["coefficients"],
+            residual=solver.diagnostics_["residual"],
+            success=np.array([pr.success for pr in solver.pixel_results_]),
+        )
+    # degenerate signals and a tight iteration cap (failure -> zeros, ||b||)
+    yd = np.stack([np.zeros(16), np.full(16, -5.0), np.full(16, 300.0), 1e-12 * np.ones(16),
+                   np.r_[1000.0, np.zeros(15)], y[0], y[1]])
+    for mi, tag in ((250, "degenerate"), (5, "maxiter5"), (20, "maxiter20")):
+        yy = yd if tag == "degenerate" else y[:32]
+        model = NNLSModel(d_range=(0.0008, 0.5), n_bins=250)
+        solver = NNLSSolver(model=model, reg_order=2, mu=0.02, max_iter=mi)
+        solver.fit(b, yy)
+        _save(
+            f"nnls_c3_{tag}", b=b, y=yy, d_range=np.array([0.0008, 0.5]), n_bins=250,
+            reg_order=2, mu=0.02, max_iter=mi,
+            coefficients=solver.params_["coefficients"],
+            residual=solver.diagnostics_["residual"],
+            success=np.array([pr.success for pr in solver.pixel_results_]),
+        )
+    # a small, odd-shaped problem
+    model = NNLSModel(d_range=(0.001, 0.2), n_bins=37)
+    solver = NNLSSolver(model=model, reg_order=1, mu=0.1, max_iter=250)
+    solver.fit(b[:11], y[:64, :11])
+    _save("nnls_small_reg1", b=b[:11], y=y[:64, :11], d_range=np.array([0.001, 0.2]), n_bins=37,
+          reg_order=1, mu=0.1, max_iter=250, coefficients=solver.params_["coefficients"],
+          residual=solver.diagnostics_["residual"],
+          success=np.array([pr.success for pr in solver.pixel_results_]))
+
+
+CASES = {k[5:]: v for k, v in globals().items() if k.startswith("case_")}
+
+if __name__ == "__main__":
+    os.makedirs(GOLD, exist_ok=True)
+    todo = sys.argv[1:] or list(CASES)
+    for c in todo:
+        print(f"[{c}]")
+        CASES[c]()
