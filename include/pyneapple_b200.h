@@ -1,0 +1,126 @@
+/*
+ * pyneapple_b200 — C ABI of the B200 voxel-fitting engine (libpnb200.so).
+ *
+ * This is the drop-in boundary: plain C, plain pointers and sizes, no torch
+ * types.  Every entry point names the reference interface it replaces
+ * (paths relative to darksim33/Pyneapple, src/pyneapple/).  Array layouts are
+ * the reference's own, so a binding needs no repacking:
+ *
+ *   ydata / signal   (n_vox, n_b)       row-major  -- fitters/base.py:297-308
+ *   p0, lb, ub       (n_params, n_vox)  row-major  -- utility/validation.py:177-203, 248-297
+ *   params (popt)    (n_params, n_vox)  row-major  -- solvers/curvefit.py:231-233
+ *   cov (pcov)       (n_vox, n_free, n_free)       -- solvers/curvefit.py:234-243
+ *   coefficients     (n_vox, n_bins)               -- solvers/nnls_solver.py:175
+ *
+ * `*_host` entry points take HOST pointers and run the whole
+ * upload / solve / download pipeline (chunked, copies overlapped with the
+ * kernels on separate streams); `*_device` entry points take DEVICE pointers
+ * and only enqueue work on the given CUDA stream.
+ *
+ * Return value: 0 on success, otherwise a CUDA error code (>0) or a
+ * PNB_E_* code (<0); pnb_last_error() gives the text.  There is no CPU
+ * fallback anywhere in this library.
+ */
+#ifndef PYNEAPPLE_B200_H
+#define PYNEAPPLE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PNB_ABI_VERSION 1
+
+/* model_id: parameter order is the reference's `_all_param_names`
+ * (models/monoexp.py:91-105, models/biexp.py:103-126, models/triexp.py:103-128) */
+enum {
+  PNB_MODEL_MONO = 0,        /* [S0, D]                     */
+  PNB_MODEL_BI_REDUCED = 1,  /* [f1, D1, D2]                */
+  PNB_MODEL_BI_FULL = 2,     /* [f1, D1, f2, D2]            */
+  PNB_MODEL_BI_S0 = 3,       /* [f1, D1, D2, S0]            */
+  PNB_MODEL_TRI_REDUCED = 4, /* [f1, D1, f2, D2, D3]        */
+  PNB_MODEL_TRI_FULL = 5,    /* [f1, D1, f2, D2, f3, D3]    */
+  PNB_MODEL_TRI_S0 = 6       /* [f1, D1, f2, D2, D3, S0]    */
+};
+/* t1_mode appends the parameter T1 (model_functions/multiexp.py:210-302) */
+enum { PNB_T1_NONE = 0, PNB_T1_STANDARD = 1, PNB_T1_STEAM = 2 };
+
+enum {
+  PNB_E_BADARG = -1,      /* inconsistent sizes / null pointers */
+  PNB_E_UNSUPPORTED = -2, /* model / option without a device implementation */
+  PNB_E_NODEVICE = -3     /* no CUDA device */
+};
+
+/* per-voxel status written by pnb_trf_fit_*: SciPy's least_squares status
+ * (0 max_nfev reached = failure, 1 gtol, 2 ftol, 3 xtol, 4 ftol and xtol), or
+ * the input error SciPy would raise for that voxel.  success <=> status > 0;
+ * on failure params = p0 and cov = NaN (solvers/curvefit.py:308-317). */
+enum {
+  PNB_ST_BAD_BOUNDS = -1,  /* "Each lower bound must be strictly less than each upper bound." */
+  PNB_ST_INFEASIBLE = -2,  /* "Initial guess is outside of provided bounds" */
+  PNB_ST_NONFINITE_Y = -3, /* "array must not contain infs or NaNs" */
+  PNB_ST_NONFINITE_F0 = -4 /* "Residuals are not finite in the initial point." */
+};
+
+/*
+ * Bounded non-linear least squares for n_vox voxels.
+ * Replaces CurveFitSolver._fit_data / _fit_single_pixel
+ * (solvers/curvefit.py:171-317), i.e. one scipy.optimize.curve_fit(
+ * method="trf", maxfev=max_nfev, ftol=ftol) call per voxel.
+ */
+typedef struct pnb_trf_problem {
+  int32_t model_id;          /* PNB_MODEL_*                                   */
+  int32_t t1_mode;           /* PNB_T1_*                                      */
+  double repetition_time;    /* TR, used when t1_mode != 0                    */
+  double mixing_time;        /* TM, used when t1_mode == PNB_T1_STEAM         */
+  int32_t n_b;               /* number of measurements (b-values)             */
+  int32_t n_params;          /* number of model parameters incl. fixed ones   */
+  int64_t n_vox;
+  const double *xdata;       /* (n_b)                                          */
+  const double *ydata;       /* (n_vox, n_b)                                   */
+  const double *p0;          /* (n_params) or (n_params, n_vox)                */
+  const double *lb;          /* like p0                                        */
+  const double *ub;
+  int32_t p0_per_voxel;      /* 0: one vector for all voxels, 1: per voxel     */
+  int32_t bounds_per_voxel;
+  uint32_t frozen_mask;      /* bit j: parameter j is fixed at p0[j] (per voxel
+                                when p0_per_voxel) -- model.fixed_params and
+                                pixel_fixed_params of curvefit.py:274-288      */
+  int32_t max_nfev;          /* CurveFitSolver.max_iter                        */
+  double ftol;               /* CurveFitSolver.tol                             */
+  double xtol;               /* SciPy default 1e-8                             */
+  double gtol;               /* SciPy default 1e-8                             */
+  int32_t jac_mode;          /* 0 analytic, 1 SciPy '2-point' finite differences */
+  int32_t x_scale_jac;       /* 1: x_scale='jac'                               */
+  double x_scale[8];         /* per parameter, 1.0 = SciPy default             */
+  /* outputs */
+  double *params;            /* (n_params, n_vox); fixed rows repeat the fixed value */
+  double *cov;               /* (n_vox, n_free, n_free) or NULL                */
+  int32_t *status;           /* (n_vox)                                        */
+  int32_t *nfev;             /* (n_vox) residual evaluations, SciPy's count     */
+  int32_t *njev;             /* (n_vox) or NULL                                */
+  double *cost;              /* (n_vox) 0.5 * ||f||^2 at the solution, or NULL */
+} pnb_trf_problem;
+
+int pnb_trf_fit_device(const pnb_trf_problem *prob, void *cuda_stream);
+int pnb_trf_fit_host(const pnb_trf_problem *prob, int device, int64_t chunk_vox);
+
+/* housekeeping */
+int pnb_abi_version(void);
+/* sizeof(struct pnb_trf_problem) as compiled, for binding self-checks */
+int pnb_sizeof_trf_problem(void);
+const char *pnb_last_error(void);
+int pnb_device_count(void);
+/* number of kernels this library has launched since load (bench.py: gpu_launches) */
+int64_t pnb_launch_count(void);
+/* pinned host memory for callers that want full-speed transfers */
+int pnb_host_alloc(void **ptr, int64_t bytes);
+int pnb_host_free(void *ptr);
+/* FP64 FMA micro-benchmark: achieved TFLOP/s of dependent-chain-free DFMA (roofline denominator) */
+int pnb_measure_fp64_peak(int device, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYNEAPPLE_B200_H */

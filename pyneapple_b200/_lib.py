@@ -1,0 +1,166 @@
+"""ctypes binding of ``csrc/libpnb200.so`` (the C ABI in ``include/pyneapple_b200.h``).
+
+The library is built in-tree by ``__graft_entry__.build()`` / ``make -C
+pyneapple_b200/csrc``.  There is no fallback: if the shared object or a CUDA
+device is missing every compute entry point raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+SO_PATH = os.path.join(CSRC, "libpnb200.so")
+HEADER = os.path.join(os.path.dirname(_HERE), "include", "pyneapple_b200.h")
+
+_lib = None
+
+
+class EngineError(RuntimeError):
+    """The CUDA engine could not run (library / device missing, CUDA error)."""
+
+
+class TrfProblem(C.Structure):
+    """Mirror of ``struct pnb_trf_problem``."""
+
+    _fields_ = [
+        ("model_id", C.c_int32),
+        ("t1_mode", C.c_int32),
+        ("repetition_time", C.c_double),
+        ("mixing_time", C.c_double),
+        ("n_b", C.c_int32),
+        ("n_params", C.c_int32),
+        ("n_vox", C.c_int64),
+        ("xdata", C.c_void_p),
+        ("ydata", C.c_void_p),
+        ("p0", C.c_void_p),
+        ("lb", C.c_void_p),
+        ("ub", C.c_void_p),
+        ("p0_per_voxel", C.c_int32),
+        ("bounds_per_voxel", C.c_int32),
+        ("frozen_mask", C.c_uint32),
+        ("max_nfev", C.c_int32),
+        ("ftol", C.c_double),
+        ("xtol", C.c_double),
+        ("gtol", C.c_double),
+        ("jac_mode", C.c_int32),
+        ("x_scale_jac", C.c_int32),
+        ("x_scale", C.c_double * 8),
+        ("params", C.c_void_p),
+        ("cov", C.c_void_p),
+        ("status", C.c_void_p),
+        ("nfev", C.c_void_p),
+        ("njev", C.c_void_p),
+        ("cost", C.c_void_p),
+    ]
+
+
+def build(verbose: bool = False, t1: bool = True) -> str:
+    """Compile ``libpnb200.so`` for sm_100a with nvcc (works without a GPU)."""
+    cmd = ["make", "-C", CSRC, "-j", str(min(16, os.cpu_count() or 4))]
+    if t1:
+        cmd.append("T1MODES=0 1 2")
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if verbose or res.returncode != 0:
+        print(res.stdout)
+    if res.returncode != 0:
+        raise EngineError("building libpnb200.so failed")
+    return SO_PATH
+
+
+def load():
+    """Load the shared library (no device needed for this)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise EngineError(
+            f"{SO_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C pyneapple_b200/csrc`. pyneapple_b200 has no CPU fallback."
+        )
+    lib = C.CDLL(SO_PATH)
+    lib.pnb_abi_version.restype = C.c_int
+    lib.pnb_last_error.restype = C.c_char_p
+    lib.pnb_device_count.restype = C.c_int
+    lib.pnb_launch_count.restype = C.c_int64
+    lib.pnb_trf_fit_device.argtypes = [C.POINTER(TrfProblem), C.c_void_p]
+    lib.pnb_trf_fit_device.restype = C.c_int
+    lib.pnb_trf_fit_host.argtypes = [C.POINTER(TrfProblem), C.c_int, C.c_int64]
+    lib.pnb_trf_fit_host.restype = C.c_int
+    lib.pnb_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_int64]
+    lib.pnb_host_free.argtypes = [C.c_void_p]
+    lib.pnb_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    _lib = lib
+    return lib
+
+
+def require_device() -> None:
+    lib = load()
+    if lib.pnb_device_count() < 1:
+        raise EngineError(
+            "no CUDA device visible: pyneapple_b200 runs on B200 GPUs only and has no CPU fallback"
+        )
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().pnb_last_error().decode("utf-8", "replace")
+        if rc == -1:
+            raise ValueError(f"{what}: {msg}")
+        if rc == -2:
+            raise NotImplementedError(f"{what}: {msg}")
+        raise EngineError(f"{what} failed (code {rc}): {msg}")
+
+
+def launch_count() -> int:
+    return int(load().pnb_launch_count())
+
+
+def exported_symbols() -> list[str]:
+    """Function names declared in ``include/pyneapple_b200.h``."""
+    import re
+
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pnb_[a-z0-9_]+)\s*\(", text)))
+
+
+class PinnedArray:
+    """A numpy array backed by page-locked host memory (full-speed H2D / D2H)."""
+
+    def __init__(self, shape, dtype=np.float64):
+        self.shape = tuple(int(s) for s in np.atleast_1d(shape))
+        self.dtype = np.dtype(dtype)
+        nbytes = max(1, int(np.prod(self.shape)) * self.dtype.itemsize)
+        ptr = C.c_void_p()
+        check(load().pnb_host_alloc(C.byref(ptr), nbytes), "pnb_host_alloc")
+        self._ptr = ptr
+        buf = (C.c_char * nbytes).from_address(ptr.value)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def free(self):
+        if self._ptr is not None:
+            self.array = None
+            load().pnb_host_free(self._ptr)
+            self._ptr = None
+
+    def __del__(self):  # pragma: no cover - best effort
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype=np.float64) -> PinnedArray:
+    return PinnedArray(shape, dtype)
+
+
+def measure_fp64_peak(device: int = 0) -> float:
+    out = C.c_double()
+    check(load().pnb_measure_fp64_peak(device, C.byref(out)), "pnb_measure_fp64_peak")
+    return float(out.value)

@@ -1,0 +1,356 @@
+// C ABI of libpnb200.so (see include/pyneapple_b200.h).
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/pyneapple_b200.h"
+#include "pnb_trf_kernel.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+int cuda_fail(cudaError_t e, const char *what) {
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return (int)e;
+}
+#define PNB_CUDA(call)                                  \
+  do {                                                  \
+    cudaError_t e_ = (call);                            \
+    if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
+  } while (0)
+
+using LaunchFn = cudaError_t (*)(const pnb::TrfDeviceArgs *, cudaStream_t);
+
+}  // namespace
+
+#define PNB_DECL(id, t1) extern "C" cudaError_t pnb_trf_launch_##id##_##t1(const pnb::TrfDeviceArgs *, cudaStream_t);
+PNB_DECL(0, 0) PNB_DECL(1, 0) PNB_DECL(2, 0) PNB_DECL(3, 0) PNB_DECL(4, 0) PNB_DECL(5, 0) PNB_DECL(6, 0)
+#ifdef PNB_WITH_T1
+PNB_DECL(0, 1) PNB_DECL(1, 1) PNB_DECL(2, 1) PNB_DECL(3, 1) PNB_DECL(4, 1) PNB_DECL(5, 1) PNB_DECL(6, 1)
+PNB_DECL(0, 2) PNB_DECL(1, 2) PNB_DECL(2, 2) PNB_DECL(3, 2) PNB_DECL(4, 2) PNB_DECL(5, 2) PNB_DECL(6, 2)
+#endif
+
+namespace {
+
+LaunchFn trf_launcher(int model_id, int t1_mode) {
+  static const LaunchFn table[3][7] = {
+      {pnb_trf_launch_0_0, pnb_trf_launch_1_0, pnb_trf_launch_2_0, pnb_trf_launch_3_0,
+       pnb_trf_launch_4_0, pnb_trf_launch_5_0, pnb_trf_launch_6_0},
+#ifdef PNB_WITH_T1
+      {pnb_trf_launch_0_1, pnb_trf_launch_1_1, pnb_trf_launch_2_1, pnb_trf_launch_3_1,
+       pnb_trf_launch_4_1, pnb_trf_launch_5_1, pnb_trf_launch_6_1},
+      {pnb_trf_launch_0_2, pnb_trf_launch_1_2, pnb_trf_launch_2_2, pnb_trf_launch_3_2,
+       pnb_trf_launch_4_2, pnb_trf_launch_5_2, pnb_trf_launch_6_2},
+#else
+      {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr},
+      {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr},
+#endif
+  };
+  if (model_id < 0 || model_id > 6 || t1_mode < 0 || t1_mode > 2) return nullptr;
+  return table[t1_mode][model_id];
+}
+
+int model_n_params(int model_id, int t1_mode) {
+  static const int base[7] = {2, 3, 4, 4, 5, 6, 6};
+  return base[model_id] + (t1_mode ? 1 : 0);
+}
+
+int check_problem(const pnb_trf_problem *p) {
+  if (!p) return fail(PNB_E_BADARG, "null problem");
+  if (p->model_id < 0 || p->model_id > 6 || p->t1_mode < 0 || p->t1_mode > 2)
+    return fail(PNB_E_UNSUPPORTED, "unknown model_id / t1_mode");
+  if (!trf_launcher(p->model_id, p->t1_mode))
+    return fail(PNB_E_UNSUPPORTED, "this build has no kernel for the requested model / T1 mode");
+  if (p->n_params != model_n_params(p->model_id, p->t1_mode))
+    return fail(PNB_E_BADARG, "n_params does not match the model");
+  if (p->n_b < 1 || p->n_b > 512) return fail(PNB_E_BADARG, "n_b must be in [1, 512]");
+  if (p->n_vox < 0) return fail(PNB_E_BADARG, "n_vox < 0");
+  if (p->max_nfev < 1) return fail(PNB_E_BADARG, "max_nfev must be positive");
+  if (p->jac_mode != 0 && p->jac_mode != 1) return fail(PNB_E_BADARG, "jac_mode must be 0 or 1");
+  if (p->n_vox > 0 &&
+      (!p->xdata || !p->ydata || !p->p0 || !p->lb || !p->ub || !p->params || !p->status || !p->nfev))
+    return fail(PNB_E_BADARG, "null array pointer");
+  const unsigned all = (1u << p->n_params) - 1u;
+  if ((p->frozen_mask & all) == all) return fail(PNB_E_BADARG, "all parameters are fixed");
+  return 0;
+}
+
+pnb::TrfOptions make_options(const pnb_trf_problem *p) {
+  pnb::TrfOptions o;
+  o.ftol = p->ftol; o.xtol = p->xtol; o.gtol = p->gtol;
+  o.max_nfev = p->max_nfev; o.jac_mode = p->jac_mode; o.x_scale_jac = p->x_scale_jac;
+  o.frozen = p->frozen_mask & ((1u << p->n_params) - 1u);
+  for (int i = 0; i < 8; i++) o.x_scale[i] = (p->x_scale[i] > 0.0) ? p->x_scale[i] : 1.0;
+  o.tr = p->repetition_time; o.tm = p->mixing_time;
+  return o;
+}
+
+int popcount(unsigned v) { int c = 0; while (v) { c += v & 1u; v >>= 1; } return c; }
+
+// A small ring of work counters per device (one per in-flight launch).
+struct CounterRing {
+  unsigned long long *buf = nullptr;
+  int next = 0;
+  static constexpr int kSlots = 256;
+};
+std::mutex g_mu;
+CounterRing g_rings[16];
+
+int next_counter(unsigned long long **out) {
+  int dev = 0;
+  PNB_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(g_mu);
+  CounterRing &r = g_rings[dev & 15];
+  if (!r.buf) PNB_CUDA(cudaMalloc(&r.buf, sizeof(unsigned long long) * CounterRing::kSlots));
+  *out = r.buf + r.next;
+  r.next = (r.next + 1) % CounterRing::kSlots;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int pnb_abi_version(void) { return PNB_ABI_VERSION; }
+extern "C" int pnb_sizeof_trf_problem(void) { return (int)sizeof(pnb_trf_problem); }
+extern "C" const char *pnb_last_error(void) { return g_err.c_str(); }
+extern "C" int64_t pnb_launch_count(void) { return g_launches.load(); }
+
+extern "C" int pnb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+extern "C" int pnb_host_alloc(void **ptr, int64_t bytes) {
+  PNB_CUDA(cudaHostAlloc(ptr, (size_t)bytes, cudaHostAllocDefault));
+  return 0;
+}
+extern "C" int pnb_host_free(void *ptr) {
+  PNB_CUDA(cudaFreeHost(ptr));
+  return 0;
+}
+
+extern "C" int pnb_trf_fit_device(const pnb_trf_problem *p, void *cuda_stream) {
+  if (int rc = check_problem(p)) return rc;
+  if (p->n_vox == 0) return 0;
+  cudaStream_t stream = (cudaStream_t)cuda_stream;
+  pnb::TrfDeviceArgs a;
+  a.n_b = p->n_b; a.n_vox = p->n_vox; a.b = p->xdata; a.y = p->ydata;
+  a.p0 = p->p0; a.lb = p->lb; a.ub = p->ub;
+  a.p0_row_stride = p->p0_per_voxel ? p->n_vox : 1;
+  a.p0_vox_stride = p->p0_per_voxel ? 1 : 0;
+  a.bd_row_stride = p->bounds_per_voxel ? p->n_vox : 1;
+  a.bd_vox_stride = p->bounds_per_voxel ? 1 : 0;
+  a.opt = make_options(p);
+  a.params = p->params; a.cov = p->cov; a.status = p->status; a.nfev = p->nfev;
+  a.njev = p->njev; a.cost = p->cost;
+  if (int rc = next_counter(&a.counter)) return rc;
+  cudaError_t e = trf_launcher(p->model_id, p->t1_mode)(&a, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "trf kernel launch");
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+// ---------------------------------------------------------------------
+// host pipeline: chunks of voxels flow H2D -> kernel -> D2H on kSlots streams
+// ---------------------------------------------------------------------
+namespace {
+
+struct Slot {
+  cudaStream_t stream = nullptr;
+  double *y = nullptr, *p0 = nullptr, *lb = nullptr, *ub = nullptr;
+  double *params = nullptr, *cov = nullptr, *cost = nullptr;
+  int *status = nullptr, *nfev = nullptr, *njev = nullptr;
+  unsigned long long *counter = nullptr;
+  size_t cap_y = 0, cap_p = 0, cap_cov = 0, cap_v = 0;
+};
+
+struct Pipeline {
+  static constexpr int kSlots = 3;
+  Slot slots[kSlots];
+  double *b = nullptr, *vec = nullptr;  // xdata, broadcast p0|lb|ub
+  size_t cap_b = 0;
+  bool init = false;
+};
+Pipeline g_pipes[16];
+std::mutex g_pipe_mu;
+
+template <class T> int grow(T **ptr, size_t *cap, size_t need) {
+  if (need <= *cap) return 0;
+  if (*ptr) PNB_CUDA(cudaFree(*ptr));
+  *ptr = nullptr; *cap = 0;
+  PNB_CUDA(cudaMalloc(ptr, need * sizeof(T)));
+  *cap = need;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int pnb_trf_fit_host(const pnb_trf_problem *p, int device, int64_t chunk_vox) {
+  if (int rc = check_problem(p)) return rc;
+  if (p->n_vox == 0) return 0;
+  if (pnb_device_count() <= device || device < 0) return fail(PNB_E_NODEVICE, "no such CUDA device");
+  PNB_CUDA(cudaSetDevice(device));
+  std::lock_guard<std::mutex> lk(g_pipe_mu);
+  Pipeline &P = g_pipes[device & 15];
+  const int np = p->n_params, nb = p->n_b;
+  const int nfree = np - popcount(p->frozen_mask & ((1u << np) - 1u));
+  if (chunk_vox <= 0) chunk_vox = 1 << 18;
+  if (chunk_vox > p->n_vox) chunk_vox = p->n_vox;
+  const size_t C = (size_t)chunk_vox;
+
+  if (!P.init) {
+    for (auto &s : P.slots) {
+      PNB_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+      PNB_CUDA(cudaMalloc(&s.counter, sizeof(unsigned long long)));
+    }
+    PNB_CUDA(cudaMalloc(&P.vec, sizeof(double) * 3 * 8));
+    P.init = true;
+  }
+  if ((size_t)nb > P.cap_b) {
+    if (P.b) PNB_CUDA(cudaFree(P.b));
+    PNB_CUDA(cudaMalloc(&P.b, sizeof(double) * nb));
+    P.cap_b = nb;
+  }
+  for (auto &s : P.slots) {
+    if (int rc = grow(&s.y, &s.cap_y, C * nb)) return rc;
+    size_t need_p = C * np;
+    if (need_p > s.cap_p) {
+      for (double **q : {&s.p0, &s.lb, &s.ub, &s.params}) {
+        if (*q) PNB_CUDA(cudaFree(*q));
+        PNB_CUDA(cudaMalloc(q, need_p * sizeof(double)));
+      }
+      s.cap_p = need_p;
+    }
+    if (p->cov)
+      if (int rc = grow(&s.cov, &s.cap_cov, C * nfree * nfree)) return rc;
+    if (C > s.cap_v) {
+      if (s.cost) PNB_CUDA(cudaFree(s.cost));
+      if (s.status) PNB_CUDA(cudaFree(s.status));
+      if (s.nfev) PNB_CUDA(cudaFree(s.nfev));
+      if (s.njev) PNB_CUDA(cudaFree(s.njev));
+      PNB_CUDA(cudaMalloc(&s.cost, C * sizeof(double)));
+      PNB_CUDA(cudaMalloc(&s.status, C * sizeof(int)));
+      PNB_CUDA(cudaMalloc(&s.nfev, C * sizeof(int)));
+      PNB_CUDA(cudaMalloc(&s.njev, C * sizeof(int)));
+      s.cap_v = C;
+    }
+  }
+  // shared small inputs (synchronous, tiny)
+  cudaStream_t s0 = P.slots[0].stream;
+  PNB_CUDA(cudaMemcpyAsync(P.b, p->xdata, sizeof(double) * nb, cudaMemcpyHostToDevice, s0));
+  if (!p->p0_per_voxel)
+    PNB_CUDA(cudaMemcpyAsync(P.vec, p->p0, sizeof(double) * np, cudaMemcpyHostToDevice, s0));
+  if (!p->bounds_per_voxel) {
+    PNB_CUDA(cudaMemcpyAsync(P.vec + 8, p->lb, sizeof(double) * np, cudaMemcpyHostToDevice, s0));
+    PNB_CUDA(cudaMemcpyAsync(P.vec + 16, p->ub, sizeof(double) * np, cudaMemcpyHostToDevice, s0));
+  }
+  PNB_CUDA(cudaStreamSynchronize(s0));
+
+  const pnb::TrfOptions opt = make_options(p);
+  LaunchFn launch = trf_launcher(p->model_id, p->t1_mode);
+  const size_t NV = (size_t)p->n_vox;
+  int slot = 0;
+  for (size_t start = 0; start < NV; start += C, slot = (slot + 1) % Pipeline::kSlots) {
+    Slot &s = P.slots[slot];
+    const size_t n = (NV - start < C) ? NV - start : C;
+    // the slot's previous chunk has been fully enqueued on the same stream, so
+    // stream order already protects the buffers; no host sync needed here.
+    PNB_CUDA(cudaMemcpyAsync(s.y, p->ydata + start * nb, sizeof(double) * n * nb,
+                             cudaMemcpyHostToDevice, s.stream));
+    if (p->p0_per_voxel)
+      PNB_CUDA(cudaMemcpy2DAsync(s.p0, n * sizeof(double), p->p0 + start, NV * sizeof(double),
+                                 n * sizeof(double), np, cudaMemcpyHostToDevice, s.stream));
+    if (p->bounds_per_voxel) {
+      PNB_CUDA(cudaMemcpy2DAsync(s.lb, n * sizeof(double), p->lb + start, NV * sizeof(double),
+                                 n * sizeof(double), np, cudaMemcpyHostToDevice, s.stream));
+      PNB_CUDA(cudaMemcpy2DAsync(s.ub, n * sizeof(double), p->ub + start, NV * sizeof(double),
+                                 n * sizeof(double), np, cudaMemcpyHostToDevice, s.stream));
+    }
+    pnb::TrfDeviceArgs a;
+    a.n_b = nb; a.n_vox = (long long)n; a.b = P.b; a.y = s.y;
+    a.p0 = p->p0_per_voxel ? s.p0 : P.vec;
+    a.lb = p->bounds_per_voxel ? s.lb : P.vec + 8;
+    a.ub = p->bounds_per_voxel ? s.ub : P.vec + 16;
+    a.p0_row_stride = p->p0_per_voxel ? (long long)n : 1;
+    a.p0_vox_stride = p->p0_per_voxel ? 1 : 0;
+    a.bd_row_stride = p->bounds_per_voxel ? (long long)n : 1;
+    a.bd_vox_stride = p->bounds_per_voxel ? 1 : 0;
+    a.opt = opt;
+    a.params = s.params; a.cov = p->cov ? s.cov : nullptr; a.status = s.status; a.nfev = s.nfev;
+    a.njev = p->njev ? s.njev : nullptr; a.cost = p->cost ? s.cost : nullptr;
+    a.counter = s.counter;
+    cudaError_t e = launch(&a, s.stream);
+    if (e != cudaSuccess) return cuda_fail(e, "trf kernel launch");
+    g_launches.fetch_add(1);
+    PNB_CUDA(cudaMemcpy2DAsync(p->params + start, NV * sizeof(double), s.params, n * sizeof(double),
+                               n * sizeof(double), np, cudaMemcpyDeviceToHost, s.stream));
+    if (p->cov)
+      PNB_CUDA(cudaMemcpyAsync(p->cov + start * nfree * nfree, s.cov,
+                               sizeof(double) * n * nfree * nfree, cudaMemcpyDeviceToHost, s.stream));
+    PNB_CUDA(cudaMemcpyAsync(p->status + start, s.status, sizeof(int) * n, cudaMemcpyDeviceToHost, s.stream));
+    PNB_CUDA(cudaMemcpyAsync(p->nfev + start, s.nfev, sizeof(int) * n, cudaMemcpyDeviceToHost, s.stream));
+    if (p->njev)
+      PNB_CUDA(cudaMemcpyAsync(p->njev + start, s.njev, sizeof(int) * n, cudaMemcpyDeviceToHost, s.stream));
+    if (p->cost)
+      PNB_CUDA(cudaMemcpyAsync(p->cost + start, s.cost, sizeof(double) * n, cudaMemcpyDeviceToHost, s.stream));
+  }
+  for (auto &s : P.slots) PNB_CUDA(cudaStreamSynchronize(s.stream));
+  return 0;
+}
+
+// ---------------------------------------------------------------------
+// FP64 FMA peak (roofline denominator; MEASURED_PEAKS.json has no FP64 figure)
+// ---------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, double seed) {
+  double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
+         a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 0.999999, c = 1e-9;
+  for (int i = 0; i < iters; i++) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+}  // namespace
+
+extern "C" int pnb_measure_fp64_peak(int device, double *tflops) {
+  if (!tflops) return fail(PNB_E_BADARG, "null output");
+  if (pnb_device_count() <= device || device < 0) return fail(PNB_E_NODEVICE, "no such CUDA device");
+  PNB_CUDA(cudaSetDevice(device));
+  int sms = 0;
+  PNB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  const int blocks = sms * 8, threads = 256, iters = 1 << 15;
+  double *out = nullptr;
+  PNB_CUDA(cudaMalloc(&out, sizeof(double) * blocks * threads));
+  cudaEvent_t e0, e1;
+  PNB_CUDA(cudaEventCreate(&e0));
+  PNB_CUDA(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 6; rep++) {
+    PNB_CUDA(cudaEventRecord(e0));
+    dfma_peak_kernel<<<blocks, threads>>>(out, iters, 1.0 + rep);
+    PNB_CUDA(cudaEventRecord(e1));
+    PNB_CUDA(cudaEventSynchronize(e1));
+    g_launches.fetch_add(1);
+    float ms = 0;
+    PNB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
+    const double tf = flops / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+  *tflops = best;
+  return 0;
+}

@@ -1,0 +1,192 @@
+"""Thin Python layer over the C ABI: array checking, pointer passing, nothing numeric.
+
+Two data paths, chosen by the type of ``ydata``:
+
+* ``numpy.ndarray``  -> ``pnb_trf_fit_host``: host pointers, the library runs
+  the chunked upload / solve / download pipeline; outputs are numpy arrays.
+* ``torch.Tensor`` on a CUDA device -> ``pnb_trf_fit_device``: device pointers,
+  work is enqueued on torch's current stream; outputs are CUDA tensors (this
+  is what the IDEAL / segmented drivers and the multi-GPU path use, so that
+  nothing round-trips through the host between levels / steps).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .models import ModelDesc
+
+STATUS_MESSAGES = {
+    -4: "Residuals are not finite in the initial point.",
+    -3: "array must not contain infs or NaNs",
+    -2: "Initial guess is outside of provided bounds",
+    -1: "Each lower bound must be strictly less than each upper bound.",
+    0: "Optimal parameters not found: The maximum number of function evaluations is exceeded.",
+    1: "`gtol` termination condition is satisfied.",
+    2: "`ftol` termination condition is satisfied.",
+    3: "`xtol` termination condition is satisfied.",
+    4: "Both `ftol` and `xtol` termination conditions are satisfied.",
+}
+
+JAC_ANALYTIC = 0
+JAC_TWO_POINT = 1
+
+
+def _is_torch_cuda(x) -> bool:
+    try:
+        import torch
+    except ImportError:  # pragma: no cover
+        return False
+    return isinstance(x, torch.Tensor) and x.is_cuda
+
+
+def _as_f64(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def frozen_mask(desc: ModelDesc, fixed_names) -> int:
+    mask = 0
+    for j, name in enumerate(desc.all_names):
+        if name in fixed_names:
+            mask |= 1 << j
+    return mask
+
+
+def trf_fit(
+    desc: ModelDesc,
+    xdata,
+    ydata,
+    p0,
+    lb,
+    ub,
+    frozen: int = 0,
+    *,
+    max_nfev: int = 250,
+    ftol: float = 1e-8,
+    xtol: float = 1e-8,
+    gtol: float = 1e-8,
+    jac_mode: int = JAC_ANALYTIC,
+    x_scale=None,
+    x_scale_jac: bool = False,
+    want_cov: bool = True,
+    device: int = 0,
+    chunk_vox: int = 0,
+    out: dict | None = None,
+):
+    """Fit all voxels.  ``p0``/``lb``/``ub``: ``(n_all,)`` or ``(n_all, n_vox)`` over
+    ``desc.all_names`` (frozen rows of ``p0`` carry the fixed values).
+
+    Returns ``dict(params (n_all, n_vox), cov (n_vox, n_free, n_free) | None,
+    status, nfev, njev, cost)``.
+    """
+    _lib.require_device()
+    lib = _lib.load()
+    n_all = desc.n_all
+    n_free = n_all - bin(frozen).count("1")
+    prob = _lib.TrfProblem()
+    prob.model_id = desc.model_id
+    prob.t1_mode = desc.t1_mode
+    prob.repetition_time = desc.repetition_time
+    prob.mixing_time = desc.mixing_time
+    prob.n_params = n_all
+    prob.frozen_mask = frozen
+    prob.max_nfev = int(max_nfev)
+    prob.ftol, prob.xtol, prob.gtol = float(ftol), float(xtol), float(gtol)
+    prob.jac_mode = int(jac_mode)
+    prob.x_scale_jac = int(bool(x_scale_jac))
+    xs = np.ones(8)
+    if x_scale is not None:
+        xs[:n_all] = np.broadcast_to(np.asarray(x_scale, float), (n_all,))
+    for i in range(8):
+        prob.x_scale[i] = xs[i]
+
+    if _is_torch_cuda(ydata):
+        return _trf_fit_device(lib, prob, desc, xdata, ydata, p0, lb, ub, n_free, want_cov)
+
+    y = _as_f64(ydata)
+    if y.ndim != 2:
+        raise ValueError(f"ydata must be (n_vox, n_b), got {y.shape}")
+    n_vox, n_b = y.shape
+    b = _as_f64(xdata)
+    if b.shape != (n_b,):
+        raise ValueError(f"xdata length {b.shape} does not match ydata {y.shape}")
+    p0 = _as_f64(p0)
+    lb = _as_f64(lb)
+    ub = _as_f64(ub)
+    for name, arr in (("p0", p0), ("lb", lb), ("ub", ub)):
+        if arr.shape not in ((n_all,), (n_all, n_vox)):
+            raise ValueError(f"{name} must have shape ({n_all},) or ({n_all}, {n_vox}), got {arr.shape}")
+    if lb.shape != ub.shape:
+        raise ValueError("lb and ub must have the same shape")
+    prob.n_b, prob.n_vox = n_b, n_vox
+    prob.p0_per_voxel = int(p0.ndim == 2)
+    prob.bounds_per_voxel = int(lb.ndim == 2)
+
+    o = out or {}
+    params = o.get("params")
+    if params is None:
+        params = np.empty((n_all, n_vox))
+    cov = o.get("cov") if want_cov else None
+    if want_cov and cov is None:
+        cov = np.empty((n_vox, n_free, n_free))
+    status = o.get("status") if o.get("status") is not None else np.empty(n_vox, np.int32)
+    nfev = o.get("nfev") if o.get("nfev") is not None else np.empty(n_vox, np.int32)
+    njev = o.get("njev") if o.get("njev") is not None else np.empty(n_vox, np.int32)
+    cost = o.get("cost") if o.get("cost") is not None else np.empty(n_vox)
+    keep = (b, y, p0, lb, ub, params, cov, status, nfev, njev, cost)
+    prob.xdata, prob.ydata = b.ctypes.data, y.ctypes.data
+    prob.p0, prob.lb, prob.ub = p0.ctypes.data, lb.ctypes.data, ub.ctypes.data
+    prob.params = params.ctypes.data
+    prob.cov = cov.ctypes.data if cov is not None else None
+    prob.status, prob.nfev = status.ctypes.data, nfev.ctypes.data
+    prob.njev, prob.cost = njev.ctypes.data, cost.ctypes.data
+    _lib.check(lib.pnb_trf_fit_host(C.byref(prob), int(device), int(chunk_vox)), "pnb_trf_fit_host")
+    del keep
+    return dict(params=params, cov=cov, status=status, nfev=nfev, njev=njev, cost=cost)
+
+
+def _trf_fit_device(lib, prob, desc, xdata, ydata, p0, lb, ub, n_free, want_cov):
+    import torch
+
+    dev = ydata.device
+    y = ydata.contiguous().to(torch.float64)
+    if y.ndim != 2:
+        raise ValueError(f"ydata must be (n_vox, n_b), got {tuple(y.shape)}")
+    n_vox, n_b = y.shape
+    n_all = desc.n_all
+
+    def dev_f64(a):
+        if isinstance(a, torch.Tensor):
+            return a.to(device=dev, dtype=torch.float64).contiguous()
+        return torch.as_tensor(np.ascontiguousarray(a, np.float64)).to(dev)
+
+    b = dev_f64(xdata)
+    p0, lb, ub = dev_f64(p0), dev_f64(lb), dev_f64(ub)
+    for name, arr in (("p0", p0), ("lb", lb), ("ub", ub)):
+        if tuple(arr.shape) not in ((n_all,), (n_all, n_vox)):
+            raise ValueError(f"{name} must have shape ({n_all},) or ({n_all}, {n_vox}), got {tuple(arr.shape)}")
+    prob.n_b, prob.n_vox = n_b, n_vox
+    prob.p0_per_voxel = int(p0.ndim == 2)
+    prob.bounds_per_voxel = int(lb.ndim == 2)
+    params = torch.empty((n_all, n_vox), dtype=torch.float64, device=dev)
+    cov = torch.empty((n_vox, n_free, n_free), dtype=torch.float64, device=dev) if want_cov else None
+    status = torch.empty(n_vox, dtype=torch.int32, device=dev)
+    nfev = torch.empty(n_vox, dtype=torch.int32, device=dev)
+    njev = torch.empty(n_vox, dtype=torch.int32, device=dev)
+    cost = torch.empty(n_vox, dtype=torch.float64, device=dev)
+    prob.xdata, prob.ydata = b.data_ptr(), y.data_ptr()
+    prob.p0, prob.lb, prob.ub = p0.data_ptr(), lb.data_ptr(), ub.data_ptr()
+    prob.params = params.data_ptr()
+    prob.cov = cov.data_ptr() if cov is not None else None
+    prob.status, prob.nfev = status.data_ptr(), nfev.data_ptr()
+    prob.njev, prob.cost = njev.data_ptr(), cost.data_ptr()
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(lib.pnb_trf_fit_device(C.byref(prob), C.c_void_p(stream)), "pnb_trf_fit_device")
+        # inputs must outlive the enqueued kernel
+        for t in (b, y, p0, lb, ub):
+            t.record_stream(torch.cuda.current_stream(dev))
+    return dict(params=params, cov=cov, status=status, nfev=nfev, njev=njev, cost=cost)

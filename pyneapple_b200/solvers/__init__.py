@@ -1,0 +1,20 @@
+"""B200 solvers with the reference's names and registry (solvers/__init__.py:8-35)."""
+
+from __future__ import annotations
+
+from .base import BaseSolver, PixelResults, _PixelFitResult
+from .curvefit import CurveFitSolver
+
+_REGISTRY: dict[str, type] = {
+    "curvefit": CurveFitSolver,
+}
+
+
+def get_solver(name: str, **kwargs) -> BaseSolver:
+    key = name.lower()
+    if key not in _REGISTRY:
+        raise ValueError(f"Unknown solver: {name!r}. Available: {sorted(_REGISTRY)}")
+    return _REGISTRY[key](**kwargs)
+
+
+__all__ = ["BaseSolver", "CurveFitSolver", "PixelResults", "get_solver"]

@@ -1,0 +1,267 @@
+"""B200 drop-in for the reference's ``CurveFitSolver`` (solvers/curvefit.py:16-392).
+
+Same constructor, same ``fit`` signature, same result attributes and error
+behaviour; the per-voxel ``scipy.optimize.curve_fit`` loop / joblib pool is
+replaced by one batched CUDA solve (``pnb_trf_fit_*``).
+"""
+
+from __future__ import annotations
+
+import logging
+from typing import Any
+
+import numpy as np
+
+from .. import engine
+from ..models import describe_model
+from .. import validation as V
+from .base import BaseSolver, PixelResults
+
+log = logging.getLogger("pyneapple_b200")
+
+# extra keyword arguments the reference would splat into curve_fit /
+# least_squares (curvefit.py:70-73, 305) and that the device solver honours
+_HONOURED_KWARGS = {"xtol", "gtol", "x_scale"}
+# accepted for TOML compatibility, meaningless on the GPU
+_IGNORED_KWARGS = {"n_pools"}
+
+
+class CurveFitSolver(BaseSolver):
+    """Bounded non-linear least squares for every voxel on the GPU.
+
+    Args mirror ``CurveFitSolver.__init__`` (curvefit.py:36-89).  Additional
+    keyword ``jac``:
+
+    * ``"reference"`` (default) — do what the reference does: SciPy's 2-point
+      finite-difference Jacobian when no parameter is fixed, the analytic
+      Jacobian when any parameter is fixed (curvefit.py:274-293);
+    * ``"analytic"`` — always the analytic Jacobian (faster, differs from the
+      reference by ~1e-6 relative);
+    * ``"2-point"`` — always finite differences.
+    """
+
+    def __init__(
+        self,
+        model: Any,
+        max_iter: int,
+        tol: float,
+        p0: dict[str, float],
+        bounds: dict[str, tuple[float, float]],
+        verbose: bool = False,
+        method: str = "trf",
+        multi_threading: bool = False,
+        use_jacobian: bool = True,
+        **solver_kwargs,
+    ):
+        super().__init__(model=model, max_iter=max_iter, tol=tol, verbose=verbose)
+        self.method = method
+        self.multi_threading = multi_threading
+        self.use_jacobian = use_jacobian and hasattr(model, "jacobian")
+        self.n_pools = solver_kwargs.pop("n_pools", None)
+        self.jac = solver_kwargs.pop("jac", "reference")
+        self.device = solver_kwargs.pop("device", 0)
+        self.chunk_vox = solver_kwargs.pop("chunk_vox", 0)
+        self.want_cov = solver_kwargs.pop("want_cov", True)
+        if self.jac not in ("reference", "analytic", "2-point"):
+            raise ValueError("jac must be 'reference', 'analytic' or '2-point'")
+        unknown = set(solver_kwargs) - _HONOURED_KWARGS - _IGNORED_KWARGS
+        if unknown:
+            raise NotImplementedError(
+                f"curve_fit option(s) {sorted(unknown)} have no B200 implementation "
+                f"(honoured: {sorted(_HONOURED_KWARGS)})"
+            )
+        self.solver_kwargs = solver_kwargs
+        self._desc = describe_model(model)  # raises NotImplementedError for unknown models
+
+        names = self.model.param_names
+        if isinstance(p0[names[0]], (int, float, np.ndarray)):
+            V.validate_parameter_names(p0, names)
+            self.p0 = p0
+        else:
+            raise ValueError(
+                "p0 must be a dict with parameter names as keys and initial values as values."
+            )
+        if isinstance(bounds[names[0]], tuple):
+            V.validate_parameter_names(bounds, names)
+            self.bounds = bounds
+        else:
+            raise ValueError(
+                "bounds must be a dict with parameter names as keys and (lower, upper) tuples as values."
+            )
+        self.status_ = None
+        self.nfev_ = None
+        self.cost_ = None
+
+    # ------------------------------------------------------------------
+    def fit(self, xdata, ydata, p0=None, bounds=None, pixel_fixed_params=None, **fit_kwargs):
+        """Fit all voxels (curvefit.py:91-159).  Unknown keyword arguments are
+        swallowed like the reference does (``fixed_param_maps=None`` arrives
+        here from ``run_pipeline`` through ``IDEALFitter.fit``)."""
+        self._reset_state()
+        if self.method != "trf":
+            raise NotImplementedError(
+                f"method={self.method!r}: only SciPy's 'trf' has a B200 implementation"
+            )
+        xdata = np.asarray(xdata)
+        on_device = engine._is_torch_cuda(ydata)
+        if not on_device:
+            ydata = np.asarray(ydata)
+        V.validate_data_shapes(xdata, ydata)
+        n_pixels = ydata.shape[0] if ydata.ndim > 1 else 1
+        if ydata.ndim == 1:
+            ydata = ydata[None, :]
+        p0_m, lb_m, ub_m = self._validate_p0_and_bounds(p0, bounds, n_pixels)
+        res, free_names = self._solve(xdata, ydata, p0_m, lb_m, ub_m, pixel_fixed_params, n_pixels)
+        if on_device:
+            res = {k: (v.cpu().numpy() if v is not None else None) for k, v in res.items()}
+        self._store(res, free_names, n_pixels)
+        return self
+
+    # ------------------------------------------------------------------
+    def _solve(self, xdata, ydata, p0_m, lb_m, ub_m, pixel_fixed_params, n_pixels):
+        """Assemble full-parameter arrays and call the engine.
+
+        ``p0_m`` / ``lb_m`` / ``ub_m`` are ``(n_model,)`` or ``(n_model,
+        n_pixels)`` over ``model.param_names``.
+        """
+        desc = self._desc
+        model_names = list(self.model.param_names)
+        all_names = list(desc.all_names)
+        pix_fixed = {k: v for k, v in (pixel_fixed_params or {}).items() if k in all_names}
+        fixed_names = set(desc.fixed) | set(pix_fixed)
+        frozen = engine.frozen_mask(desc, fixed_names)
+        free_names = [n for n in model_names if n not in pix_fixed]
+
+        per_voxel_p0 = p0_m.ndim == 2 or bool(pix_fixed)
+        per_voxel_bd = lb_m.ndim == 2
+
+        def full(src, per_voxel, filler, is_p0):
+            rows = []
+            for name in all_names:
+                if name in desc.fixed:
+                    v = float(desc.fixed[name]) if is_p0 else filler
+                elif name in pix_fixed:
+                    v = pix_fixed[name] if is_p0 else filler
+                else:
+                    v = src[model_names.index(name)]
+                rows.append(v)
+            if not per_voxel:
+                return np.array([float(r) for r in rows])
+            out = np.empty((len(all_names), n_pixels))
+            for j, r in enumerate(rows):
+                r = np.asarray(r, dtype=float)
+                if r.ndim == 1 and r.shape[0] != n_pixels:
+                    raise ValueError(
+                        f"per-pixel values for '{all_names[j]}' have length {r.shape[0]}, expected {n_pixels}"
+                    )
+                out[j] = r
+            return out
+
+        P0 = full(p0_m, per_voxel_p0, 0.0, True)
+        LB = full(lb_m, per_voxel_bd, -np.inf, False)
+        UB = full(ub_m, per_voxel_bd, np.inf, False)
+
+        if self.jac == "reference":
+            jac_mode = engine.JAC_ANALYTIC if fixed_names else engine.JAC_TWO_POINT
+        else:
+            jac_mode = engine.JAC_ANALYTIC if self.jac == "analytic" else engine.JAC_TWO_POINT
+        x_scale = self.solver_kwargs.get("x_scale", 1.0)
+        x_scale_jac = isinstance(x_scale, str)
+        if x_scale_jac and x_scale != "jac":
+            raise ValueError("`x_scale` must be 'jac' or array_like with positive numbers.")
+        xs_full = None
+        if not x_scale_jac:
+            xs = np.broadcast_to(np.asarray(x_scale, float), (len(model_names),))
+            if not np.all(np.isfinite(xs)) or np.any(xs <= 0):
+                raise ValueError("`x_scale` must be 'jac' or array_like with positive numbers.")
+            xs_full = np.ones(len(all_names))
+            for i, n in enumerate(model_names):
+                xs_full[all_names.index(n)] = xs[i]
+        res = engine.trf_fit(
+            desc, xdata, ydata, P0, LB, UB, frozen,
+            max_nfev=self.max_iter, ftol=self.tol,
+            xtol=self.solver_kwargs.get("xtol", 1e-8), gtol=self.solver_kwargs.get("gtol", 1e-8),
+            jac_mode=jac_mode, x_scale=xs_full, x_scale_jac=x_scale_jac,
+            want_cov=self.want_cov, device=self.device, chunk_vox=self.chunk_vox,
+        )
+        self._free_rows = [all_names.index(n) for n in free_names]
+        return res, free_names
+
+    def _store(self, res, free_names, n_pixels):
+        popt = res["params"][self._free_rows]  # (n_free, n_pixels)
+        pcov = res["cov"]
+        status = res["status"]
+        self.status_, self.nfev_, self.cost_ = status, res["nfev"], res["cost"]
+        self.njev_ = res["njev"]
+        success = status > 0
+        if pcov is None:
+            pcov = np.full((n_pixels, len(free_names), len(free_names)), np.nan)
+        self.pixel_results_ = PixelResults(
+            params=popt.T, covariance=pcov, success=success,
+            messages=lambda i, s=status: engine.STATUS_MESSAGES[int(s[i])] if s[i] <= 0 else None,
+        )
+        self.params_ = {
+            name: [float(popt[i, 0])] if n_pixels == 1 else popt[i]
+            for i, name in enumerate(free_names)
+        }
+        self.diagnostics_ = {"pcov": pcov[0] if n_pixels == 1 else pcov, "n_pixels": n_pixels}
+        n_fail = int((~success).sum())
+        if n_fail:
+            log.warning("%d of %d voxel fits failed (see pixel_results_[i].message)", n_fail, n_pixels)
+
+    # ------------------------------------------------------------------
+    def _validate_p0_and_bounds(self, p0, bounds, n_pixels):
+        """Reference ``_validate_p0_and_bounds`` (curvefit.py:319-392) without the tiling:
+        returns ``(p0, lb, ub)`` as ``(n_params,)`` vectors or ``(n_params, n_pixels)`` arrays."""
+        names = self.model.param_names
+        if p0 is not None:
+            if isinstance(p0, dict):
+                if isinstance(p0[names[0]], np.ndarray):
+                    raise ValueError(
+                        "p0 should either be a basic dict with scalar values or a single np.ndarray "
+                        "of initial values for all parameters. Spatial non-uniform p0 should be "
+                        "handled separately before calling fit()."
+                    )
+                elif isinstance(p0[names[0]], (int, float)):
+                    p0 = V.p0_vector(p0, names)
+                else:
+                    raise ValueError(
+                        "p0 dict values must be either all scalars or a single np.ndarray of "
+                        "initial values for all parameters."
+                    )
+            elif isinstance(p0, np.ndarray):
+                if p0.ndim != 2 or p0.shape[1] != n_pixels:
+                    raise ValueError(
+                        f"p0 shape {p0.shape} does not match number of voxels in ydata {n_pixels}."
+                    )
+            else:
+                raise ValueError("p0 must be either a dict or a single np.ndarray.")
+        else:
+            p0 = V.p0_vector(self.p0, names)
+
+        if bounds is not None:
+            if isinstance(bounds, dict):
+                if isinstance(bounds[names[0]], tuple):
+                    lb, ub = V.bounds_vectors(bounds, names)
+                else:
+                    raise ValueError(
+                        "bounds dict values must be tuples of (lower, upper) for each parameter."
+                    )
+            elif isinstance(bounds, tuple) and len(bounds) == 2:
+                if not all(isinstance(b, np.ndarray) for b in bounds):
+                    raise ValueError(
+                        "bounds tuple must contain two np.ndarrays (lower, upper) of shape (n_params, n_pixels)."
+                    )
+                lb, ub = bounds
+                if lb.ndim != 2 or ub.ndim != 2 or lb.shape[1] != n_pixels or ub.shape[1] != n_pixels:
+                    raise ValueError(
+                        f"bounds shape {lb.shape} and {ub.shape} do not match number of voxels in ydata {n_pixels}."
+                    )
+            else:
+                raise ValueError(
+                    "bounds must be either a dict with parameter names as keys and (lower, upper) "
+                    "tuples as values, or a tuple of (lower, upper) np.ndarrays."
+                )
+        else:
+            lb, ub = V.bounds_vectors(self.bounds, names)
+        return np.asarray(p0, float), np.asarray(lb, float), np.asarray(ub, float)

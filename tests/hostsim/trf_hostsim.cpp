@@ -1,0 +1,78 @@
+// TEST INFRASTRUCTURE ONLY.  Compiles the per-voxel device mathematics
+// (pyneapple_b200/csrc/pnb_trf_core.cuh) with g++ so that it can be compared
+// with the oracle in the GPU-less authoring container.  The product never
+// loads this library; pyneapple_b200 only ever calls the CUDA build.
+#define PNB_HOST_SIM 1
+#include <cstring>
+#include <cmath>
+using std::exp; using std::sqrt; using std::fabs; using std::copysign; using std::nextafter;
+#include "../../pyneapple_b200/csrc/pnb_trf_core.cuh"
+
+using namespace pnb;
+
+template <class M>
+static void run_one(const TrfOptions &O, int m, const double *b, const double *y, const double *p0,
+                    const double *lb, const double *ub, double *params, double *cov, int *status,
+                    int *nfev, double *cost) {
+  constexpr int N = M::NP;
+  TrfLane<M> S;
+  double p0v[N];
+  for (int i = 0; i < N; i++) p0v[i] = p0[i];
+  bool yfin = true;
+  for (int r = 0; r < m; r++) yfin = yfin && finite_d(y[r]);
+  auto yb = [&](int r, double &yv, double &bv) { yv = y[r]; bv = b[r]; };
+  bool running = trf_begin<M>(S, O, p0v, lb, ub, 1, yfin);
+  double c, g[N], A[N][N];
+  if (running) {
+    trf_evaluate<M>(S.x, O, m, yb, lb, ub, 1, c, g, A);
+    running = trf_after_first_eval<M>(S, O, c, g, A, lb, ub, 1);
+  }
+  while (running) {
+    if (S.need_prologue) {
+      if (!trf_prologue<M>(S, O, lb, ub, 1)) break;
+      S.need_prologue = false;
+    }
+    double p_h[N];
+    trf_solve_tr<M>(S, p_h);
+    trf_select_step<M>(S, p_h, lb, ub, 1, O.frozen);
+    trf_evaluate<M>(S.x_new, O, m, yb, lb, ub, 1, c, g, A);
+    S.need_prologue = trf_after_trial<M>(S, O, c, g, A);
+  }
+  *status = S.status; *nfev = S.nfev; *cost = S.cost;
+  int nf = 0;
+  for (int i = 0; i < N; i++) nf += ((O.frozen >> i) & 1u) ? 0 : 1;
+  if (S.status > 0) {
+    for (int i = 0; i < N; i++) params[i] = S.x[i];
+    trf_covariance<M>(S, O, m, cov);
+  } else {
+    for (int i = 0; i < N; i++) params[i] = p0[i];
+    for (int i = 0; i < nf * nf; i++) cov[i] = NAN;
+  }
+}
+
+template <class M>
+static void run_all(const TrfOptions &O, int m, const double *b, long n_vox, const double *y,
+                    const double *p0, const double *lb, const double *ub, double *params, double *cov,
+                    int *status, int *nfev, double *cost) {
+  constexpr int N = M::NP;
+  int nf = 0;
+  for (int i = 0; i < N; i++) nf += ((O.frozen >> i) & 1u) ? 0 : 1;
+  for (long v = 0; v < n_vox; v++)
+    run_one<M>(O, m, b, y + v * m, p0 + v * N, lb + v * N, ub + v * N, params + v * N,
+               cov + v * nf * nf, status + v, nfev + v, cost + v);
+}
+
+extern "C" int pnbh_trf_fit(int model_id, int t1_mode, double tr, double tm, int nb, const double *b,
+                            long n_vox, const double *y, const double *p0, const double *lb,
+                            const double *ub, const int *frozen, double ftol, double xtol, double gtol,
+                            int max_nfev, int jac_mode, int x_scale_jac, const double *x_scale,
+                            double *params, double *cov, int *status, int *nfev, double *cost) {
+  TrfOptions O;
+  O.ftol = ftol; O.xtol = xtol; O.gtol = gtol; O.max_nfev = max_nfev; O.jac_mode = jac_mode;
+  O.x_scale_jac = x_scale_jac; O.frozen = 0; O.tr = tr; O.tm = tm;
+  for (int i = 0; i < 8; i++) { O.x_scale[i] = x_scale ? x_scale[i] : 1.0; if (frozen && i < 7 && frozen[i]) O.frozen |= 1u << i; }
+#define CASE(ID, T) if (model_id == ID && t1_mode == T) { run_all<Model<ID, T>>(O, nb, b, n_vox, y, p0, lb, ub, params, cov, status, nfev, cost); return 0; }
+  CASE(0, 0) CASE(1, 0) CASE(2, 0) CASE(3, 0) CASE(4, 0) CASE(5, 0) CASE(6, 0)
+  CASE(0, 1) CASE(1, 1) CASE(3, 1) CASE(0, 2) CASE(3, 2) CASE(4, 1) CASE(6, 2)
+  return -1;
+}

@@ -1,0 +1,53 @@
+"""The C-ABI library builds, loads and exports every symbol the header declares (no GPU needed)."""
+
+import ctypes
+import os
+
+import pytest
+
+from pyneapple_b200 import _lib
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(_lib.SO_PATH):
+        _lib.build()
+    return _lib.load()
+
+
+def test_exports_every_declared_symbol(lib):
+    names = _lib.exported_symbols()
+    assert "pnb_trf_fit_host" in names and "pnb_trf_fit_device" in names
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/pyneapple_b200.h but not exported"
+
+
+def test_abi_version(lib):
+    assert lib.pnb_abi_version() == 1
+
+
+def test_struct_layout_matches_header(lib):
+    # sizeof(pnb_trf_problem) as compiled by nvcc must equal the ctypes mirror
+    assert ctypes.sizeof(_lib.TrfProblem) == lib.pnb_sizeof_trf_problem()
+
+
+def test_bad_arguments_are_rejected_without_a_device(lib):
+    prob = _lib.TrfProblem()
+    prob.model_id = 99
+    rc = lib.pnb_trf_fit_host(ctypes.byref(prob), 0, 0)
+    assert rc == -2
+    assert b"model" in lib.pnb_last_error()
+
+
+def test_no_cpu_fallback():
+    import numpy as np
+    from pyneapple_b200 import models
+    from pyneapple_b200.solvers import CurveFitSolver
+
+    if _lib.load().pnb_device_count() > 0:
+        pytest.skip("a GPU is present")
+    s = CurveFitSolver(models.MonoExpModel(), 250, 1e-8, {"S0": 1000.0, "D": 1e-3},
+                       {"S0": (1.0, 5000.0), "D": (1e-5, 0.1)})
+    b = np.linspace(0, 1000, 8)
+    with pytest.raises(_lib.EngineError):
+        s.fit(b, 1000 * np.exp(-b * 1e-3))
