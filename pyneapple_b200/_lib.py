@@ -130,34 +130,36 @@ def exported_symbols() -> list[str]:
     return sorted(set(re.findall(r"\b(pnb_[a-z0-9_]+)\s*\(", text)))
 
 
-class PinnedArray:
-    """A numpy array backed by page-locked host memory (full-speed H2D / D2H)."""
+class _PinnedBlock:
+    """Owner of one cudaHostAlloc block; freed when the last array viewing it dies."""
 
-    def __init__(self, shape, dtype=np.float64):
-        self.shape = tuple(int(s) for s in np.atleast_1d(shape))
-        self.dtype = np.dtype(dtype)
-        nbytes = max(1, int(np.prod(self.shape)) * self.dtype.itemsize)
+    def __init__(self, nbytes: int):
         ptr = C.c_void_p()
         check(load().pnb_host_alloc(C.byref(ptr), nbytes), "pnb_host_alloc")
-        self._ptr = ptr
-        buf = (C.c_char * nbytes).from_address(ptr.value)
-        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
-
-    def free(self):
-        if self._ptr is not None:
-            self.array = None
-            load().pnb_host_free(self._ptr)
-            self._ptr = None
+        self.ptr = ptr
 
     def __del__(self):  # pragma: no cover - best effort
         try:
-            self.free()
+            if self.ptr is not None:
+                load().pnb_host_free(self.ptr)
+                self.ptr = None
         except Exception:
             pass
 
 
-def pinned_empty(shape, dtype=np.float64) -> PinnedArray:
-    return PinnedArray(shape, dtype)
+def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
+    """A numpy array in page-locked host memory (full-speed, truly asynchronous H2D / D2H).
+
+    The block is released when the array (and every view of it) is garbage collected.
+    """
+    shape = tuple(int(s) for s in np.atleast_1d(shape))
+    dtype = np.dtype(dtype)
+    count = int(np.prod(shape))
+    nbytes = max(1, count * dtype.itemsize)
+    block = _PinnedBlock(nbytes)
+    buf = (C.c_char * nbytes).from_address(block.ptr.value)
+    buf._pnb_block = block  # the ctypes buffer is the ndarray's base and keeps the block alive
+    return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
 
 
 def measure_fp64_peak(device: int = 0) -> float:

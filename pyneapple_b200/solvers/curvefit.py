@@ -62,6 +62,10 @@ class CurveFitSolver(BaseSolver):
         self.device = solver_kwargs.pop("device", 0)
         self.chunk_vox = solver_kwargs.pop("chunk_vox", 0)
         self.want_cov = solver_kwargs.pop("want_cov", True)
+        # opt-in: keep page-locked output buffers between fits (results are then views
+        # that the next fit overwrites) -- removes the pageable D2H staging cost
+        self.pinned_outputs = solver_kwargs.pop("pinned_outputs", False)
+        self._out_cache = None
         if self.jac not in ("reference", "analytic", "2-point"):
             raise ValueError("jac must be 'reference', 'analytic' or '2-point'")
         unknown = set(solver_kwargs) - _HONOURED_KWARGS - _IGNORED_KWARGS
@@ -183,9 +187,29 @@ class CurveFitSolver(BaseSolver):
             xtol=self.solver_kwargs.get("xtol", 1e-8), gtol=self.solver_kwargs.get("gtol", 1e-8),
             jac_mode=jac_mode, x_scale=xs_full, x_scale_jac=x_scale_jac,
             want_cov=self.want_cov, device=self.device, chunk_vox=self.chunk_vox,
+            out=self._pinned_out(len(all_names), len(all_names) - len(fixed_names), n_pixels, ydata),
         )
         self._free_rows = [all_names.index(n) for n in free_names]
         return res, free_names
+
+    def _pinned_out(self, n_all, n_free, n_pixels, ydata):
+        if not self.pinned_outputs or engine._is_torch_cuda(ydata):
+            return None
+        from .. import _lib
+
+        key = (n_all, n_free, n_pixels, bool(self.want_cov))
+        if self._out_cache is None or self._out_cache[0] != key:
+            out = dict(
+                params=_lib.pinned_empty((n_all, n_pixels)),
+                status=_lib.pinned_empty((n_pixels,), np.int32),
+                nfev=_lib.pinned_empty((n_pixels,), np.int32),
+                njev=_lib.pinned_empty((n_pixels,), np.int32),
+                cost=_lib.pinned_empty((n_pixels,)),
+            )
+            if self.want_cov:
+                out["cov"] = _lib.pinned_empty((n_pixels, n_free, n_free))
+            self._out_cache = (key, out)
+        return self._out_cache[1]
 
     def _store(self, res, free_names, n_pixels):
         popt = res["params"][self._free_rows]  # (n_free, n_pixels)

@@ -40,11 +40,11 @@ for label, yy in (("pageable", y),):
     for rep in range(3):
         t = time.perf_counter(); r = engine.trf_fit(desc, b, yy, p0, lb, ub, 0, jac_mode=1); dt = time.perf_counter() - t
     print(f"host path {label}: {y.shape[0]} vox in {dt*1e3:.1f} ms -> {y.shape[0]/dt/1e6:.2f} Mvox/s")
-pin = _lib.pinned_empty(y.shape); pin.array[...] = y
+pin = _lib.pinned_empty(y.shape); pin[...] = y
 n = y.shape[0]
-outs = dict(params=_lib.pinned_empty((4, n)).array, cov=_lib.pinned_empty((n, 4, 4)).array, status=_lib.pinned_empty((n,), np.int32).array,
-            nfev=_lib.pinned_empty((n,), np.int32).array, njev=_lib.pinned_empty((n,), np.int32).array, cost=_lib.pinned_empty((n,)).array)
+outs = dict(params=_lib.pinned_empty((4, n)), cov=_lib.pinned_empty((n, 4, 4)), status=_lib.pinned_empty((n,), np.int32),
+            nfev=_lib.pinned_empty((n,), np.int32), njev=_lib.pinned_empty((n,), np.int32), cost=_lib.pinned_empty((n,)))
 for chunk in (1 << 16, 1 << 18, 1 << 20):
     for rep in range(3):
-        t = time.perf_counter(); r = engine.trf_fit(desc, b, pin.array, p0, lb, ub, 0, jac_mode=1, out=outs, chunk_vox=chunk); dt = time.perf_counter() - t
+        t = time.perf_counter(); r = engine.trf_fit(desc, b, pin, p0, lb, ub, 0, jac_mode=1, out=outs, chunk_vox=chunk); dt = time.perf_counter() - t
     print(f"host path pinned chunk={chunk}: {n} vox in {dt*1e3:.1f} ms -> {n/dt/1e6:.2f} Mvox/s")
