@@ -1,21 +1,27 @@
 // Persistent one-lane-per-voxel TRF kernel.
 //
 // Execution model (B200, FP64 CUDA-core bound — there is no FP64 tcgen05 path):
-//   * grid = resident CTAs per SM x 148 SMs, every thread is a lane that pulls
-//     voxel indices from a global counter (warp-aggregated atomicAdd) until the
-//     volume is exhausted.  A lane whose voxel converges refills immediately,
-//     so the 4..30 iterations different voxels need do not idle the other 31
-//     lanes of the warp the way a one-voxel-per-thread grid would.
-//   * each pass of the main loop is the same straight-line sequence for every
-//     lane — [refill] -> [prologue + trust-region solve + step selection] ->
-//     [model / Jacobian / normal-equation accumulation over the b-values] ->
-//     [accept / reject bookkeeping] -> [finalise] — guarded by per-lane
-//     predicates, so lanes at different iterations of different voxels still
-//     execute the FP64-heavy middle part convergently.
-//   * shared memory holds the b-value vector (broadcast reads) and, per lane,
-//     its voxel's signal and bounds in [row][lane] order (conflict-free 8-byte
-//     accesses); the signal row of a voxel is fetched from the voxel-major
-//     (n_vox, n_b) array with 16-byte loads.  All solver state is in registers.
+//   * grid = resident CTAs per SM x 148 SMs; every thread is a lane that works
+//     through voxels until the volume is exhausted.  A lane whose voxel
+//     converges starts its next voxel on the following pass, so the 4..30
+//     iterations different voxels need do not idle the other lanes of the warp.
+//   * voxel indices come from a global counter, claimed 64 at a time per warp
+//     (one atomicAdd by lane 0, issued one range ahead of need so its latency
+//     is never waited for) and handed to lanes with ballot / popc arithmetic.
+//   * a lane always holds one voxel *ahead*: as soon as it starts voxel v it
+//     claims the next index and pulls that voxel's signal row (and per-voxel
+//     p0 / bounds) into the other half of a double-buffered shared-memory
+//     column with cp.async, ~8 passes before the data is used, so HBM/L2
+//     latency is hidden even at 8 warps per SM.
+//   * every pass of the main loop is the same sequence for all 32 lanes —
+//     [claim/prefetch] [start] [prologue + trust-region solve + step selection]
+//     [model / Jacobian / normal equations over the b-values] [accept/reject]
+//     [write results] — with a warp-wide vote at the top of the pass, which
+//     re-converges the warp: without it the lanes drift apart after the first
+//     divergent branch and the FP64-heavy evaluation runs at half width.
+//   * shared memory: the b-value vector (broadcast reads) and, per lane, signal
+//     and bounds columns in [row][lane] order (conflict-free 8-byte accesses).
+//     All solver state is in registers.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -43,66 +49,135 @@ struct TrfDeviceArgs {
   unsigned long long *counter;  // work counter, zeroed before launch
 };
 
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+constexpr int kTrfClaim = 64;  // voxel indices claimed per warp-level atomicAdd
+
 template <class M, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) trf_kernel(const TrfDeviceArgs a) {
   constexpr int N = M::NP;
+  constexpr unsigned FULL = 0xffffffffu;
   extern __shared__ double smem[];
   const int m = a.n_b;
   const int tid = threadIdx.x;
-  double *b_s = smem;                       // [m]
-  double *y_s = b_s + ((m + 1) & ~1);       // [m][BLOCK]
-  double *lb_s = y_s + (size_t)m * BLOCK;   // [N][BLOCK]
-  double *ub_s = lb_s + N * BLOCK;          // [N][BLOCK]
-  for (int i = tid; i < m; i += BLOCK) b_s[i] = a.b[i];
-  __syncthreads();
-  double *my_y = y_s + tid;
-  const double *my_lb = lb_s + tid;
-  const double *my_ub = ub_s + tid;
-  const TrfOptions &O = a.opt;
   const unsigned lane = tid & 31;
+  const bool pv_p0 = a.p0_vox_stride != 0;
+  const bool pv_bd = a.bd_vox_stride != 0;
+  // layout: b[m'] | y[2][m][BLOCK] | lb[2][N][BLOCK] | ub[2][N][BLOCK] | p0[2][N][BLOCK]
+  double *b_s = smem;
+  double *y_s = b_s + ((m + 1) & ~1);
+  double *lb_s = y_s + (size_t)2 * m * BLOCK;
+  double *ub_s = lb_s + 2 * N * BLOCK;
+  double *p0_s = ub_s + 2 * N * BLOCK;
+  for (int i = tid; i < m; i += BLOCK) b_s[i] = a.b[i];
+  if (!pv_bd) {
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+      const double l = a.lb[k * a.bd_row_stride], u = a.ub[k * a.bd_row_stride];
+      lb_s[k * BLOCK + tid] = l; lb_s[(N + k) * BLOCK + tid] = l;
+      ub_s[k * BLOCK + tid] = u; ub_s[(N + k) * BLOCK + tid] = u;
+    }
+  }
+  if (!pv_p0) {
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+      const double v = a.p0[k * a.p0_row_stride];
+      p0_s[k * BLOCK + tid] = v; p0_s[(N + k) * BLOCK + tid] = v;
+    }
+  }
+  __syncthreads();
+  const TrfOptions &O = a.opt;
+
+  // warp-level queue of claimed voxel indices: two contiguous ranges
+  long long qa = 0, qb = 0;
+  int na = 0, nb = 0;
+  auto claim_range = [&](long long &base, int &cnt) {
+    unsigned long long v = 0;
+    if (lane == 0) v = atomicAdd(a.counter, (unsigned long long)kTrfClaim);
+    v = __shfl_sync(FULL, v, 0);
+    base = (long long)v;
+    long long left = a.n_vox - base;
+    cnt = left <= 0 ? 0 : (left < kTrfClaim ? (int)left : kTrfClaim);
+  };
+  claim_range(qa, na);
+  claim_range(qb, nb);
 
   TrfLane<M> S;
-  long long vox = -1;
+  long long cur = -1, nxt = -1;
+  int buf = 0, nxt_buf = 0;  // which half of the double buffers holds `cur` / receives `nxt`
   bool first_eval = false;
-  auto yb = [&](int r, double &yv, double &bv) { yv = my_y[r * BLOCK]; bv = b_s[r]; };
 
   for (;;) {
+    // ---- claim + prefetch the voxel after the current one ----------------
+    const bool want = nxt < 0;
+    const unsigned wmask = __ballot_sync(FULL, want);
+    if (wmask && (na + nb) > 0) {
+      const int k = __popc(wmask);
+      const int i = __popc(wmask & ((1u << lane) - 1));
+      if (want) {
+        if (i < na) nxt = qa + i;
+        else if (i - na < nb) nxt = qb + (i - na);
+      }
+      if (k >= na) {  // range A used up: B becomes A, claim a new B (needed a few passes from now)
+        const int used_b = k - na;
+        qa = qb + used_b;
+        na = nb > used_b ? nb - used_b : 0;
+        claim_range(qb, nb);
+      } else {
+        qa += k;
+        na -= k;
+      }
+      if (want && nxt >= 0) {
+        nxt_buf = (cur >= 0) ? (buf ^ 1) : buf;
+        const double *yrow = a.y + nxt * m;
+        double *ycol = y_s + (size_t)nxt_buf * m * BLOCK + tid;
+        for (int r = 0; r < m; r++) cp_async8(ycol + r * BLOCK, yrow + r);
+        if (pv_bd) {
+#pragma unroll
+          for (int kk = 0; kk < N; kk++) {
+            cp_async8(lb_s + (nxt_buf * N + kk) * BLOCK + tid, a.lb + kk * a.bd_row_stride + nxt);
+            cp_async8(ub_s + (nxt_buf * N + kk) * BLOCK + tid, a.ub + kk * a.bd_row_stride + nxt);
+          }
+        }
+        if (pv_p0) {
+#pragma unroll
+          for (int kk = 0; kk < N; kk++)
+            cp_async8(p0_s + (nxt_buf * N + kk) * BLOCK + tid, a.p0 + kk * a.p0_row_stride + nxt);
+        }
+        cp_async_commit();
+      }
+    }
+    // ---- every lane out of work: done --------------------------------------
+    if (__all_sync(FULL, cur < 0 && nxt < 0)) break;
+
     bool finished = false;
     bool do_eval = false;
-    // ---- refill -----------------------------------------------------
-    if (vox < 0) {
-      const unsigned mask = __activemask();
-      const int leader = __ffs(mask) - 1;
-      unsigned long long base = 0;
-      if ((int)lane == leader) base = atomicAdd(a.counter, (unsigned long long)__popc(mask));
-      base = __shfl_sync(mask, base, leader);
-      vox = (long long)(base + __popc(mask & ((1u << lane) - 1)));
-      if (vox >= a.n_vox) break;
-      // signal row -> shared (16-byte loads when the row is 16-byte aligned)
-      const double *yrow = a.y + vox * m;
+    bool starting = false;
+    if (cur < 0 && nxt >= 0) {
+      cp_async_wait_all();  // issued ~a whole voxel ago, except for the very first voxel
+      cur = nxt;
+      nxt = -1;
+      buf = nxt_buf;
+      starting = true;
+    }
+    const double *my_y = y_s + (size_t)buf * m * BLOCK + tid;
+    const double *my_lb = lb_s + buf * N * BLOCK + tid;
+    const double *my_ub = ub_s + buf * N * BLOCK + tid;
+    const double *my_p0 = p0_s + buf * N * BLOCK + tid;
+    auto yb = [&](int r, double &yv, double &bv) { yv = my_y[r * BLOCK]; bv = b_s[r]; };
+
+    if (starting) {
+      // ---- least_squares() preamble -------------------------------------------
       bool yfin = true;
-      if ((m & 1) == 0 && ((reinterpret_cast<uintptr_t>(yrow) & 15) == 0)) {
-        const double2 *y2 = reinterpret_cast<const double2 *>(yrow);
-        for (int r = 0; r < m / 2; r++) {
-          const double2 v = __ldg(y2 + r);
-          my_y[(2 * r) * BLOCK] = v.x;
-          my_y[(2 * r + 1) * BLOCK] = v.y;
-          yfin = yfin && finite_d(v.x) && finite_d(v.y);
-        }
-      } else {
-        for (int r = 0; r < m; r++) {
-          const double v = __ldg(yrow + r);
-          my_y[r * BLOCK] = v;
-          yfin = yfin && finite_d(v);
-        }
-      }
+      for (int r = 0; r < m; r++) yfin = yfin && finite_d(my_y[r * BLOCK]);
       double p0v[N];
 #pragma unroll
-      for (int k = 0; k < N; k++) {
-        p0v[k] = __ldg(a.p0 + k * a.p0_row_stride + vox * a.p0_vox_stride);
-        lb_s[k * BLOCK + tid] = __ldg(a.lb + k * a.bd_row_stride + vox * a.bd_vox_stride);
-        ub_s[k * BLOCK + tid] = __ldg(a.ub + k * a.bd_row_stride + vox * a.bd_vox_stride);
-      }
+      for (int k = 0; k < N; k++) p0v[k] = my_p0[k * BLOCK];
       if (trf_begin<M>(S, O, p0v, my_lb, my_ub, BLOCK, yfin)) {
         first_eval = true;
         do_eval = true;
@@ -111,8 +186,8 @@ __global__ void __launch_bounds__(BLOCK) trf_kernel(const TrfDeviceArgs a) {
       } else {
         finished = true;
       }
-    } else {
-      // ---- prepare a trial step ---------------------------------------
+    } else if (cur >= 0) {
+      // ---- prepare a trial step -------------------------------------------------
       bool go = true;
       if (S.need_prologue) {
         go = trf_prologue<M>(S, O, my_lb, my_ub, BLOCK);
@@ -127,7 +202,8 @@ __global__ void __launch_bounds__(BLOCK) trf_kernel(const TrfDeviceArgs a) {
         finished = true;
       }
     }
-    // ---- model, Jacobian and normal equations at x_new ------------------
+    __syncwarp();
+    // ---- model, Jacobian and normal equations at x_new --------------------------
     if (do_eval) {
       double c, g[N], A[N][N];
       trf_evaluate<M>(S.x_new, O, m, yb, my_lb, my_ub, BLOCK, c, g, A);
@@ -138,20 +214,21 @@ __global__ void __launch_bounds__(BLOCK) trf_kernel(const TrfDeviceArgs a) {
         S.need_prologue = trf_after_trial<M>(S, O, c, g, A);
       }
     }
-    // ---- write results ------------------------------------------------
+    __syncwarp();
+    // ---- write results ------------------------------------------------------------
     if (finished) {
+      const long long vox = cur;
       const bool ok = S.status > 0;
       int n_free = 0;
 #pragma unroll
       for (int k = 0; k < N; k++) {
         n_free += ((O.frozen >> k) & 1u) ? 0 : 1;
-        const double v = ok ? S.x[k] : __ldg(a.p0 + k * a.p0_row_stride + vox * a.p0_vox_stride);
-        a.params[(long long)k * a.n_vox + vox] = v;
+        a.params[(long long)k * a.n_vox + vox] = ok ? S.x[k] : my_p0[k * BLOCK];
       }
       a.status[vox] = S.status;
       a.nfev[vox] = S.nfev;
       if (a.njev) a.njev[vox] = S.njev;
-      if (a.cost) a.cost[vox] = ok || S.status == kStMaxNfev ? S.cost : nan("");
+      if (a.cost) a.cost[vox] = (ok || S.status == kStMaxNfev) ? S.cost : nan("");
       if (a.cov) {
         double *cv = a.cov + vox * (long long)(n_free * n_free);
         if (ok) {
@@ -161,13 +238,13 @@ __global__ void __launch_bounds__(BLOCK) trf_kernel(const TrfDeviceArgs a) {
           for (int i = 0; i < n_free * n_free; i++) cv[i] = qnan;
         }
       }
-      vox = -1;
+      cur = -1;
     }
   }
 }
 
 template <class M, int BLOCK> size_t trf_smem_bytes(int n_b) {
-  return sizeof(double) * (((n_b + 1) & ~1) + (size_t)n_b * BLOCK + 2 * M::NP * BLOCK);
+  return sizeof(double) * (((n_b + 1) & ~1) + (size_t)2 * n_b * BLOCK + 6 * M::NP * BLOCK);
 }
 
 // Launch configuration: persistent grid, as many CTAs as are resident.
@@ -178,6 +255,7 @@ template <class M, int BLOCK> cudaError_t trf_launch(const TrfDeviceArgs &a, cud
   static size_t smem_cache = 0;
   static int sm_count = 0;
   cudaError_t err;
+  if (smem > 200 * 1024) return cudaErrorInvalidValue;  // n_b too large for this block size
   if (smem > 48 * 1024) {
     err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
@@ -195,6 +273,7 @@ template <class M, int BLOCK> cudaError_t trf_launch(const TrfDeviceArgs &a, cud
     blocks_per_sm_cache = bps;
     smem_cache = smem;
   }
+  // one voxel in flight + one prefetched per lane: do not launch more lanes than that needs
   long long want = (a.n_vox + BLOCK - 1) / BLOCK;
   long long grid = (long long)blocks_per_sm_cache * sm_count;
   if (want < grid) grid = want;
