@@ -106,6 +106,35 @@ typedef struct pnb_trf_problem {
 int pnb_trf_fit_device(const pnb_trf_problem *prob, void *cuda_stream);
 int pnb_trf_fit_host(const pnb_trf_problem *prob, int device, int64_t chunk_vox);
 
+/*
+ * Tikhonov-regularised non-negative least squares for n_vox voxels on a shared
+ * dictionary.  Replaces NNLSSolver._fit_data / _fit_single_pixel
+ * (solvers/nnls_solver.py:129-210), i.e. one scipy.optimize.nnls([basis; mu R],
+ * [signal; 0], maxiter=max_iter) call per voxel.  The caller passes the plain
+ * basis (model_functions/nnls.py:31-43) and the band of mu^2 R^T R of the
+ * regularisation matrix (model_functions/nnls.py:46-85); both are built once
+ * per fit on the host with the reference's own formulas.
+ */
+typedef struct pnb_nnls_problem {
+  int32_t n_b;               /* measurements                                    */
+  int32_t n_bins;            /* dictionary size                                 */
+  int32_t rtr_halfband;      /* W: (R^T R)[i][j] = 0 for |i-j| > W              */
+  int32_t max_iter;          /* NNLSSolver.max_iter (Lawson-Hanson iteration cap) */
+  int64_t n_vox;
+  const double *basis;       /* (n_b, n_bins)                                   */
+  const double *rtr_band;    /* (n_bins, 2W+1): [j][d+W] = (mu^2 R^T R)[j][j+d] */
+  const double *signal;      /* (n_vox, n_b)                                    */
+  double *coefficients;      /* (n_vox, n_bins)                                 */
+  double *residual;          /* (n_vox) ||[basis; mu R] x - [signal; 0]||_2     */
+  int32_t *status;           /* (n_vox) 1 converged; 3 iteration cap, 2 non-finite
+                                signal: coefficients = 0, residual = ||signal|| */
+  int32_t *iterations;       /* (n_vox) Lawson-Hanson iteration count           */
+} pnb_nnls_problem;
+
+int pnb_nnls_fit_device(const pnb_nnls_problem *prob, void *cuda_stream);
+int pnb_nnls_fit_host(const pnb_nnls_problem *prob, int device, int64_t chunk_vox);
+int pnb_sizeof_nnls_problem(void);
+
 /* housekeeping */
 int pnb_abi_version(void);
 /* sizeof(struct pnb_trf_problem) as compiled, for binding self-checks */

@@ -60,6 +60,25 @@ class TrfProblem(C.Structure):
     ]
 
 
+class NnlsProblem(C.Structure):
+    """Mirror of ``struct pnb_nnls_problem``."""
+
+    _fields_ = [
+        ("n_b", C.c_int32),
+        ("n_bins", C.c_int32),
+        ("rtr_halfband", C.c_int32),
+        ("max_iter", C.c_int32),
+        ("n_vox", C.c_int64),
+        ("basis", C.c_void_p),
+        ("rtr_band", C.c_void_p),
+        ("signal", C.c_void_p),
+        ("coefficients", C.c_void_p),
+        ("residual", C.c_void_p),
+        ("status", C.c_void_p),
+        ("iterations", C.c_void_p),
+    ]
+
+
 def build(verbose: bool = False, t1: bool = True) -> str:
     """Compile ``libpnb200.so`` for sm_100a with nvcc (works without a GPU)."""
     cmd = ["make", "-C", CSRC, "-j", str(min(16, os.cpu_count() or 4))]
@@ -92,6 +111,10 @@ def load():
     lib.pnb_trf_fit_device.restype = C.c_int
     lib.pnb_trf_fit_host.argtypes = [C.POINTER(TrfProblem), C.c_int, C.c_int64]
     lib.pnb_trf_fit_host.restype = C.c_int
+    lib.pnb_nnls_fit_device.argtypes = [C.POINTER(NnlsProblem), C.c_void_p]
+    lib.pnb_nnls_fit_device.restype = C.c_int
+    lib.pnb_nnls_fit_host.argtypes = [C.POINTER(NnlsProblem), C.c_int, C.c_int64]
+    lib.pnb_nnls_fit_host.restype = C.c_int
     lib.pnb_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_int64]
     lib.pnb_host_free.argtypes = [C.c_void_p]
     lib.pnb_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]

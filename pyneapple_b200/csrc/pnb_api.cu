@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../include/pyneapple_b200.h"
+#include "pnb_internal.h"
 #include "pnb_trf_kernel.cuh"
 
 namespace {
@@ -33,6 +34,12 @@ int cuda_fail(cudaError_t e, const char *what) {
 using LaunchFn = cudaError_t (*)(const pnb::TrfDeviceArgs *, cudaStream_t);
 
 }  // namespace
+
+namespace pnbi {
+int fail(int code, const std::string &msg) { return ::fail(code, msg); }
+int cuda_fail(cudaError_t e, const char *what) { return ::cuda_fail(e, what); }
+void count_launch() { g_launches.fetch_add(1); }
+}  // namespace pnbi
 
 #define PNB_DECL(id, t1) extern "C" cudaError_t pnb_trf_launch_##id##_##t1(const pnb::TrfDeviceArgs *, cudaStream_t);
 PNB_DECL(0, 0) PNB_DECL(1, 0) PNB_DECL(2, 0) PNB_DECL(3, 0) PNB_DECL(4, 0) PNB_DECL(5, 0) PNB_DECL(6, 0)

@@ -1,0 +1,156 @@
+// C ABI of the batched NNLS solver (see include/pyneapple_b200.h).
+#include <cuda_runtime.h>
+
+#include <mutex>
+
+#include "../../include/pyneapple_b200.h"
+#include "pnb_internal.h"
+#include "pnb_nnls_kernel.cuh"
+
+namespace {
+
+constexpr int kWarps = 8;
+constexpr size_t kSmemBudget = 220 * 1024;
+
+struct NnlsCtx {
+  unsigned long long *counters = nullptr;  // ring
+  int next = 0;
+  double *scratch = nullptr;
+  size_t scratch_cap = 0;
+  // host pipeline
+  cudaStream_t streams[2] = {nullptr, nullptr};
+  double *y[2] = {nullptr, nullptr}, *coef[2] = {nullptr, nullptr}, *rn[2] = {nullptr, nullptr};
+  int *st[2] = {nullptr, nullptr}, *it[2] = {nullptr, nullptr};
+  size_t cap_vox = 0, cap_m = 0, cap_n = 0;
+  double *B = nullptr, *rtr = nullptr;
+  size_t cap_B = 0, cap_rtr = 0;
+};
+NnlsCtx g_ctx[16];
+std::mutex g_mu;
+
+int check(const pnb_nnls_problem *p) {
+  if (!p) return pnbi::fail(PNB_E_BADARG, "null problem");
+  if (p->n_b < 1 || p->n_b > 512) return pnbi::fail(PNB_E_BADARG, "n_b must be in [1, 512]");
+  if (p->n_bins < 1 || p->n_bins > 1024) return pnbi::fail(PNB_E_BADARG, "n_bins must be in [1, 1024]");
+  if (p->rtr_halfband < 0 || p->rtr_halfband > 8) return pnbi::fail(PNB_E_BADARG, "rtr_halfband must be in [0, 8]");
+  if (p->max_iter < 1) return pnbi::fail(PNB_E_BADARG, "max_iter must be positive");
+  if (p->n_vox < 0) return pnbi::fail(PNB_E_BADARG, "n_vox < 0");
+  if (p->n_vox > 0 && (!p->basis || !p->rtr_band || !p->signal || !p->coefficients || !p->residual ||
+                       !p->status || !p->iterations))
+    return pnbi::fail(PNB_E_BADARG, "null array pointer");
+  return 0;
+}
+
+// the largest active-set size whose factor fits shared memory next to everything else
+int pick_kmax(int m, int n, int W) {
+  int k = n;
+  while (k > 8 && pnb::nnls_smem_bytes(m, n, W, k, kWarps) > kSmemBudget) k--;
+  return k;
+}
+
+int launch(NnlsCtx &C, const pnb_nnls_problem *p, const double *B, const double *rtr, const double *y,
+           long long n_vox, double *coef, double *rn, int *st, int *it, cudaStream_t stream) {
+  const int m = p->n_b, n = p->n_bins, W = p->rtr_halfband;
+  const int kmax = pick_kmax(m, n, W);
+  const size_t smem = pnb::nnls_smem_bytes(m, n, W, kmax, kWarps);
+  if (smem > 227 * 1024) return pnbi::fail(PNB_E_UNSUPPORTED, "n_b x n_bins too large for shared memory");
+  auto kern = pnb::nnls_kernel<kWarps>;
+  PNBI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int dev = 0, sms = 0, bps = 0;
+  PNBI_CUDA(cudaGetDevice(&dev));
+  PNBI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  PNBI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, kWarps * 32, smem));
+  if (bps < 1) return pnbi::fail(PNB_E_UNSUPPORTED, "NNLS kernel does not fit on this device");
+  long long grid = (long long)bps * sms;
+  const long long want = (n_vox + kWarps - 1) / kWarps;
+  if (want < grid) grid = want;
+  if (grid < 1) grid = 1;
+  const size_t per_warp = (size_t)n * (n + 1) / 2 + 5 * (size_t)n;
+  const size_t need = (size_t)bps * sms * kWarps * per_warp;
+  {
+    if (need > C.scratch_cap) {
+      if (C.scratch) PNBI_CUDA(cudaFree(C.scratch));
+      C.scratch = nullptr; C.scratch_cap = 0;
+      PNBI_CUDA(cudaMalloc(&C.scratch, need * sizeof(double)));
+      C.scratch_cap = need;
+    }
+    if (!C.counters) PNBI_CUDA(cudaMalloc(&C.counters, 64 * sizeof(unsigned long long)));
+  }
+  pnb::NnlsDeviceArgs a;
+  a.m = m; a.n = n; a.W = W; a.maxiter = p->max_iter; a.n_vox = n_vox;
+  a.B = B; a.rtr = rtr; a.y = y; a.coef = coef; a.rnorm = rn; a.status = st; a.iters = it;
+  a.counter = C.counters + C.next;
+  C.next = (C.next + 1) % 64;
+  a.scratch = C.scratch; a.kmax = kmax;
+  PNBI_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(unsigned long long), stream));
+  kern<<<(unsigned)grid, kWarps * 32, smem, stream>>>(a);
+  PNBI_CUDA(cudaGetLastError());
+  pnbi::count_launch();
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int pnb_nnls_fit_device(const pnb_nnls_problem *p, void *cuda_stream) {
+  if (int rc = check(p)) return rc;
+  if (p->n_vox == 0) return 0;
+  int dev = 0;
+  PNBI_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(g_mu);
+  return launch(g_ctx[dev & 15], p, p->basis, p->rtr_band, p->signal, p->n_vox, p->coefficients,
+                p->residual, p->status, p->iterations, (cudaStream_t)cuda_stream);
+}
+
+extern "C" int pnb_nnls_fit_host(const pnb_nnls_problem *p, int device, int64_t chunk_vox) {
+  if (int rc = check(p)) return rc;
+  if (p->n_vox == 0) return 0;
+  if (pnb_device_count() <= device || device < 0) return pnbi::fail(PNB_E_NODEVICE, "no such CUDA device");
+  PNBI_CUDA(cudaSetDevice(device));
+  std::lock_guard<std::mutex> lk(g_mu);
+  NnlsCtx &C = g_ctx[device & 15];
+  const int m = p->n_b, n = p->n_bins, BW = 2 * p->rtr_halfband + 1;
+  if (chunk_vox <= 0) chunk_vox = 1 << 16;
+  if (chunk_vox > p->n_vox) chunk_vox = p->n_vox;
+  const size_t Cn = (size_t)chunk_vox;
+  if (!C.streams[0])
+    for (auto &s : C.streams) PNBI_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  if (Cn > C.cap_vox || (size_t)m > C.cap_m || (size_t)n > C.cap_n) {
+    for (int s = 0; s < 2; s++) {
+      if (C.y[s]) { cudaFree(C.y[s]); cudaFree(C.coef[s]); cudaFree(C.rn[s]); cudaFree(C.st[s]); cudaFree(C.it[s]); }
+      PNBI_CUDA(cudaMalloc(&C.y[s], Cn * m * sizeof(double)));
+      PNBI_CUDA(cudaMalloc(&C.coef[s], Cn * n * sizeof(double)));
+      PNBI_CUDA(cudaMalloc(&C.rn[s], Cn * sizeof(double)));
+      PNBI_CUDA(cudaMalloc(&C.st[s], Cn * sizeof(int)));
+      PNBI_CUDA(cudaMalloc(&C.it[s], Cn * sizeof(int)));
+    }
+    C.cap_vox = Cn; C.cap_m = m; C.cap_n = n;
+  }
+  if ((size_t)m * n > C.cap_B) {
+    if (C.B) cudaFree(C.B);
+    PNBI_CUDA(cudaMalloc(&C.B, (size_t)m * n * sizeof(double)));
+    C.cap_B = (size_t)m * n;
+  }
+  if ((size_t)n * BW > C.cap_rtr) {
+    if (C.rtr) cudaFree(C.rtr);
+    PNBI_CUDA(cudaMalloc(&C.rtr, (size_t)n * BW * sizeof(double)));
+    C.cap_rtr = (size_t)n * BW;
+  }
+  PNBI_CUDA(cudaMemcpy(C.B, p->basis, (size_t)m * n * sizeof(double), cudaMemcpyHostToDevice));
+  PNBI_CUDA(cudaMemcpy(C.rtr, p->rtr_band, (size_t)n * BW * sizeof(double), cudaMemcpyHostToDevice));
+  const size_t NV = (size_t)p->n_vox;
+  int s = 0;
+  for (size_t start = 0; start < NV; start += Cn, s ^= 1) {
+    const size_t nv = (NV - start < Cn) ? NV - start : Cn;
+    cudaStream_t st = C.streams[s];
+    PNBI_CUDA(cudaMemcpyAsync(C.y[s], p->signal + start * m, nv * m * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (int rc = launch(C, p, C.B, C.rtr, C.y[s], (long long)nv, C.coef[s], C.rn[s], C.st[s], C.it[s], st)) return rc;
+    PNBI_CUDA(cudaMemcpyAsync(p->coefficients + start * n, C.coef[s], nv * n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    PNBI_CUDA(cudaMemcpyAsync(p->residual + start, C.rn[s], nv * sizeof(double), cudaMemcpyDeviceToHost, st));
+    PNBI_CUDA(cudaMemcpyAsync(p->status + start, C.st[s], nv * sizeof(int), cudaMemcpyDeviceToHost, st));
+    PNBI_CUDA(cudaMemcpyAsync(p->iterations + start, C.it[s], nv * sizeof(int), cudaMemcpyDeviceToHost, st));
+  }
+  for (auto &st : C.streams) PNBI_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int pnb_sizeof_nnls_problem(void) { return (int)sizeof(pnb_nnls_problem); }

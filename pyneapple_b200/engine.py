@@ -190,3 +190,83 @@ def _trf_fit_device(lib, prob, desc, xdata, ydata, p0, lb, ub, n_free, want_cov)
         for t in (b, y, p0, lb, ub):
             t.record_stream(torch.cuda.current_stream(dev))
     return dict(params=params, cov=cov, status=status, nfev=nfev, njev=njev, cost=cost)
+
+
+# ---------------------------------------------------------------------------
+# NNLS
+# ---------------------------------------------------------------------------
+
+
+def rtr_band(reg_matrix: np.ndarray):
+    """Band storage of ``R^T R`` for a (banded) regularisation matrix ``R`` (n x n).
+
+    Returns ``(band (n, 2W+1), W)`` with ``band[j, d + W] = (R^T R)[j, j + d]``.
+    """
+    R = np.asarray(reg_matrix, dtype=np.float64)
+    n = R.shape[1]
+    rtr = R.T @ R
+    nz = np.nonzero(rtr)
+    W = int(np.max(np.abs(nz[0] - nz[1]))) if nz[0].size else 0
+    if W > 8:
+        raise NotImplementedError(f"regularisation matrix with R^T R half-bandwidth {W} > 8")
+    band = np.zeros((n, 2 * W + 1))
+    for d in range(-W, W + 1):
+        j = np.arange(max(0, -d), min(n, n - d))
+        band[j, d + W] = rtr[j, j + d]
+    return band, W
+
+
+def nnls_fit(basis, reg_matrix, signal, max_iter: int, *, device: int = 0, chunk_vox: int = 0,
+             out: dict | None = None):
+    """Batched ``scipy.optimize.nnls([basis; reg_matrix], [signal; 0], maxiter=max_iter)``.
+
+    ``signal``: numpy ``(n_vox, n_b)`` (host path) or CUDA tensor (device path).
+    Returns ``dict(coefficients (n_vox, n_bins), residual, status, iterations)``.
+    """
+    _lib.require_device()
+    lib = _lib.load()
+    B = _as_f64(basis)
+    n_b, n_bins = B.shape
+    band, W = rtr_band(reg_matrix)
+    prob = _lib.NnlsProblem()
+    prob.n_b, prob.n_bins, prob.rtr_halfband, prob.max_iter = n_b, n_bins, W, int(max_iter)
+    if _is_torch_cuda(signal):
+        import torch
+
+        dev = signal.device
+        y = signal.contiguous().to(torch.float64)
+        if y.ndim != 2 or y.shape[1] != n_b:
+            raise ValueError(f"signal must be (n_vox, {n_b}), got {tuple(y.shape)}")
+        n_vox = y.shape[0]
+        Bd = torch.as_tensor(B).to(dev)
+        bd = torch.as_tensor(band).to(dev)
+        coef = torch.empty((n_vox, n_bins), dtype=torch.float64, device=dev)
+        res = torch.empty(n_vox, dtype=torch.float64, device=dev)
+        status = torch.empty(n_vox, dtype=torch.int32, device=dev)
+        iters = torch.empty(n_vox, dtype=torch.int32, device=dev)
+        prob.n_vox = n_vox
+        prob.basis, prob.rtr_band, prob.signal = Bd.data_ptr(), bd.data_ptr(), y.data_ptr()
+        prob.coefficients, prob.residual = coef.data_ptr(), res.data_ptr()
+        prob.status, prob.iterations = status.data_ptr(), iters.data_ptr()
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev)
+            _lib.check(lib.pnb_nnls_fit_device(C.byref(prob), C.c_void_p(stream.cuda_stream)),
+                       "pnb_nnls_fit_device")
+            for t in (Bd, bd, y):
+                t.record_stream(stream)
+        return dict(coefficients=coef, residual=res, status=status, iterations=iters)
+    y = _as_f64(signal)
+    if y.ndim != 2 or y.shape[1] != n_b:
+        raise ValueError(f"signal must be (n_vox, {n_b}), got {y.shape}")
+    n_vox = y.shape[0]
+    o = out or {}
+    coef = o.get("coefficients") if o.get("coefficients") is not None else np.empty((n_vox, n_bins))
+    res = o.get("residual") if o.get("residual") is not None else np.empty(n_vox)
+    status = o.get("status") if o.get("status") is not None else np.empty(n_vox, np.int32)
+    iters = o.get("iterations") if o.get("iterations") is not None else np.empty(n_vox, np.int32)
+    prob.n_vox = n_vox
+    prob.basis, prob.rtr_band, prob.signal = B.ctypes.data, band.ctypes.data, y.ctypes.data
+    prob.coefficients, prob.residual = coef.ctypes.data, res.ctypes.data
+    prob.status, prob.iterations = status.ctypes.data, iters.ctypes.data
+    _lib.check(lib.pnb_nnls_fit_host(C.byref(prob), int(device), int(chunk_vox)), "pnb_nnls_fit_host")
+    return dict(coefficients=coef, residual=res, status=status, iterations=iters)

@@ -4,9 +4,11 @@ from __future__ import annotations
 
 from .base import BaseSolver, PixelResults, _PixelFitResult
 from .curvefit import CurveFitSolver
+from .nnls import NNLSSolver
 
 _REGISTRY: dict[str, type] = {
     "curvefit": CurveFitSolver,
+    "nnls": NNLSSolver,
 }
 
 
@@ -17,4 +19,4 @@ def get_solver(name: str, **kwargs) -> BaseSolver:
     return _REGISTRY[key](**kwargs)
 
 
-__all__ = ["BaseSolver", "CurveFitSolver", "PixelResults", "get_solver"]
+__all__ = ["BaseSolver", "CurveFitSolver", "NNLSSolver", "PixelResults", "get_solver"]

@@ -1,0 +1,95 @@
+"""GPU parity: CUDA NNLS path vs the reference's golden outputs and the C restatement."""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from _util import load
+
+pytestmark = pytest.mark.gpu
+
+from pyneapple_b200 import models  # noqa: E402
+from pyneapple_b200.solvers import NNLSSolver  # noqa: E402
+
+CASES = ["nnls_c3_reg2", "nnls_c3_reg0", "nnls_c3_reg1", "nnls_c3_reg3", "nnls_c3_degenerate",
+         "nnls_c3_maxiter5", "nnls_c3_maxiter20", "nnls_small_reg1"]
+
+
+def _solver(g):
+    model = models.NNLSModel(d_range=tuple(float(v) for v in g["d_range"]), n_bins=int(g["n_bins"]))
+    return NNLSSolver(model=model, reg_order=int(g["reg_order"]), mu=float(g["mu"]),
+                      max_iter=int(g["max_iter"]))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_golden_parity(name):
+    g = load(name)
+    s = _solver(g).fit(g["b"], g["y"])
+    coef, res = s.params_["coefficients"], s.diagnostics_["residual"]
+    success = np.array([pr.success for pr in s.pixel_results_])
+    assert (success == g["success"]).all()
+    assert coef.shape == g["coefficients"].shape
+    assert (coef >= 0).all()
+    # north_star tolerance: coefficients within 1e-6 absolute
+    assert np.abs(coef - g["coefficients"]).max() <= 1e-6
+    assert (np.abs(res - g["residual"]) <= 1e-9 * np.maximum(1.0, g["residual"])).all()
+    fail = ~g["success"]
+    if fail.any():
+        assert (coef[fail] == 0).all()
+
+
+def test_iteration_counts_match_lawson_hanson():
+    """Same active-set path as the classical algorithm: identical iteration counts."""
+    from oracle import c_oracle, ref_port
+
+    g = load("nnls_c3_reg2")
+    s = _solver(g).fit(g["b"], g["y"])
+    bins = ref_port.nnls_bins(0.0008, 0.5, 250)
+    A = np.concatenate([ref_port.nnls_basis(g["b"], bins), ref_port.regularization_matrix(250, 2, 0.02)])
+    Bx = np.concatenate([g["y"], np.zeros((g["y"].shape[0], 250))], axis=1)
+    ref = c_oracle.nnls(A, Bx, 250)
+    assert (s.iterations_ == ref["iters"]).mean() > 0.99
+
+
+def test_against_c_oracle_large():
+    from oracle import c_oracle, ref_port
+    from pyneapple_b200 import synth
+
+    b, y, _ = synth.sample_voxels(synth.CONFIGS["C3"], 4096, z=7)
+    model = models.NNLSModel(d_range=(0.0008, 0.5), n_bins=250)
+    s = NNLSSolver(model=model, reg_order=2, mu=0.02, max_iter=250).fit(b, y)
+    A = np.concatenate([ref_port.nnls_basis(b, model.bins), ref_port.regularization_matrix(250, 2, 0.02)])
+    Bx = np.concatenate([y, np.zeros((y.shape[0], 250))], axis=1)
+    ref = c_oracle.nnls(A, Bx, 250)
+    assert ((s.status_ == 1) == (ref["status"] == 1)).all()
+    assert np.abs(s.params_["coefficients"] - ref["x"]).max() <= 1e-6
+    assert np.abs(s.diagnostics_["residual"] - ref["rnorm"]).max() <= 1e-8
+
+
+def test_large_active_set_overflows_to_global_scratch():
+    """Strong regularisation -> broad spectra -> active sets beyond the shared-memory factor."""
+    from oracle import c_oracle, ref_port
+    from pyneapple_b200 import synth
+
+    b, y, _ = synth.sample_voxels(synth.CONFIGS["C3"], 64, z=3)
+    model = models.NNLSModel(d_range=(0.0008, 0.5), n_bins=250)
+    s = NNLSSolver(model=model, reg_order=2, mu=3.0, max_iter=750).fit(b, y)
+    A = np.concatenate([ref_port.nnls_basis(b, model.bins), ref_port.regularization_matrix(250, 2, 3.0)])
+    Bx = np.concatenate([y, np.zeros((y.shape[0], 250))], axis=1)
+    ref = c_oracle.nnls(A, Bx, 750)
+    assert (ref["x"] > 0).sum(axis=1).max() > 64  # the case does exercise the overflow path
+    assert ((s.status_ == 1) == (ref["status"] == 1)).all()
+    assert np.abs(s.params_["coefficients"] - ref["x"]).max() <= 1e-6
+
+
+def test_single_voxel_and_device_path():
+    import torch
+
+    g = load("nnls_c3_reg2")
+    s = _solver(g)
+    s.fit(g["b"], g["y"][0])
+    assert s.params_["coefficients"].shape == (1, 250)
+    host = s.fit(g["b"], g["y"]).params_["coefficients"].copy()
+    dev = s.fit(g["b"], torch.as_tensor(g["y"]).cuda()).params_["coefficients"]
+    assert np.array_equal(host, dev)
