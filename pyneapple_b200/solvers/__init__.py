@@ -5,10 +5,12 @@ from __future__ import annotations
 from .base import BaseSolver, PixelResults, _PixelFitResult
 from .curvefit import CurveFitSolver
 from .nnls import NNLSSolver
+from .constrained import ConstrainedCurveFitSolver
 
 _REGISTRY: dict[str, type] = {
     "curvefit": CurveFitSolver,
     "nnls": NNLSSolver,
+    "constrained_curvefit": ConstrainedCurveFitSolver,
 }
 
 
@@ -19,4 +21,4 @@ def get_solver(name: str, **kwargs) -> BaseSolver:
     return _REGISTRY[key](**kwargs)
 
 
-__all__ = ["BaseSolver", "CurveFitSolver", "NNLSSolver", "PixelResults", "get_solver"]
+__all__ = ["BaseSolver", "ConstrainedCurveFitSolver", "CurveFitSolver", "NNLSSolver", "PixelResults", "get_solver"]
