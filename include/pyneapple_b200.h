@@ -135,6 +135,25 @@ int pnb_nnls_fit_device(const pnb_nnls_problem *prob, void *cuda_stream);
 int pnb_nnls_fit_host(const pnb_nnls_problem *prob, int device, int64_t chunk_vox);
 int pnb_sizeof_nnls_problem(void);
 
+/*
+ * In-plane (x, y) resampling of an (H, W, inner) array for all `inner` =
+ * slices x channels planes at once, bit-faithful to the per-slice, per-channel
+ * cv2.resize(plane, (W', H'), interpolation) loop of IDEALFitter._interpolate_array
+ * (fitters/ideal.py:299-320).  FP64 cubic is bit-identical to OpenCV.
+ */
+typedef struct pnb_resize_problem {
+  int32_t dtype;             /* 0 float64, 1 float32                            */
+  int32_t method;            /* 0 cv2.INTER_LINEAR, 1 cv2.INTER_CUBIC           */
+  int32_t src_h, src_w;      /* source extent of the two leading axes (x, y)    */
+  int32_t dst_h, dst_w;      /* target extent                                   */
+  int64_t inner;             /* product of the trailing axes (z * channels)     */
+  const void *src;           /* (src_h, src_w, inner) C-contiguous              */
+  void *dst;                 /* (dst_h, dst_w, inner)                           */
+} pnb_resize_problem;
+
+int pnb_resize2d_device(const pnb_resize_problem *prob, void *cuda_stream);
+int pnb_resize2d_host(const pnb_resize_problem *prob, int device);
+
 /* housekeeping */
 int pnb_abi_version(void);
 /* sizeof(struct pnb_trf_problem) as compiled, for binding self-checks */

@@ -241,6 +241,47 @@ def case_nnls_c3():
           success=np.array([pr.success for pr in solver.pixel_results_]))
 
 
+
+
+def case_resize():
+    """cv2.resize outputs for the IDEAL resampler (fitters/ideal.py:299-320).
+
+    Linear goldens are taken with IPP disabled: the opencv-python wheel routes large
+    INTER_LINEAR resizes to Intel IPP (closed arithmetic); OpenCV's own code is the pin.
+    """
+    import cv2
+
+    rng = np.random.default_rng(11)
+    shapes = [(8, 8, 16, 16), (16, 16, 8, 8), (32, 32, 64, 64), (64, 64, 16, 16), (5, 7, 10, 14),
+              (10, 10, 24, 24), (3, 3, 7, 7), (24, 24, 10, 10), (40, 40, 72, 72), (7, 9, 33, 20),
+              (64, 64, 8, 8), (16, 16, 32, 32), (4, 4, 2, 2)]
+    out = {}
+    for n, (h, w, H, W) in enumerate(shapes):
+        a = rng.normal(size=(h, w, 1, 2)) * 1000.0
+        cub = np.zeros((H, W, 1, 2))
+        lin = np.zeros((H, W, 1, 2))
+        for z in range(1):
+            for c in range(2):
+                cub[..., z, c] = cv2.resize(a[..., z, c], (W, H), interpolation=cv2.INTER_CUBIC)
+        cv2.ipp.setUseIPP(False)
+        for z in range(1):
+            for c in range(2):
+                lin[..., z, c] = cv2.resize(a[..., z, c], (W, H), interpolation=cv2.INTER_LINEAR)
+        cv2.ipp.setUseIPP(True)
+        out[f"src{n}"], out[f"cubic{n}"], out[f"linear{n}"] = a, cub, lin
+    # integer label mask on dyadic pyramids (the FP32 path of the IDEAL fitter)
+    seg = synth.ellipsoid_mask((64, 64, 4))[..., None] * 2
+    for n, t in enumerate((4, 8, 16, 32)):
+        s32 = seg.astype(np.float32)
+        o = np.zeros((t, t, 4, 1), np.float32)
+        for z in range(4):
+            o[..., z, 0] = cv2.resize(s32[..., z, 0], (t, t), interpolation=cv2.INTER_CUBIC)
+        out[f"seg{n}"] = o
+    out["seg_src"] = seg
+    out["n_cases"] = len(shapes)
+    _save("resize_cv2", **out)
+
+
 CASES = {k[5:]: v for k, v in globals().items() if k.startswith("case_")}
 
 if __name__ == "__main__":

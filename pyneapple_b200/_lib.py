@@ -79,6 +79,22 @@ class NnlsProblem(C.Structure):
     ]
 
 
+class ResizeProblem(C.Structure):
+    """Mirror of ``struct pnb_resize_problem``."""
+
+    _fields_ = [
+        ("dtype", C.c_int32),
+        ("method", C.c_int32),
+        ("src_h", C.c_int32),
+        ("src_w", C.c_int32),
+        ("dst_h", C.c_int32),
+        ("dst_w", C.c_int32),
+        ("inner", C.c_int64),
+        ("src", C.c_void_p),
+        ("dst", C.c_void_p),
+    ]
+
+
 def build(verbose: bool = False, t1: bool = True) -> str:
     """Compile ``libpnb200.so`` for sm_100a with nvcc (works without a GPU)."""
     cmd = ["make", "-C", CSRC, "-j", str(min(16, os.cpu_count() or 4))]
@@ -115,6 +131,10 @@ def load():
     lib.pnb_nnls_fit_device.restype = C.c_int
     lib.pnb_nnls_fit_host.argtypes = [C.POINTER(NnlsProblem), C.c_int, C.c_int64]
     lib.pnb_nnls_fit_host.restype = C.c_int
+    lib.pnb_resize2d_device.argtypes = [C.POINTER(ResizeProblem), C.c_void_p]
+    lib.pnb_resize2d_device.restype = C.c_int
+    lib.pnb_resize2d_host.argtypes = [C.POINTER(ResizeProblem), C.c_int]
+    lib.pnb_resize2d_host.restype = C.c_int
     lib.pnb_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_int64]
     lib.pnb_host_free.argtypes = [C.c_void_p]
     lib.pnb_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
