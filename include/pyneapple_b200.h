@@ -101,6 +101,8 @@ typedef struct pnb_trf_problem {
   int32_t *nfev;             /* (n_vox) residual evaluations, SciPy's count     */
   int32_t *njev;             /* (n_vox) or NULL                                */
   double *cost;              /* (n_vox) 0.5 * ||f||^2 at the solution, or NULL */
+  double *r_squared;         /* (n_vox) R^2 of fitters/base.py:142-186 at the returned
+                                parameters (NaN for a constant signal), or NULL  */
 } pnb_trf_problem;
 
 int pnb_trf_fit_device(const pnb_trf_problem *prob, void *cuda_stream);
@@ -129,6 +131,7 @@ typedef struct pnb_nnls_problem {
   int32_t *status;           /* (n_vox) 1 converged; 3 iteration cap, 2 non-finite
                                 signal: coefficients = 0, residual = ||signal|| */
   int32_t *iterations;       /* (n_vox) Lawson-Hanson iteration count           */
+  double *r_squared;         /* (n_vox) R^2 of the un-regularised prediction, or NULL */
 } pnb_nnls_problem;
 
 int pnb_nnls_fit_device(const pnb_nnls_problem *prob, void *cuda_stream);

@@ -282,6 +282,57 @@ def case_resize():
     _save("resize_cv2", **out)
 
 
+def _small_volume(shape=(32, 32, 2), seed=4):
+    """A C4-style biexp volume with smooth parameter fields, small enough for the CPU reference."""
+    cfg = synth.Config(**{**synth.CONFIGS["C4"].__dict__, "shape": shape, "seed": seed})
+    b, img, truth = synth.make_volume(cfg)
+    x = (np.arange(shape[0]) - (shape[0] - 1) / 2) / (shape[0] / 2)
+    y = (np.arange(shape[1]) - (shape[1] - 1) / 2) / (shape[1] / 2)
+    mask = ((x[:, None] ** 2 + y[None, :] ** 2) <= 0.85).astype(np.int64)
+    seg = np.repeat(mask[:, :, None], shape[2], axis=2)
+    return cfg, b, img, seg
+
+
+def case_fitters():
+    """PixelWise / IDEAL / Segmented fitters of the reference on a 32 x 32 x 2 volume."""
+    from pyneapple.fitters import IDEALFitter, PixelWiseFitter, SegmentedFitter
+
+    cfg, b, img, seg = _small_volume()
+    p0, bounds = cfg.p0, cfg.bounds
+
+    def solver():
+        return CurveFitSolver(model=BiExpModel(fit_s0=True), max_iter=250, tol=1e-8, p0=p0, bounds=bounds)
+
+    # pixelwise with a mask
+    f = PixelWiseFitter(solver=solver()).fit(b, img, seg)
+    r = f.results_
+    _save("fitter_pixelwise", b=b, image=img, seg=seg, names=np.array(list(r.params)),
+          params=np.stack([r.params[n] for n in r.params]), success=r.success, r_squared=r.r_squared,
+          covariance=r.covariance, pixel_indices=np.array(r.pixel_indices),
+          predict=f.predict(b))
+    # IDEAL, cubic, 4 levels
+    steps = np.array([[4, 4], [8, 8], [16, 16], [32, 32]])
+    tol = {"S0": 0.5, "f1": 0.2, "D1": 0.2, "D2": 0.2}
+    fi = IDEALFitter(solver=solver(), dim_steps=steps, step_tol=tol, ideal_dims=2,
+                     segmentation_threshold=0.2, interpolation_method="cubic").fit(b, img, seg)
+    ri = fi.results_
+    out = {f"step{i}": m for i, m in enumerate(fi.step_params)}
+    _save("fitter_ideal", b=b, image=img, seg=seg, dim_steps=steps, names=np.array(list(ri.params)),
+          params=np.stack([ri.params[n] for n in ri.params]), success=ri.success, r_squared=ri.r_squared,
+          pixel_indices=np.array(ri.pixel_indices), n_steps=len(fi.step_params), **out)
+    # segmented: monoexp on b >= 200 -> D fixed as the slow D1 of the biexp
+    s1 = CurveFitSolver(model=MonoExpModel(), max_iter=250, tol=1e-8, p0={"S0": 1000.0, "D": 0.001},
+                        bounds={"S0": (1.0, 5000.0), "D": (1e-5, 0.003)})
+    fs = SegmentedFitter(step1_solver=s1, step2_solver=solver(), step1_bvalue_range=(200, None),
+                         fixed_from_step1=["D"], param_mapping={"D": "D1"}).fit(b, img, seg)
+    rs = fs.results_
+    _save("fitter_segmented", b=b, image=img, seg=seg,
+          names=np.array(list(fs.fitted_params_)), params=np.stack([fs.fitted_params_[n] for n in fs.fitted_params_]),
+          step1_names=np.array(list(fs.step1_params_)),
+          step1_params=np.stack([fs.step1_params_[n] for n in fs.step1_params_]),
+          success=rs.success, r_squared=rs.r_squared, step1_success=fs.step1_result_.success)
+
+
 CASES = {k[5:]: v for k, v in globals().items() if k.startswith("case_")}
 
 if __name__ == "__main__":

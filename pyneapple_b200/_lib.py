@@ -57,6 +57,7 @@ class TrfProblem(C.Structure):
         ("nfev", C.c_void_p),
         ("njev", C.c_void_p),
         ("cost", C.c_void_p),
+        ("r_squared", C.c_void_p),
     ]
 
 
@@ -76,6 +77,7 @@ class NnlsProblem(C.Structure):
         ("residual", C.c_void_p),
         ("status", C.c_void_p),
         ("iterations", C.c_void_p),
+        ("r_squared", C.c_void_p),
     ]
 
 

@@ -160,7 +160,7 @@ extern "C" int pnb_trf_fit_device(const pnb_trf_problem *p, void *cuda_stream) {
   a.bd_vox_stride = p->bounds_per_voxel ? 1 : 0;
   a.opt = make_options(p);
   a.params = p->params; a.cov = p->cov; a.status = p->status; a.nfev = p->nfev;
-  a.njev = p->njev; a.cost = p->cost;
+  a.njev = p->njev; a.cost = p->cost; a.r2 = p->r_squared;
   if (int rc = next_counter(&a.counter)) return rc;
   cudaError_t e = trf_launcher(p->model_id, p->t1_mode)(&a, stream);
   if (e != cudaSuccess) return cuda_fail(e, "trf kernel launch");
@@ -176,7 +176,7 @@ namespace {
 struct Slot {
   cudaStream_t stream = nullptr;
   double *y = nullptr, *p0 = nullptr, *lb = nullptr, *ub = nullptr;
-  double *params = nullptr, *cov = nullptr, *cost = nullptr;
+  double *params = nullptr, *cov = nullptr, *cost = nullptr, *r2 = nullptr;
   int *status = nullptr, *nfev = nullptr, *njev = nullptr;
   unsigned long long *counter = nullptr;
   size_t cap_y = 0, cap_p = 0, cap_cov = 0, cap_v = 0;
@@ -246,7 +246,9 @@ extern "C" int pnb_trf_fit_host(const pnb_trf_problem *p, int device, int64_t ch
       if (s.status) PNB_CUDA(cudaFree(s.status));
       if (s.nfev) PNB_CUDA(cudaFree(s.nfev));
       if (s.njev) PNB_CUDA(cudaFree(s.njev));
+      if (s.r2) PNB_CUDA(cudaFree(s.r2));
       PNB_CUDA(cudaMalloc(&s.cost, C * sizeof(double)));
+      PNB_CUDA(cudaMalloc(&s.r2, C * sizeof(double)));
       PNB_CUDA(cudaMalloc(&s.status, C * sizeof(int)));
       PNB_CUDA(cudaMalloc(&s.nfev, C * sizeof(int)));
       PNB_CUDA(cudaMalloc(&s.njev, C * sizeof(int)));
@@ -296,6 +298,7 @@ extern "C" int pnb_trf_fit_host(const pnb_trf_problem *p, int device, int64_t ch
     a.opt = opt;
     a.params = s.params; a.cov = p->cov ? s.cov : nullptr; a.status = s.status; a.nfev = s.nfev;
     a.njev = p->njev ? s.njev : nullptr; a.cost = p->cost ? s.cost : nullptr;
+    a.r2 = p->r_squared ? s.r2 : nullptr;
     a.counter = s.counter;
     cudaError_t e = launch(&a, s.stream);
     if (e != cudaSuccess) return cuda_fail(e, "trf kernel launch");
@@ -311,6 +314,8 @@ extern "C" int pnb_trf_fit_host(const pnb_trf_problem *p, int device, int64_t ch
       PNB_CUDA(cudaMemcpyAsync(p->njev + start, s.njev, sizeof(int) * n, cudaMemcpyDeviceToHost, s.stream));
     if (p->cost)
       PNB_CUDA(cudaMemcpyAsync(p->cost + start, s.cost, sizeof(double) * n, cudaMemcpyDeviceToHost, s.stream));
+    if (p->r_squared)
+      PNB_CUDA(cudaMemcpyAsync(p->r_squared + start, s.r2, sizeof(double) * n, cudaMemcpyDeviceToHost, s.stream));
   }
   for (auto &s : P.slots) PNB_CUDA(cudaStreamSynchronize(s.stream));
   return 0;

@@ -19,7 +19,7 @@ struct NnlsCtx {
   size_t scratch_cap = 0;
   // host pipeline
   cudaStream_t streams[2] = {nullptr, nullptr};
-  double *y[2] = {nullptr, nullptr}, *coef[2] = {nullptr, nullptr}, *rn[2] = {nullptr, nullptr};
+  double *y[2] = {nullptr, nullptr}, *coef[2] = {nullptr, nullptr}, *rn[2] = {nullptr, nullptr}, *r2[2] = {nullptr, nullptr};
   int *st[2] = {nullptr, nullptr}, *it[2] = {nullptr, nullptr};
   size_t cap_vox = 0, cap_m = 0, cap_n = 0;
   double *B = nullptr, *rtr = nullptr;
@@ -49,7 +49,7 @@ int pick_kmax(int m, int n, int W) {
 }
 
 int launch(NnlsCtx &C, const pnb_nnls_problem *p, const double *B, const double *rtr, const double *y,
-           long long n_vox, double *coef, double *rn, int *st, int *it, cudaStream_t stream) {
+           long long n_vox, double *coef, double *rn, int *st, int *it, double *r2, cudaStream_t stream) {
   const int m = p->n_b, n = p->n_bins, W = p->rtr_halfband;
   const int kmax = pick_kmax(m, n, W);
   const size_t smem = pnb::nnls_smem_bytes(m, n, W, kmax, kWarps);
@@ -78,7 +78,7 @@ int launch(NnlsCtx &C, const pnb_nnls_problem *p, const double *B, const double 
   }
   pnb::NnlsDeviceArgs a;
   a.m = m; a.n = n; a.W = W; a.maxiter = p->max_iter; a.n_vox = n_vox;
-  a.B = B; a.rtr = rtr; a.y = y; a.coef = coef; a.rnorm = rn; a.status = st; a.iters = it;
+  a.B = B; a.rtr = rtr; a.y = y; a.coef = coef; a.rnorm = rn; a.status = st; a.iters = it; a.r2 = r2;
   a.counter = C.counters + C.next;
   C.next = (C.next + 1) % 64;
   a.scratch = C.scratch; a.kmax = kmax;
@@ -98,7 +98,7 @@ extern "C" int pnb_nnls_fit_device(const pnb_nnls_problem *p, void *cuda_stream)
   PNBI_CUDA(cudaGetDevice(&dev));
   std::lock_guard<std::mutex> lk(g_mu);
   return launch(g_ctx[dev & 15], p, p->basis, p->rtr_band, p->signal, p->n_vox, p->coefficients,
-                p->residual, p->status, p->iterations, (cudaStream_t)cuda_stream);
+                p->residual, p->status, p->iterations, p->r_squared, (cudaStream_t)cuda_stream);
 }
 
 extern "C" int pnb_nnls_fit_host(const pnb_nnls_problem *p, int device, int64_t chunk_vox) {
@@ -116,10 +116,11 @@ extern "C" int pnb_nnls_fit_host(const pnb_nnls_problem *p, int device, int64_t 
     for (auto &s : C.streams) PNBI_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
   if (Cn > C.cap_vox || (size_t)m > C.cap_m || (size_t)n > C.cap_n) {
     for (int s = 0; s < 2; s++) {
-      if (C.y[s]) { cudaFree(C.y[s]); cudaFree(C.coef[s]); cudaFree(C.rn[s]); cudaFree(C.st[s]); cudaFree(C.it[s]); }
+      if (C.y[s]) { cudaFree(C.y[s]); cudaFree(C.coef[s]); cudaFree(C.rn[s]); cudaFree(C.r2[s]); cudaFree(C.st[s]); cudaFree(C.it[s]); }
       PNBI_CUDA(cudaMalloc(&C.y[s], Cn * m * sizeof(double)));
       PNBI_CUDA(cudaMalloc(&C.coef[s], Cn * n * sizeof(double)));
       PNBI_CUDA(cudaMalloc(&C.rn[s], Cn * sizeof(double)));
+      PNBI_CUDA(cudaMalloc(&C.r2[s], Cn * sizeof(double)));
       PNBI_CUDA(cudaMalloc(&C.st[s], Cn * sizeof(int)));
       PNBI_CUDA(cudaMalloc(&C.it[s], Cn * sizeof(int)));
     }
@@ -143,9 +144,11 @@ extern "C" int pnb_nnls_fit_host(const pnb_nnls_problem *p, int device, int64_t 
     const size_t nv = (NV - start < Cn) ? NV - start : Cn;
     cudaStream_t st = C.streams[s];
     PNBI_CUDA(cudaMemcpyAsync(C.y[s], p->signal + start * m, nv * m * sizeof(double), cudaMemcpyHostToDevice, st));
-    if (int rc = launch(C, p, C.B, C.rtr, C.y[s], (long long)nv, C.coef[s], C.rn[s], C.st[s], C.it[s], st)) return rc;
+    if (int rc = launch(C, p, C.B, C.rtr, C.y[s], (long long)nv, C.coef[s], C.rn[s], C.st[s], C.it[s], p->r_squared ? C.r2[s] : nullptr, st)) return rc;
     PNBI_CUDA(cudaMemcpyAsync(p->coefficients + start * n, C.coef[s], nv * n * sizeof(double), cudaMemcpyDeviceToHost, st));
     PNBI_CUDA(cudaMemcpyAsync(p->residual + start, C.rn[s], nv * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (p->r_squared)
+      PNBI_CUDA(cudaMemcpyAsync(p->r_squared + start, C.r2[s], nv * sizeof(double), cudaMemcpyDeviceToHost, st));
     PNBI_CUDA(cudaMemcpyAsync(p->status + start, C.st[s], nv * sizeof(int), cudaMemcpyDeviceToHost, st));
     PNBI_CUDA(cudaMemcpyAsync(p->iterations + start, C.it[s], nv * sizeof(int), cudaMemcpyDeviceToHost, st));
   }

@@ -48,6 +48,7 @@ struct NnlsDeviceArgs {
   double *rnorm;         // (n_vox)
   int *status;           // (n_vox) 1 ok, 3 iteration cap reached (-> zeros, ||y||), 2 non-finite input
   int *iters;            // (n_vox)
+  double *r2;            // (n_vox) or nullptr: 1 - ||y - B x||^2 / SS_tot
   unsigned long long *counter;
   double *scratch;       // per-warp overflow storage, (n (n+1) / 2 + 5 n) doubles per warp
   int kmax;              // active-set size that fits the shared-memory factor
@@ -369,8 +370,20 @@ __global__ void __launch_bounds__(WARPS * 32) nnls_kernel(const NnlsDeviceArgs a
           part += xj * acc;
         }
       }
+      double top = 0.0;
+      for (int b = lane; b < m; b += 32) top += rs[b] * rs[b];
+      top = warp_sum(top);
       const double tot = warp_sum(part);
       if (lane == 0) a.rnorm[vox] = sqrt(tot > 0.0 ? tot : 0.0);
+      if (a.r2) {
+        double sm = 0.0;
+        for (int b = lane; b < m; b += 32) sm += ys[b];
+        const double mean = warp_sum(sm) / (double)m;
+        double st = 0.0;
+        for (int b = lane; b < m; b += 32) { const double d = ys[b] - mean; st += d * d; }
+        st = warp_sum(st);
+        if (lane == 0) a.r2[vox] = (st > 0.0) ? 1.0 - top / st : nan("");
+      }
     } else {
       // failure (nnls_solver.py:201-210): zeros and ||[y; 0]||
       double part = 0.0;
@@ -378,6 +391,15 @@ __global__ void __launch_bounds__(WARPS * 32) nnls_kernel(const NnlsDeviceArgs a
       for (int j = lane; j < n; j += 32) out[j] = 0.0;
       const double tot = warp_sum(part);
       if (lane == 0) a.rnorm[vox] = sqrt(tot);
+      if (a.r2) {  // prediction is zero
+        double sm = 0.0;
+        for (int b = lane; b < m; b += 32) sm += ys[b];
+        const double mean = warp_sum(sm) / (double)m;
+        double st = 0.0;
+        for (int b = lane; b < m; b += 32) { const double d = ys[b] - mean; st += d * d; }
+        st = warp_sum(st);
+        if (lane == 0) a.r2[vox] = (st > 0.0) ? 1.0 - tot / st : nan("");
+      }
     }
     if (lane == 0) { a.status[vox] = mode; a.iters[vox] = iter; }
     __syncwarp();

@@ -46,6 +46,7 @@ struct TrfDeviceArgs {
   int *nfev;             // (n_vox)
   int *njev;             // (n_vox) or nullptr
   double *cost;          // (n_vox) or nullptr
+  double *r2;            // (n_vox) or nullptr: 1 - SS_res / SS_tot at the returned parameters
   unsigned long long *counter;  // work counter, zeroed before launch
 };
 
@@ -229,6 +230,25 @@ __global__ void __launch_bounds__(BLOCK) trf_kernel(const TrfDeviceArgs a) {
       a.nfev[vox] = S.nfev;
       if (a.njev) a.njev[vox] = S.njev;
       if (a.cost) a.cost[vox] = (ok || S.status == kStMaxNfev) ? S.cost : nan("");
+      if (a.r2) {
+        // fitters/base.py:142-186: R^2 = 1 - SS_res / SS_tot, NaN when the signal is constant
+        double mean = 0.0;
+        for (int r = 0; r < m; r++) mean += my_y[r * BLOCK];
+        mean /= (double)m;
+        double ss_tot = 0.0;
+        for (int r = 0; r < m; r++) { const double d = my_y[r * BLOCK] - mean; ss_tot += d * d; }
+        double ss_res = 2.0 * S.cost;
+        if (!ok) {  // the returned parameters are p0: evaluate the model there
+          double p0v[N], c0, g0[N], A0[N][N];
+#pragma unroll
+          for (int k = 0; k < N; k++) p0v[k] = my_p0[k * BLOCK];
+          TrfOptions O2 = O;
+          O2.jac_mode = 0;
+          trf_evaluate<M>(p0v, O2, m, yb, my_lb, my_ub, BLOCK, c0, g0, A0);
+          ss_res = 2.0 * c0;
+        }
+        a.r2[vox] = (ss_tot > 0.0) ? 1.0 - ss_res / ss_tot : nan("");
+      }
       if (a.cov) {
         double *cv = a.cov + vox * (long long)(n_free * n_free);
         if (ok) {

@@ -136,16 +136,18 @@ def trf_fit(
     nfev = o.get("nfev") if o.get("nfev") is not None else np.empty(n_vox, np.int32)
     njev = o.get("njev") if o.get("njev") is not None else np.empty(n_vox, np.int32)
     cost = o.get("cost") if o.get("cost") is not None else np.empty(n_vox)
-    keep = (b, y, p0, lb, ub, params, cov, status, nfev, njev, cost)
+    r2 = o.get("r2") if o.get("r2") is not None else np.empty(n_vox)
+    keep = (b, y, p0, lb, ub, params, cov, status, nfev, njev, cost, r2)
     prob.xdata, prob.ydata = b.ctypes.data, y.ctypes.data
     prob.p0, prob.lb, prob.ub = p0.ctypes.data, lb.ctypes.data, ub.ctypes.data
     prob.params = params.ctypes.data
     prob.cov = cov.ctypes.data if cov is not None else None
     prob.status, prob.nfev = status.ctypes.data, nfev.ctypes.data
     prob.njev, prob.cost = njev.ctypes.data, cost.ctypes.data
+    prob.r_squared = r2.ctypes.data
     _lib.check(lib.pnb_trf_fit_host(C.byref(prob), int(device), int(chunk_vox)), "pnb_trf_fit_host")
     del keep
-    return dict(params=params, cov=cov, status=status, nfev=nfev, njev=njev, cost=cost)
+    return dict(params=params, cov=cov, status=status, nfev=nfev, njev=njev, cost=cost, r2=r2)
 
 
 def _trf_fit_device(lib, prob, desc, xdata, ydata, p0, lb, ub, n_free, want_cov):
@@ -177,19 +179,21 @@ def _trf_fit_device(lib, prob, desc, xdata, ydata, p0, lb, ub, n_free, want_cov)
     nfev = torch.empty(n_vox, dtype=torch.int32, device=dev)
     njev = torch.empty(n_vox, dtype=torch.int32, device=dev)
     cost = torch.empty(n_vox, dtype=torch.float64, device=dev)
+    r2 = torch.empty(n_vox, dtype=torch.float64, device=dev)
     prob.xdata, prob.ydata = b.data_ptr(), y.data_ptr()
     prob.p0, prob.lb, prob.ub = p0.data_ptr(), lb.data_ptr(), ub.data_ptr()
     prob.params = params.data_ptr()
     prob.cov = cov.data_ptr() if cov is not None else None
     prob.status, prob.nfev = status.data_ptr(), nfev.data_ptr()
     prob.njev, prob.cost = njev.data_ptr(), cost.data_ptr()
+    prob.r_squared = r2.data_ptr()
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
         _lib.check(lib.pnb_trf_fit_device(C.byref(prob), C.c_void_p(stream)), "pnb_trf_fit_device")
         # inputs must outlive the enqueued kernel
         for t in (b, y, p0, lb, ub):
             t.record_stream(torch.cuda.current_stream(dev))
-    return dict(params=params, cov=cov, status=status, nfev=nfev, njev=njev, cost=cost)
+    return dict(params=params, cov=cov, status=status, nfev=nfev, njev=njev, cost=cost, r2=r2)
 
 
 # ---------------------------------------------------------------------------
@@ -244,17 +248,19 @@ def nnls_fit(basis, reg_matrix, signal, max_iter: int, *, device: int = 0, chunk
         res = torch.empty(n_vox, dtype=torch.float64, device=dev)
         status = torch.empty(n_vox, dtype=torch.int32, device=dev)
         iters = torch.empty(n_vox, dtype=torch.int32, device=dev)
+        r2 = torch.empty(n_vox, dtype=torch.float64, device=dev)
         prob.n_vox = n_vox
         prob.basis, prob.rtr_band, prob.signal = Bd.data_ptr(), bd.data_ptr(), y.data_ptr()
         prob.coefficients, prob.residual = coef.data_ptr(), res.data_ptr()
         prob.status, prob.iterations = status.data_ptr(), iters.data_ptr()
+        prob.r_squared = r2.data_ptr()
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev)
             _lib.check(lib.pnb_nnls_fit_device(C.byref(prob), C.c_void_p(stream.cuda_stream)),
                        "pnb_nnls_fit_device")
             for t in (Bd, bd, y):
                 t.record_stream(stream)
-        return dict(coefficients=coef, residual=res, status=status, iterations=iters)
+        return dict(coefficients=coef, residual=res, status=status, iterations=iters, r2=r2)
     y = _as_f64(signal)
     if y.ndim != 2 or y.shape[1] != n_b:
         raise ValueError(f"signal must be (n_vox, {n_b}), got {y.shape}")
@@ -264,9 +270,11 @@ def nnls_fit(basis, reg_matrix, signal, max_iter: int, *, device: int = 0, chunk
     res = o.get("residual") if o.get("residual") is not None else np.empty(n_vox)
     status = o.get("status") if o.get("status") is not None else np.empty(n_vox, np.int32)
     iters = o.get("iterations") if o.get("iterations") is not None else np.empty(n_vox, np.int32)
+    r2 = o.get("r2") if o.get("r2") is not None else np.empty(n_vox)
     prob.n_vox = n_vox
     prob.basis, prob.rtr_band, prob.signal = B.ctypes.data, band.ctypes.data, y.ctypes.data
     prob.coefficients, prob.residual = coef.ctypes.data, res.ctypes.data
     prob.status, prob.iterations = status.ctypes.data, iters.ctypes.data
+    prob.r_squared = r2.ctypes.data
     _lib.check(lib.pnb_nnls_fit_host(C.byref(prob), int(device), int(chunk_vox)), "pnb_nnls_fit_host")
-    return dict(coefficients=coef, residual=res, status=status, iterations=iters)
+    return dict(coefficients=coef, residual=res, status=status, iterations=iters, r2=r2)

@@ -162,6 +162,8 @@ class ConstrainedCurveFitSolver(CurveFitSolver):
         res["nfev"][idx] += r2["nfev"]
         res["status"][idx[~ok]] = 0
         res["cost"][idx[ok]] = r2["cost"][ok]
+        if res.get("r2") is not None:
+            res["r2"][idx[ok]] = r2["r2"][ok]  # same signal, same prediction on the face
         if res["cov"] is not None:
             # J^T J is singular on the face (dS/dD3 = -b f3 e3 = 0): np.linalg.inv raises ->
             # NaN covariance (constrained_curvefit.py:300-305)

@@ -95,6 +95,7 @@ class CurveFitSolver(BaseSolver):
         self.status_ = None
         self.nfev_ = None
         self.cost_ = None
+        self.r_squared_ = None
 
     # ------------------------------------------------------------------
     def fit(self, xdata, ydata, p0=None, bounds=None, pixel_fixed_params=None, **fit_kwargs):
@@ -192,6 +193,77 @@ class CurveFitSolver(BaseSolver):
         self._free_rows = [all_names.index(n) for n in free_names]
         return res, free_names
 
+    # ------------------------------------------------------------------
+    def fit_device(self, xdata, y_dev, p0=None, bounds=None, pixel_fixed_params=None, want_cov=None):
+        """Device-resident fit for the IDEAL / segmented drivers: nothing leaves the GPU.
+
+        ``y_dev (n_pix, n_b)``, optional ``p0 (n_params, n_pix)``, ``bounds = (lb, ub)`` and
+        ``pixel_fixed_params {name: (n_pix,)}`` are CUDA tensors (rows over
+        ``model.param_names``).  Returns the engine's dict of CUDA tensors plus
+        ``free_names``; call :meth:`store_device_result` to publish it as ``params_`` etc.
+        """
+        import torch
+
+        desc = self._desc
+        model_names = list(self.model.param_names)
+        all_names = list(desc.all_names)
+        n_pix = y_dev.shape[0]
+        dev = y_dev.device
+        pix_fixed = {k: v for k, v in (pixel_fixed_params or {}).items() if k in all_names}
+        fixed_names = set(desc.fixed) | set(pix_fixed)
+        frozen = engine.frozen_mask(desc, fixed_names)
+        free_names = [n for n in model_names if n not in pix_fixed]
+        p0_def = V.p0_vector(self.p0, model_names)
+        lb_def, ub_def = V.bounds_vectors(self.bounds, model_names)
+
+        def assemble(src, default, filler, is_p0):
+            rows, per_voxel = [], False
+            for name in all_names:
+                if name in desc.fixed:
+                    rows.append(float(desc.fixed[name]) if is_p0 else filler)
+                elif name in pix_fixed:
+                    if is_p0:
+                        rows.append(pix_fixed[name].to(device=dev, dtype=torch.float64))
+                        per_voxel = True
+                    else:
+                        rows.append(filler)
+                elif src is not None:
+                    rows.append(src[model_names.index(name)])
+                    per_voxel = True
+                else:
+                    rows.append(float(default[model_names.index(name)]))
+            if not per_voxel:
+                return np.array(rows, dtype=float)
+            return torch.stack([r if isinstance(r, torch.Tensor)
+                                else torch.full((n_pix,), float(r), dtype=torch.float64, device=dev)
+                                for r in rows])
+
+        P0 = assemble(p0, p0_def, 0.0, True)
+        LB = assemble(None if bounds is None else bounds[0], lb_def, -np.inf, False)
+        UB = assemble(None if bounds is None else bounds[1], ub_def, np.inf, False)
+        if self.jac == "reference":
+            jac_mode = engine.JAC_ANALYTIC if fixed_names else engine.JAC_TWO_POINT
+        else:
+            jac_mode = engine.JAC_ANALYTIC if self.jac == "analytic" else engine.JAC_TWO_POINT
+        res = engine.trf_fit(
+            desc, np.asarray(xdata, float), y_dev, P0, LB, UB, frozen, max_nfev=self.max_iter,
+            ftol=self.tol, xtol=self.solver_kwargs.get("xtol", 1e-8),
+            gtol=self.solver_kwargs.get("gtol", 1e-8), jac_mode=jac_mode,
+            want_cov=self.want_cov if want_cov is None else want_cov, device=self.device,
+        )
+        res["free_names"] = free_names
+        res["free_rows"] = [all_names.index(n) for n in free_names]
+        return res
+
+    def store_device_result(self, res):
+        """Copy a :meth:`fit_device` result to the host and publish it like ``fit`` does."""
+        self._reset_state()
+        free_names, self._free_rows = res["free_names"], res["free_rows"]
+        host = {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in res.items()
+                if k not in ("free_names", "free_rows")}
+        self._store(host, free_names, host["params"].shape[1])
+        return self
+
     def _pinned_out(self, n_all, n_free, n_pixels, ydata):
         if not self.pinned_outputs or engine._is_torch_cuda(ydata):
             return None
@@ -205,6 +277,7 @@ class CurveFitSolver(BaseSolver):
                 nfev=_lib.pinned_empty((n_pixels,), np.int32),
                 njev=_lib.pinned_empty((n_pixels,), np.int32),
                 cost=_lib.pinned_empty((n_pixels,)),
+                r2=_lib.pinned_empty((n_pixels,)),
             )
             if self.want_cov:
                 out["cov"] = _lib.pinned_empty((n_pixels, n_free, n_free))
@@ -217,6 +290,7 @@ class CurveFitSolver(BaseSolver):
         status = res["status"]
         self.status_, self.nfev_, self.cost_ = status, res["nfev"], res["cost"]
         self.njev_ = res["njev"]
+        self.r_squared_ = res.get("r2")
         success = status > 0
         if pcov is None:
             pcov = np.full((n_pixels, len(free_names), len(free_names)), np.nan)

@@ -50,6 +50,7 @@ class NNLSSolver(BaseSolver):
         self.mu = mu
         self.status_ = None
         self.iterations_ = None
+        self.r_squared_ = None
 
     def get_regularization_matrix(self) -> np.ndarray:
         return regularization_matrix(self.model.n_bins, self.reg_order, self.mu)
@@ -81,7 +82,8 @@ class NNLSSolver(BaseSolver):
                     coefficients=_lib.pinned_empty((self.n_pixels, basis.shape[1])),
                     residual=_lib.pinned_empty((self.n_pixels,)),
                     status=_lib.pinned_empty((self.n_pixels,), np.int32),
-                    iterations=_lib.pinned_empty((self.n_pixels,), np.int32)))
+                    iterations=_lib.pinned_empty((self.n_pixels,), np.int32),
+                    r2=_lib.pinned_empty((self.n_pixels,))))
             out = self._out_cache[1]
         res = engine.nnls_fit(basis, reg, signal, self.max_iter, device=self.device,
                               chunk_vox=self.chunk_vox, out=out)
@@ -89,6 +91,7 @@ class NNLSSolver(BaseSolver):
             res = {k: v.cpu().numpy() for k, v in res.items()}
         status = res["status"]
         self.status_, self.iterations_ = status, res["iterations"]
+        self.r_squared_ = res.get("r2")
         success = status == 1
         self.pixel_results_ = PixelResults(
             params=res["coefficients"], covariance=None, success=success,

@@ -1,0 +1,136 @@
+"""GPU: fitters (pixelwise, IDEAL, segmented, segmentation-wise) vs the reference's fitters."""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from _util import load, rel_err
+
+pytestmark = pytest.mark.gpu
+
+from pyneapple_b200 import models, synth  # noqa: E402
+from pyneapple_b200.fitters import (IDEALFitter, PixelWiseFitter, SegmentationWiseFitter,  # noqa: E402
+                                    SegmentedFitter)
+from pyneapple_b200.solvers import CurveFitSolver, NNLSSolver  # noqa: E402
+
+CFG = synth.CONFIGS["C4"]
+
+
+def _solver(**kw):
+    return CurveFitSolver(model=models.BiExpModel(fit_s0=True), max_iter=250, tol=1e-8, p0=CFG.p0,
+                          bounds=CFG.bounds, **kw)
+
+
+def test_pixelwise_matches_reference_fitter():
+    g = load("fitter_pixelwise")
+    f = PixelWiseFitter(solver=_solver()).fit(g["b"], g["image"], g["seg"])
+    r = f.results_
+    names = [str(n) for n in g["names"]]
+    assert list(r.params) == names
+    got = np.stack([r.params[n] for n in names])
+    assert (r.success == g["success"]).all()
+    assert rel_err(got, g["params"]).max() < 1e-4
+    assert np.array_equal(np.array(list(f.pixel_indices)), g["pixel_indices"])
+    assert np.nanmax(np.abs(r.r_squared - g["r_squared"])) < 1e-9
+    assert r.covariance.shape == g["covariance"].shape
+    assert r.n_pixels == got.shape[1] and r.solver_name == "CurveFitSolver" and r.model_name == "BiExpModel"
+    assert r.n_iterations is None and r.messages is None and r.residuals is None
+    pred = f.predict(g["b"])
+    assert pred.shape == g["predict"].shape
+    np.testing.assert_allclose(pred, g["predict"], rtol=1e-4, atol=1e-6)
+    # no mask: every voxel, same order as image.reshape(-1, n_b)
+    f2 = PixelWiseFitter(solver=_solver()).fit(g["b"], g["image"][:4, :4])
+    assert f2.results_.n_pixels == 4 * 4 * g["image"].shape[2]
+    assert list(f2.pixel_indices)[:3] == [(0, 0, 0), (0, 0, 1), (0, 1, 0)]
+
+
+def test_ideal_matches_reference_level_by_level():
+    g = load("fitter_ideal")
+    tol = {"S0": 0.5, "f1": 0.2, "D1": 0.2, "D2": 0.2}
+    f = IDEALFitter(solver=_solver(), dim_steps=g["dim_steps"], step_tol=tol, ideal_dims=2,
+                    segmentation_threshold=0.2, interpolation_method="cubic").fit(g["b"], g["image"], g["seg"])
+    n_steps = int(g["n_steps"])
+    assert len(f.step_params) == n_steps
+    for i in range(n_steps):
+        ref = g[f"step{i}"]
+        got = f.step_params[i]
+        assert got.shape == ref.shape
+        assert np.array_equal(got != 0, ref != 0), f"level {i}: fitted-voxel mask differs"
+        nz = ref != 0
+        assert rel_err(got[nz], ref[nz]).max() < 1e-4, f"level {i}"
+    names = [str(n) for n in g["names"]]
+    got = np.stack([f.results_.params[n] for n in names])
+    assert rel_err(got, g["params"]).max() < 1e-4
+    assert (f.results_.success == g["success"]).all()
+    assert np.array_equal(np.array(list(f.pixel_indices)), g["pixel_indices"])
+    assert np.nanmax(np.abs(f.results_.r_squared - g["r_squared"])) < 1e-9
+
+
+def test_ideal_z_slab_equals_full_volume():
+    """Multi-GPU sharding property: fitting a z-slab gives exactly that slab of the full fit."""
+    g = load("fitter_ideal")
+    tol = {"S0": 0.5, "f1": 0.2, "D1": 0.2, "D2": 0.2}
+    kw = dict(dim_steps=g["dim_steps"], step_tol=tol)
+    full = IDEALFitter(solver=_solver(), **kw).fit(g["b"], g["image"], g["seg"])
+    slab = IDEALFitter(solver=_solver(), **kw).fit(g["b"], g["image"], g["seg"], z_range=(1, 2))
+    assert np.array_equal(slab.step_params[-1], full.step_params[-1][:, :, 1:2])
+
+
+def test_ideal_validation():
+    with pytest.raises(ValueError):
+        IDEALFitter(solver=_solver(), dim_steps=np.array([[4, 4], [8, 8]]), step_tol={"S0": 0.5},
+                    ).fit(CFG.bvalues, np.ones((8, 8, 1, 16)))
+    with pytest.raises(ValueError):
+        IDEALFitter(solver=_solver(), dim_steps=np.array([[4, 4]]), step_tol={}, interpolation_method="nearest")
+    tol = {"S0": 0.5, "f1": 0.2, "D1": 0.2, "D2": 0.2}
+    with pytest.raises(ValueError):  # last step must match the image
+        IDEALFitter(solver=_solver(), dim_steps=np.array([[4, 4], [8, 8]]), step_tol=tol,
+                    ).fit(CFG.bvalues, np.ones((16, 16, 1, 16)))
+
+
+def test_segmented_matches_reference():
+    g = load("fitter_segmented")
+    s1 = CurveFitSolver(model=models.MonoExpModel(), max_iter=250, tol=1e-8, p0={"S0": 1000.0, "D": 0.001},
+                        bounds={"S0": (1.0, 5000.0), "D": (1e-5, 0.003)})
+    f = SegmentedFitter(step1_solver=s1, step2_solver=_solver(), step1_bvalue_range=(200, None),
+                        fixed_from_step1=["D"], param_mapping={"D": "D1"}).fit(g["b"], g["image"], g["seg"])
+    s1n = [str(n) for n in g["step1_names"]]
+    got1 = np.stack([f.step1_params_[n] for n in s1n])
+    assert rel_err(got1, g["step1_params"]).max() < 1e-4
+    names = [str(n) for n in g["names"]]
+    assert set(f.fitted_params_) == set(names)
+    got = np.stack([f.fitted_params_[n] for n in names])
+    assert rel_err(got, g["params"]).max() < 1e-4
+    # the fixed parameter of step 2 is exactly step 1's estimate (tests/test_fitter_segmented.py:379-386)
+    assert np.array_equal(f.fitted_params_["D1"], f.step1_params_["D"])
+    assert (f.results_.success == g["success"]).all() and (f.step1_result_.success == g["step1_success"]).all()
+    assert np.nanmax(np.abs(f.results_.r_squared - g["r_squared"])) < 1e-9
+    with pytest.raises(ValueError):
+        SegmentedFitter(step1_solver=s1, step2_solver=_solver(), fixed_from_step1=["nope"])
+    with pytest.raises(ValueError):
+        SegmentedFitter(step1_solver=s1, step2_solver=_solver(), step1_bvalue_range=(1100, None),
+                        fixed_from_step1=["D"], param_mapping={"D": "D1"}).fit(g["b"], g["image"], g["seg"])
+
+
+def test_segmentationwise_and_nnls_fitter():
+    g = load("fitter_pixelwise")
+    seg = g["seg"].copy()
+    seg[:8] *= 2  # labels 0, 1, 2
+    f = SegmentationWiseFitter(solver=_solver()).fit(g["b"], g["image"], seg)
+    assert list(f.segment_labels) == [0, 1, 2]
+    assert f.results_.n_pixels == 3
+    # label 2's fit equals a direct fit of its mean signal
+    mean2 = g["image"][seg == 2].mean(axis=0)
+    s = _solver().fit(g["b"], mean2)
+    assert abs(f.fitted_params_["D1"][2] - s.params_["D1"][0]) <= 1e-12 * abs(s.params_["D1"][0])
+    assert f.predict(g["b"]).shape == g["image"].shape
+    with pytest.raises(ValueError):
+        SegmentationWiseFitter(solver=_solver()).fit(g["b"], g["image"])
+    # NNLS through the pixelwise fitter: R^2 and residuals come from the kernel
+    n = NNLSSolver(model=models.NNLSModel((0.0008, 0.5), 250), reg_order=2, mu=0.02, max_iter=250)
+    fn = PixelWiseFitter(solver=n).fit(g["b"], g["image"], g["seg"])
+    r = fn.results_
+    assert r.covariance is None and r.residuals is not None and r.params["coefficients"].shape[1] == 250
+    host_r2 = fn._compute_r_squared(g["b"], g["image"][g["seg"] != 0])
+    assert np.nanmax(np.abs(r.r_squared - host_r2)) < 1e-9
