@@ -105,7 +105,12 @@ def test_segmented_matches_reference():
     # the fixed parameter of step 2 is exactly step 1's estimate (tests/test_fitter_segmented.py:379-386)
     assert np.array_equal(f.fitted_params_["D1"], f.step1_params_["D"])
     assert (f.results_.success == g["success"]).all() and (f.step1_result_.success == g["step1_success"]).all()
-    assert np.nanmax(np.abs(f.results_.r_squared - g["r_squared"])) < 1e-9
+    # Reference quirk: with per-pixel fixed parameters its R^2 loop raises
+    # KeyError internally and degrades to NaN (fitters/base.py:166-186).  The kernel's R^2 is the
+    # real one; check it against a host recomputation from the fitted parameters instead.
+    assert np.isnan(g["r_squared"]).all()
+    host_r2 = f._compute_r_squared(g["b"], g["image"][g["seg"] != 0])
+    assert np.nanmax(np.abs(f.results_.r_squared - host_r2)) < 1e-9
     with pytest.raises(ValueError):
         SegmentedFitter(step1_solver=s1, step2_solver=_solver(), fixed_from_step1=["nope"])
     with pytest.raises(ValueError):
