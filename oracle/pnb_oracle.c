@@ -749,7 +749,7 @@ static int nnls_one(int m, int n, double *A, double *b, int itmax, double *x, do
     /* secondary loop */
     for (;;) {
       iter++;
-      if (iter > itmax) { mode = 3; goto terminate; }
+      if (iter >= itmax) { mode = 3; goto terminate; } /* SciPy 1.18: fails once the count reaches maxiter */
       double alpha = 2.0;
       int jj = -1;
       for (int ip = 0; ip < nsetp; ip++) {

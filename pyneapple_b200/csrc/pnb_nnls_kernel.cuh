@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(WARPS * 32) nnls_kernel(const NnlsDeviceArgs a
       back_solve(us, zs);
       for (;;) {
         iter += 1;
-        if (iter > a.maxiter) { mode = 3; break; }
+        if (iter >= a.maxiter) { mode = 3; break; }  // SciPy fails once the count reaches maxiter
         double alpha = 2.0;
         int jj = -1;
         for (int i = lane; i < k; i += 32) {

@@ -80,7 +80,7 @@ def nnls_gram(Bm, rtr, y, maxiter, refine=True):
         fail = False
         while True:
             it += 1
-            if it > maxiter:
+            if it >= maxiter:
                 mode = 3; fail = True
                 break
             alpha, jj = 2.0, -1

@@ -1,0 +1,212 @@
+"""Host-side logic: models, validation / packing, solver and fitter contracts (no GPU)."""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from oracle import ref_port
+from pyneapple_b200 import engine, models, validation as V
+from pyneapple_b200.fitters import IDEALFitter, PixelIndices, SegmentedFitter, get_fitter
+from pyneapple_b200.solvers import (ConstrainedCurveFitSolver, CurveFitSolver, NNLSSolver, PixelResults,
+                                    get_solver)
+from pyneapple_b200.solvers.nnls import regularization_matrix
+
+B = np.array([0, 25, 50, 75, 100, 150, 200, 300, 400, 500, 600, 700, 800, 900, 1000, 1200], float)
+
+MODEL_CASES = [
+    (models.MonoExpModel, {}, ("monoexp", "s0"), [900.0, 1.2e-3]),
+    (models.BiExpModel, {}, ("biexp", "reduced"), [0.25, 1.1e-3, 0.03]),
+    (models.BiExpModel, {"fit_reduced": False}, ("biexp", "full"), [0.25, 1.1e-3, 0.7, 0.03]),
+    (models.BiExpModel, {"fit_s0": True}, ("biexp", "s0"), [0.25, 1.1e-3, 0.03, 950.0]),
+    (models.TriExpModel, {}, ("triexp", "reduced"), [0.2, 0.1, 0.3, 0.01, 1e-3]),
+    (models.TriExpModel, {"fit_reduced": False}, ("triexp", "full"), [0.2, 0.1, 0.3, 0.01, 0.5, 1e-3]),
+    (models.TriExpModel, {"fit_s0": True}, ("triexp", "s0"), [0.2, 0.1, 0.3, 0.01, 1e-3, 800.0]),
+]
+
+
+@pytest.mark.parametrize("cls,kw,key,p", MODEL_CASES)
+@pytest.mark.parametrize("t1", [None, "t1", "steam"])
+def test_models_match_reference_equations(cls, kw, key, p, t1):
+    extra, pp = {}, list(p)
+    if t1:
+        extra = dict(fit_t1=True, repetition_time=2500.0)
+        if t1 == "steam":
+            extra.update(fit_t1_steam=True, mixing_time=40.0)
+        pp = pp + [1300.0]
+    m = cls(**kw, **extra)
+    ref = ref_port.Model(key[0], key[1], t1=t1, tr=2500.0, tm=40.0)
+    assert m.param_names == ref.param_names == m._all_param_names
+    np.testing.assert_allclose(m.forward(B, *pp), ref.forward(B, *pp), rtol=1e-10)  # tests/test_models.py:93-134
+    np.testing.assert_allclose(m.jacobian(B, *pp), ref.jacobian(B, *pp), rtol=1e-10, atol=1e-300)
+    # the analytic Jacobian is the derivative of forward
+    eps = 1e-6
+    J = m.jacobian(B, *pp)
+    for j in range(len(pp)):
+        q = list(pp)
+        h = eps * abs(q[j])
+        q[j] += h
+        fd = (m.forward(B, *q) - m.forward(B, *pp)) / h
+        np.testing.assert_allclose(J[:, j], fd, rtol=2e-4, atol=1e-6 * np.abs(J[:, j]).max() + 1e-12)
+    desc = models.describe_model(m)
+    assert desc.all_names == tuple(m._all_param_names) and desc.n_all == len(pp)
+    batched = models.family_forward(desc, B, [np.array([v, v]) for v in pp])
+    np.testing.assert_allclose(batched[1], m.forward(B, *pp), rtol=1e-14)
+
+
+def test_model_constructor_errors_and_fixed_params():
+    with pytest.raises(ValueError):
+        models.BiExpModel(fit_s0=True, fit_reduced=False)
+    with pytest.raises(ValueError):
+        models.MonoExpModel(fit_t1=True)
+    with pytest.raises(ValueError):
+        models.MonoExpModel(fit_t1_steam=True, repetition_time=100.0)
+    with pytest.raises(ValueError):
+        models.BiExpModel(fixed_params={"nope": 1.0})
+    with pytest.raises(ValueError):
+        models.MonoExpModel(fixed_params={"S0": 1.0, "D": 1.0})
+    m = models.BiExpModel(fit_s0=True, fixed_params={"D2": 0.03})
+    assert m.param_names == ["f1", "D1", "S0"] and m._free_indices({"D2": 0.03}) == [0, 1, 3]
+    full = m._inject_fixed((0.2, 1e-3, 900.0), {"D2": 0.03})
+    assert full == (0.2, 1e-3, 0.03, 900.0)
+    np.testing.assert_allclose(m.forward_with_fixed(B, {"D2": 0.03}, 0.2, 1e-3, 900.0), m.forward(B, *full))
+    assert m.jacobian_with_fixed(B, {"D2": 0.03}, 0.2, 1e-3, 900.0).shape == (16, 3)
+    nn = models.NNLSModel((0.0008, 0.5), 250)
+    assert np.array_equal(nn.bins, ref_port.nnls_bins(0.0008, 0.5, 250))
+    assert np.array_equal(nn.get_basis(B), ref_port.nnls_basis(B, nn.bins))
+    with pytest.raises(ValueError):
+        nn.get_basis(B[None, :])
+
+
+def test_describe_model_duck_types_foreign_objects():
+    class BiExpModel:  # looks like pyneapple.models.BiExpModel
+        fit_reduced, fit_s0, fit_t1, fit_t1_steam = True, True, False, False
+        repetition_time = mixing_time = None
+        fixed_params = {"D2": 0.02}
+        _all_param_names = ["f1", "D1", "D2", "S0"]
+
+    d = models.describe_model(BiExpModel())
+    assert d.model_id == models.MODEL_BI_S0 and d.fixed == {"D2": 0.02}
+    assert engine.frozen_mask(d, {"D2"}) == 0b0100
+
+    class Strange:
+        pass
+
+    with pytest.raises(NotImplementedError):
+        models.describe_model(Strange())
+
+
+def _mono(**kw):
+    return CurveFitSolver(models.MonoExpModel(), 250, 1e-8, {"S0": 1000.0, "D": 1e-3},
+                          {"S0": (1.0, 5000.0), "D": (1e-5, 0.1)}, **kw)
+
+
+def test_curvefit_solver_constructor_contract():
+    s = _mono(multi_threading=True, n_pools=4, xtol=1e-9)
+    assert (s.method, s.multi_threading, s.n_pools, s.use_jacobian) == ("trf", True, 4, True)
+    assert s.solver_kwargs == {"xtol": 1e-9}
+    with pytest.raises(RuntimeError):
+        s.get_params()
+    with pytest.raises(RuntimeError):
+        s.get_diagnostics()
+    with pytest.raises(ValueError):  # bounds must be tuples (curvefit.py:83-89)
+        CurveFitSolver(models.MonoExpModel(), 250, 1e-8, {"S0": 1.0, "D": 1e-3}, {"S0": [1, 2], "D": [0, 1]})
+    with pytest.raises(ValueError):  # missing name
+        CurveFitSolver(models.MonoExpModel(), 250, 1e-8, {"S0": 1.0}, {"S0": (1, 2), "D": (0, 1)})
+    with pytest.raises(ValueError):  # p0 list
+        CurveFitSolver(models.MonoExpModel(), 250, 1e-8, {"S0": [1.0], "D": [1e-3]}, {"S0": (1, 2), "D": (0, 1)})
+    with pytest.raises(NotImplementedError):  # curve_fit kwargs without a device implementation
+        _mono(loss="huber")
+    assert get_solver("curvefit", model=models.MonoExpModel(), max_iter=5, tol=1e-3, p0=s.p0,
+                      bounds=s.bounds).max_iter == 5
+    with pytest.raises(ValueError):
+        get_solver("nope")
+
+
+def test_p0_and_bounds_packing_errors():
+    s = _mono()
+    p0, lb, ub = s._validate_p0_and_bounds(None, None, 7)
+    assert p0.shape == lb.shape == ub.shape == (2,)  # broadcast vector, not tiled
+    p0, lb, ub = s._validate_p0_and_bounds({"S0": 900.0, "D": 2e-3}, {"S0": (2.0, 10.0), "D": (0.0, 1.0)}, 7)
+    assert list(p0) == [900.0, 2e-3] and list(ub) == [10.0, 1.0]
+    arr = np.ones((2, 7))
+    p0, lb, ub = s._validate_p0_and_bounds(arr, (arr * 0, arr * 2), 7)
+    assert p0.shape == (2, 7)
+    with pytest.raises(ValueError):
+        s._validate_p0_and_bounds(np.ones((2, 6)), None, 7)
+    with pytest.raises(ValueError):
+        s._validate_p0_and_bounds({"S0": np.ones(7), "D": np.ones(7)}, None, 7)
+    with pytest.raises(ValueError):
+        s._validate_p0_and_bounds([1.0, 2.0], None, 7)
+    with pytest.raises(ValueError):
+        s._validate_p0_and_bounds(None, (arr, [1, 2]), 7)
+    with pytest.raises(ValueError):
+        s._validate_p0_and_bounds(None, (np.ones((2, 3)), np.ones((2, 3))), 7)
+    with pytest.raises(ValueError):
+        V.validate_data_shapes(B, np.ones((4, 15)))
+    with pytest.raises(ValueError):
+        V.validate_data_shapes(B[None], np.ones((4, 16)))
+    seg = V.validate_segmentation(np.ones((4, 4, 2, 1)), (4, 4, 2, 16))
+    assert seg.shape == (4, 4, 2)
+    with pytest.raises(ValueError):
+        V.validate_segmentation(np.ones((4, 4)), (4, 4, 2, 16))
+
+
+def test_constrained_and_nnls_constructor_contract():
+    with pytest.raises(ValueError):
+        ConstrainedCurveFitSolver(models.TriExpModel(fit_reduced=False), 250, 1e-8, {}, {})
+    tri = ConstrainedCurveFitSolver(
+        models.TriExpModel(), 250, 1e-8, {"f1": .15, "D1": .1, "f2": .25, "D2": .01, "D3": .001},
+        {"f1": (0., 1.), "D1": (.03, .5), "f2": (0., 1.), "D2": (.003, .03), "D3": (1e-4, .003)},
+        use_jacobian=True, some_unknown_option=3)
+    assert tri.method == "SLSQP" and tri._fraction_indices == [0, 2] and tri.fraction_constraint
+    n = NNLSSolver(models.NNLSModel((0.0008, 0.5), 250), reg_order=2, mu=0.02, multi_threading=True, n_pools=8)
+    assert n.n_pools == 8 and n.tol == 1e-8 and n.max_iter == 250
+    assert n.get_regularization_matrix().shape == (250, 250)
+    assert n._extend_signal(np.ones((3, 16))).shape == (3, 266)
+    with pytest.raises(NotImplementedError):
+        regularization_matrix(10, 4, 1.0)
+    R = regularization_matrix(6, 2, 0.5)  # stencils of tests/test_solver_nnls.py:282-307
+    assert R[2, 1] == 0.5 and R[2, 2] == -1.0 and R[2, 3] == 0.5
+    band, W = engine.rtr_band(regularization_matrix(9, 3, 0.1))
+    assert W == 4 and band.shape == (9, 9)
+    full = regularization_matrix(9, 3, 0.1).T @ regularization_matrix(9, 3, 0.1)
+    for j in range(9):
+        for d in range(-4, 5):
+            if 0 <= j + d < 9:
+                assert band[j, d + 4] == full[j, j + d]
+    assert engine.rtr_band(np.zeros((5, 5)))[1] == 0
+
+
+def test_lazy_containers():
+    pr = PixelResults(params=np.arange(6.0).reshape(3, 2), covariance=np.zeros((3, 2, 2)),
+                      success=[True, False, True], messages=lambda i: f"m{i}")
+    assert len(pr) == 3 and pr[1].success is False and pr[1].message == "m1" and pr[-1].params[0] == 4.0
+    assert [p.success for p in pr] == [True, False, True] and len(pr[0:2]) == 2
+    with pytest.raises(IndexError):
+        pr[3]
+    pi = PixelIndices(np.array([[0, 1, 2], [3, 4, 5]]))
+    assert list(pi) == [(0, 1, 2), (3, 4, 5)] and pi[1] == (3, 4, 5) and pi == [(0, 1, 2), (3, 4, 5)]
+
+
+def test_fitter_construction_contract():
+    s = CurveFitSolver(models.BiExpModel(fit_s0=True), 250, 1e-8, {"f1": .2, "D1": 1e-3, "D2": .02, "S0": 1e3},
+                       {"f1": (.01, .99), "D1": (1e-5, .003), "D2": (.003, .3), "S0": (1., 5e3)})
+    f = get_fitter("pixelwise", solver=s)
+    assert f.results_ is None and f.fitted_params_ == {} and f.pixel_indices is None
+    with pytest.raises(RuntimeError):
+        f.predict(B)
+    with pytest.raises(ValueError):
+        get_fitter("nope")
+    i = IDEALFitter(s, np.array([[2, 2], [4, 4]]), {"f1": .2, "D1": .2, "D2": .2, "S0": .5})
+    assert i.step_params == [] and i.ideal_dims == 2 and i.segmentation_threshold == 0.2
+    with pytest.raises(ValueError):
+        i._validate_fitter_inputs(np.array([[4, 4], [2, 2]]), 2)
+    with pytest.raises(ValueError):
+        i._validate_fitter_inputs(np.array([2, 4]), 2)
+    mono = _mono()
+    sf = SegmentedFitter(mono, s, step1_bvalue_range=(200, None), fixed_from_step1=["D"], param_mapping={"D": "D1"})
+    xb, img = sf._subset_bvalues(B, np.ones((2, 2, 1, 16)))
+    assert xb.min() == 200 and img.shape[-1] == xb.size
+    with pytest.raises(ValueError):
+        SegmentedFitter(mono, s, fixed_from_step1=["D"])  # "D" is not a step-2 parameter without a mapping

@@ -1,0 +1,81 @@
+"""The per-voxel device mathematics (pnb_trf_core.cuh) compiled with g++ against the goldens.
+
+This is how the kernel arithmetic is checked in the GPU-less container; the product only ever
+runs the nvcc build (tests/test_trf_gpu.py checks that one on the B200).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from _util import TRF_CASES, full_problem, rel_err
+from hostsim import hostsim
+from oracle import c_oracle
+
+
+@pytest.mark.parametrize("name", sorted(TRF_CASES))
+@pytest.mark.parametrize("mode", ["reference", "analytic"])
+def test_core_matches_reference(name, mode):
+    kind, m = TRF_CASES[name]
+    P = full_problem(name)
+    jm = (1 if P["uses_fd"] else 0) if mode == "reference" else 0
+    r = hostsim.trf_fit(c_oracle.MODEL_IDS[(kind, m)], P["b"], P["y"], P["P0"], P["LB"], P["UB"],
+                        frozen=P["frozen"], ftol=P["tol"], max_nfev=P["max_iter"], jac_mode=jm)
+    free = [i for i in range(len(P["all_names"])) if not P["frozen"][i]]
+    par = r["params"][:, free]
+    assert ((r["status"] > 0) == P["ref_success"]).all()
+    fail = ~P["ref_success"]
+    assert np.array_equal(par[fail], P["ref_params"][fail])
+    ok = P["ref_success"]
+    if ok.any():
+        err = rel_err(par[ok], P["ref_params"][ok]).max(axis=1)
+        allowed = 2 if name == "trf_triexp_full" else 0
+        assert (err > 1e-4).sum() <= allowed
+        if mode == "reference":
+            assert np.median(err) < 1e-7
+
+
+def test_t1_variants_against_c_oracle():
+    """T1 / STEAM models (model_functions/multiexp.py:210-302): core vs the C restatement."""
+    rng = np.random.default_rng(3)
+    b = np.array([0, 50, 100, 200, 400, 600, 800, 1000, 1200, 1500], float)
+    n = 64
+    s0, d, t1 = rng.uniform(800, 1200, n), rng.uniform(8e-4, 2e-3, n), rng.uniform(900, 1500, n)
+    for t1_mode, tm in ((1, 0.0), (2, 30.0)):
+        tr = 2500.0
+        y = s0[:, None] * np.exp(-b * d[:, None]) * (1 - np.exp(-tr / t1[:, None]))
+        if t1_mode == 2:
+            y = y * np.exp(-tm / t1[:, None])
+        y = y + rng.normal(0, 3, y.shape)
+        P0 = np.tile([1000.0, 1e-3, 1200.0], (n, 1))
+        LB = np.tile([1.0, 1e-5, 100.0], (n, 1))
+        UB = np.tile([5000.0, 0.1, 5000.0], (n, 1))
+        a = hostsim.trf_fit(0, b, y, P0, LB, UB, t1_mode=t1_mode, tr=tr, tm=tm, jac_mode=0)
+        c = c_oracle.trf_fit(0, b, y, P0, LB, UB, t1_mode=t1_mode, tr=tr, tm=tm, jac_mode=0)
+        assert ((a["status"] > 0) == (c["status"] > 0)).all()
+        ok = c["status"] > 0
+        # S0 and T1 enter only through the product S0 * C(T1): compare the identifiable quantities
+        def amp(p):
+            f = 1 - np.exp(-tr / p[:, 2])
+            return p[:, 0] * (f * np.exp(-tm / p[:, 2]) if t1_mode == 2 else f)
+        assert rel_err(a["params"][ok, 1], c["params"][ok, 1]).max() < 1e-7
+        assert rel_err(amp(a["params"][ok]), amp(c["params"][ok])).max() < 1e-7
+        assert rel_err(a["cost"][ok], c["cost"][ok]).max() < 1e-9
+
+
+def test_x_scale_jac_against_scipy():
+    from scipy.optimize import least_squares
+
+    P = full_problem("trf_biexp_s0_c2")
+    n = 24
+    r = hostsim.trf_fit(3, P["b"], P["y"][:n], P["P0"][:n], P["LB"][:n], P["UB"][:n], jac_mode=1,
+                        x_scale_jac=True)
+    from oracle import ref_port
+
+    m = ref_port.Model("biexp", "s0")
+    for i in range(n):
+        ref = least_squares(lambda p: m.forward(P["b"], *p) - P["y"][i], P["P0"][i],
+                            bounds=(P["LB"][i], P["UB"][i]), method="trf", x_scale="jac", ftol=1e-8,
+                            max_nfev=250)
+        assert rel_err(r["params"][i], ref.x).max() < 1e-5
