@@ -113,6 +113,126 @@ class ClockSampler:
         }
 
 
+def nnls_algorithmic_flops(m, n_bins, w, iters, k_final):
+    """SURVEY.md §8(d) K4 model, evaluated from the device counters (iterations, final active size).
+
+    adds = (iters + k_final) / 2 outer iterations, mean active size ~0.6 k_final.
+    """
+    iters = np.asarray(iters, np.float64)
+    k = np.asarray(k_final, np.float64)
+    n_outer = 0.5 * (iters + k)
+    kbar = 0.6 * k
+    per_outer = 2 * m * n_bins + 2 * (2 * w + 1) * n_bins + 2 * m * kbar + (2 * w + 1) * kbar
+    per_inner = 3 * kbar * kbar + 2 * m * kbar
+    return float(np.sum(2 * m * n_bins + n_outer * per_outer + iters * per_inner))
+
+
+def bench_nnls(args, world, rank, local_rank, dev):
+    """250-bin NNLS half of the metric: config C3 (d_range [0.0008, 0.5], reg_order 2, mu 0.02)."""
+    import torch
+    import torch.distributed as dist
+
+    from pyneapple_b200 import _lib, engine, models, synth
+    from pyneapple_b200.solvers import NNLSSolver
+    from pyneapple_b200.solvers.nnls import regularization_matrix
+
+    base = synth.CONFIGS["C3"]
+    cfg = synth.Config(**{**base.__dict__, "shape": (base.shape[0], base.shape[1], args.slices * world)})
+    z0 = rank * args.slices
+    b, img, _ = synth.make_volume(cfg, z0, z0 + args.slices)
+    y_host = img.reshape(-1, b.shape[0])
+    del img
+    n_vox, n_b = y_host.shape
+    model = models.NNLSModel(d_range=(0.0008, 0.5), n_bins=250)
+    basis = model.get_basis(b)
+    R = regularization_matrix(250, 2, 0.02)
+    y_dev = torch.as_tensor(y_host).to(dev)
+    steps = max(1, min(args.steps, 3))
+    r = engine.nnls_fit(basis, R, y_dev, 250, device=local_rank)  # warm-up
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = _lib.launch_count()
+    e0.record()
+    for _ in range(steps):
+        r = engine.nnls_fit(basis, R, y_dev, 250, device=local_rank)
+    e1.record()
+    torch.cuda.synchronize()
+    launches = _lib.launch_count() - l0
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    value = n_vox * world * steps / (ms * 1e-3)
+    iters = r["iterations"].cpu().numpy()
+    k_final = (r["coefficients"] > 0).sum(dim=1).cpu().numpy()
+    ok_rate = float((r["status"] == 1).double().mean().item())
+    del r
+    torch.cuda.empty_cache()
+    # e2e through NNLSSolver.fit with pinned host buffers
+    y_pin = _lib.pinned_empty(y_host.shape)
+    y_pin[...] = y_host
+    solver = NNLSSolver(model=model, reg_order=2, mu=0.02, max_iter=250, device=local_rank, pinned_outputs=True)
+    solver.fit(b, y_pin)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    solver.fit(b, y_pin)
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = n_vox * world / float(e2e_s.item())
+    if rank != 0:
+        return None
+    flops = nnls_algorithmic_flops(n_b, 250, 2, iters, k_final)
+    kernel_ms = ms / steps
+    fp64_peak = _lib.measure_fp64_peak(local_rank)
+    alg_bytes = n_vox * (8 * n_b + 8 * 250 + 8 + 4 + 4 + 8)
+    out = {
+        "workload": "C3: pixelwise NNLS n_bins=250, d_range [0.0008, 0.5], reg_order=2, mu=0.02, max_iter=250, "
+                    "256x256x64 voxels x 16 b-values",
+        "value": value, "unit": UNIT, "steps": steps, "ms_per_step": ms / steps, "gpu_launches": int(launches),
+        "voxels_per_gpu": n_vox, "success_rate": ok_rate, "mean_iterations": float(iters.mean()),
+        "mean_active_set": float(k_final.mean()), "max_active_set": int(k_final.max()),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(y_host.nbytes),
+                "d2h_bytes_per_step": int(n_vox * (250 * 8 + 8 + 4 + 4 + 8)),
+                "api": "NNLSSolver.fit(numpy pinned) -> pnb_nnls_fit_host"},
+        "roofline": {"bound": "fp64", "kernel": "nnls_kernel<8>", "achieved": flops / (kernel_ms * 1e-3) / 1e12,
+                     "peak": fp64_peak, "unit": "TFLOP/s", "frac": flops / (kernel_ms * 1e-3) / 1e12 / fp64_peak,
+                     "flops_per_launch": flops, "flop_model": "SURVEY.md §8(d) K4, from device iteration counters",
+                     "kernel_ms": kernel_ms, "traffic": None,
+                     "hbm": {"achieved": alg_bytes / (kernel_ms * 1e-3) / 1e9, "unit": "GB/s",
+                             "algorithmic_bytes_per_launch": alg_bytes}},
+    }
+    if not args.no_cpu_baseline:
+        from oracle import ref_port
+
+        cores = os.cpu_count() or 1
+        sb, sy, _ = synth.sample_voxels(base, 32768, z=0)
+        ref_port.nnls_fit(sb, sy[: 8 * cores], (0.0008, 0.5), 250, 2, 0.02, 250, n_jobs=-1)
+        t0 = time.perf_counter()
+        probe = ref_port.nnls_fit(sb, sy[: 64 * cores], (0.0008, 0.5), 250, 2, 0.02, 250, n_jobs=-1)
+        rate = 64 * cores / (time.perf_counter() - t0)
+        n = int(min(32768, max(64 * cores, rate * 10.0)))
+        t0 = time.perf_counter()
+        ref = ref_port.nnls_fit(sb, sy[:n], (0.0008, 0.5), 250, 2, 0.02, 250, n_jobs=-1)
+        dt = time.perf_counter() - t0
+        del probe
+        out["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                               "sample": f"{n} voxels, scipy.optimize.nnls per voxel via oracle/ref_port.py, "
+                                         f"joblib n_jobs=-1, {dt:.1f} s"}
+        chk = NNLSSolver(model=model, reg_order=2, mu=0.02, max_iter=250, device=local_rank).fit(sb, sy[:n])
+        out["parity_vs_cpu_sample"] = {
+            "voxels": n,
+            "max_abs_coefficient_diff": float(np.abs(chk.params_["coefficients"] - ref["coefficients"]).max()),
+            "max_abs_residual_diff": float(np.abs(chk.diagnostics_["residual"] - ref["residual"]).max()),
+            "success_flags_equal": bool(((chk.status_ == 1) == ref["success"]).all()),
+        }
+    return out
+
+
 def problem_arrays(cfg):
     names = ["f1", "D1", "D2", "S0"]
     return (names, np.array([cfg.p0[n] for n in names]), np.array([cfg.bounds[n][0] for n in names]),
@@ -276,7 +396,6 @@ def main():
         torch.cuda.synchronize()
         kt.append(kev0.elapsed_time(kev1))
     kernel_ms = float(np.mean(kt[1:]))
-    clocks = sampler.stop() if rank == 0 else None
     nfev_sum = int(r["nfev"].sum().item())
     njev_sum = int(r["njev"].sum().item())
     success = float((r["status"] > 0).double().mean().item())
@@ -301,9 +420,13 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
     e2e_value = n_vox * world * e2e_steps / e2e_s
+    clocks = sampler.stop() if rank == 0 else None
     h2d = y_host.nbytes + b.nbytes + 3 * 4 * 8
     d2h = n_vox * (4 * 8 + 16 * 8 + 4 + 4 + 4 + 8)
 
+    del y_pin, solver, y_dev
+    torch.cuda.empty_cache()
+    nnls = None if args.no_nnls else bench_nnls(args, world, rank, local_rank, dev)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -368,6 +491,7 @@ def main():
         "cpu_baseline": cpu,
     }
     line.update(extra)
+    line["nnls"] = nnls
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
