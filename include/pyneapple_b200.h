@@ -122,6 +122,10 @@ typedef struct pnb_nnls_problem {
   int32_t n_bins;            /* dictionary size                                 */
   int32_t rtr_halfband;      /* W: (R^T R)[i][j] = 0 for |i-j| > W              */
   int32_t max_iter;          /* NNLSSolver.max_iter (Lawson-Hanson iteration cap) */
+  int32_t algorithm;         /* 0 auto: inverse-update fast path, voxels it cannot certify
+                                are re-solved by the robust path; 1 robust (Cholesky +
+                                refinement) only -- use for un-regularised problems */
+  int32_t reserved;
   int64_t n_vox;
   const double *basis;       /* (n_b, n_bins)                                   */
   const double *rtr_band;    /* (n_bins, 2W+1): [j][d+W] = (mu^2 R^T R)[j][j+d] */

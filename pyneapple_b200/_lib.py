@@ -69,6 +69,8 @@ class NnlsProblem(C.Structure):
         ("n_bins", C.c_int32),
         ("rtr_halfband", C.c_int32),
         ("max_iter", C.c_int32),
+        ("algorithm", C.c_int32),
+        ("reserved", C.c_int32),
         ("n_vox", C.c_int64),
         ("basis", C.c_void_p),
         ("rtr_band", C.c_void_p),

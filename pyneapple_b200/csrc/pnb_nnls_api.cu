@@ -5,7 +5,7 @@
 
 #include "../../include/pyneapple_b200.h"
 #include "pnb_internal.h"
-#include "pnb_nnls_kernel.cuh"
+#include "pnb_nnls_fast.cuh"
 
 namespace {
 
@@ -17,6 +17,8 @@ struct NnlsCtx {
   int next = 0;
   double *scratch = nullptr;
   size_t scratch_cap = 0;
+  int *redo_list = nullptr;
+  size_t redo_cap = 0;
   // host pipeline
   cudaStream_t streams[2] = {nullptr, nullptr};
   double *y[2] = {nullptr, nullptr}, *coef[2] = {nullptr, nullptr}, *rn[2] = {nullptr, nullptr}, *r2[2] = {nullptr, nullptr};
@@ -34,6 +36,7 @@ int check(const pnb_nnls_problem *p) {
   if (p->n_bins < 1 || p->n_bins > 1024) return pnbi::fail(PNB_E_BADARG, "n_bins must be in [1, 1024]");
   if (p->rtr_halfband < 0 || p->rtr_halfband > 8) return pnbi::fail(PNB_E_BADARG, "rtr_halfband must be in [0, 8]");
   if (p->max_iter < 1) return pnbi::fail(PNB_E_BADARG, "max_iter must be positive");
+  if (p->algorithm != 0 && p->algorithm != 1) return pnbi::fail(PNB_E_BADARG, "algorithm must be 0 or 1");
   if (p->n_vox < 0) return pnbi::fail(PNB_E_BADARG, "n_vox < 0");
   if (p->n_vox > 0 && (!p->basis || !p->rtr_band || !p->signal || !p->coefficients || !p->residual ||
                        !p->status || !p->iterations))
@@ -48,44 +51,77 @@ int pick_kmax(int m, int n, int W) {
   return k;
 }
 
+int pick_kcap_fast(int m, int n, int W) {
+  int k = n < 96 ? n : 96;
+  while (k > 8 && pnb::nnls_fast_smem_bytes(m, n, W, k, kWarps) > kSmemBudget) k--;
+  return k;
+}
+
 int launch(NnlsCtx &C, const pnb_nnls_problem *p, const double *B, const double *rtr, const double *y,
            long long n_vox, double *coef, double *rn, int *st, int *it, double *r2, cudaStream_t stream) {
   const int m = p->n_b, n = p->n_bins, W = p->rtr_halfband;
   const int kmax = pick_kmax(m, n, W);
   const size_t smem = pnb::nnls_smem_bytes(m, n, W, kmax, kWarps);
   if (smem > 227 * 1024) return pnbi::fail(PNB_E_UNSUPPORTED, "n_b x n_bins too large for shared memory");
-  auto kern = pnb::nnls_kernel<kWarps>;
-  PNBI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int dev = 0, sms = 0, bps = 0;
+  auto robust = pnb::nnls_kernel<kWarps>;
+  auto fast = pnb::nnls_fast_kernel<kWarps>;
+  const int kcap = pick_kcap_fast(m, n, W);
+  const size_t smem_fast = pnb::nnls_fast_smem_bytes(m, n, W, kcap, kWarps);
+  PNBI_CUDA(cudaFuncSetAttribute(robust, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PNBI_CUDA(cudaFuncSetAttribute(fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast));
+  int dev = 0, sms = 0, bps = 0, bps_fast = 0;
   PNBI_CUDA(cudaGetDevice(&dev));
   PNBI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  PNBI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, kWarps * 32, smem));
-  if (bps < 1) return pnbi::fail(PNB_E_UNSUPPORTED, "NNLS kernel does not fit on this device");
-  long long grid = (long long)bps * sms;
+  PNBI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, robust, kWarps * 32, smem));
+  PNBI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_fast, fast, kWarps * 32, smem_fast));
+  if (bps < 1 || bps_fast < 1) return pnbi::fail(PNB_E_UNSUPPORTED, "NNLS kernel does not fit on this device");
   const long long want = (n_vox + kWarps - 1) / kWarps;
-  if (want < grid) grid = want;
-  if (grid < 1) grid = 1;
   const size_t per_warp = (size_t)n * (n + 1) / 2 + 5 * (size_t)n;
   const size_t need = (size_t)bps * sms * kWarps * per_warp;
-  {
-    if (need > C.scratch_cap) {
-      if (C.scratch) PNBI_CUDA(cudaFree(C.scratch));
-      C.scratch = nullptr; C.scratch_cap = 0;
-      PNBI_CUDA(cudaMalloc(&C.scratch, need * sizeof(double)));
-      C.scratch_cap = need;
-    }
-    if (!C.counters) PNBI_CUDA(cudaMalloc(&C.counters, 64 * sizeof(unsigned long long)));
+  if (need > C.scratch_cap) {
+    if (C.scratch) PNBI_CUDA(cudaFree(C.scratch));
+    C.scratch = nullptr; C.scratch_cap = 0;
+    PNBI_CUDA(cudaMalloc(&C.scratch, need * sizeof(double)));
+    C.scratch_cap = need;
   }
+  if ((size_t)n_vox > C.redo_cap) {
+    if (C.redo_list) PNBI_CUDA(cudaFree(C.redo_list));
+    C.redo_list = nullptr; C.redo_cap = 0;
+    PNBI_CUDA(cudaMalloc(&C.redo_list, (size_t)n_vox * sizeof(int)));
+    C.redo_cap = (size_t)n_vox;
+  }
+  if (!C.counters) PNBI_CUDA(cudaMalloc(&C.counters, 64 * sizeof(unsigned long long)));
+  // three consecutive counters per call: fast work queue, redo count, robust work queue
+  unsigned long long *ctr = C.counters + C.next;
+  C.next = (C.next + 3) % 60;
+  PNBI_CUDA(cudaMemsetAsync(ctr, 0, 3 * sizeof(unsigned long long), stream));
   pnb::NnlsDeviceArgs a;
   a.m = m; a.n = n; a.W = W; a.maxiter = p->max_iter; a.n_vox = n_vox;
   a.B = B; a.rtr = rtr; a.y = y; a.coef = coef; a.rnorm = rn; a.status = st; a.iters = it; a.r2 = r2;
-  a.counter = C.counters + C.next;
-  C.next = (C.next + 1) % 64;
-  a.scratch = C.scratch; a.kmax = kmax;
-  PNBI_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(unsigned long long), stream));
-  kern<<<(unsigned)grid, kWarps * 32, smem, stream>>>(a);
-  PNBI_CUDA(cudaGetLastError());
-  pnbi::count_launch();
+  a.scratch = C.scratch;
+  a.redo_count = ctr + 1; a.redo_list = C.redo_list;
+  if (p->algorithm == 0) {
+    long long grid = (long long)bps_fast * sms;
+    if (want < grid) grid = want;
+    if (grid < 1) grid = 1;
+    a.counter = ctr; a.kmax = kcap; a.work_list = nullptr; a.work_count = nullptr;
+    fast<<<(unsigned)grid, kWarps * 32, smem_fast, stream>>>(a);
+    PNBI_CUDA(cudaGetLastError());
+    pnbi::count_launch();
+    // voxels the fast path could not certify (the count stays on the device)
+    a.counter = ctr + 2; a.kmax = kmax; a.work_list = C.redo_list; a.work_count = ctr + 1;
+    robust<<<(unsigned)((long long)bps * sms), kWarps * 32, smem, stream>>>(a);
+    PNBI_CUDA(cudaGetLastError());
+    pnbi::count_launch();
+  } else {
+    long long grid = (long long)bps * sms;
+    if (want < grid) grid = want;
+    if (grid < 1) grid = 1;
+    a.counter = ctr; a.kmax = kmax; a.work_list = nullptr; a.work_count = nullptr;
+    robust<<<(unsigned)grid, kWarps * 32, smem, stream>>>(a);
+    PNBI_CUDA(cudaGetLastError());
+    pnbi::count_launch();
+  }
   return 0;
 }
 

@@ -52,6 +52,12 @@ struct NnlsDeviceArgs {
   unsigned long long *counter;
   double *scratch;       // per-warp overflow storage, (n (n+1) / 2 + 5 n) doubles per warp
   int kmax;              // active-set size that fits the shared-memory factor
+  // fast path -> robust path hand-over: the fast kernel appends voxels it gives up on,
+  // the robust kernel (work_list != nullptr) processes exactly work_count[0] of them
+  unsigned long long *redo_count;
+  int *redo_list;
+  const int *work_list;
+  const unsigned long long *work_count;
 };
 
 // column-major packed lower triangle with leading dimension ld: element (i, c), i >= c
@@ -89,8 +95,13 @@ __global__ void __launch_bounds__(WARPS * 32) nnls_kernel(const NnlsDeviceArgs a
   for (;;) {
     unsigned long long vq = 0;
     if (lane == 0) vq = atomicAdd(a.counter, 1ULL);
-    const long long vox = (long long)__shfl_sync(FULL, vq, 0);
-    if (vox >= a.n_vox) break;
+    long long vox = (long long)__shfl_sync(FULL, vq, 0);
+    if (a.work_list) {
+      if (vox >= (long long)a.work_count[0]) break;
+      vox = a.work_list[vox];
+    } else if (vox >= a.n_vox) {
+      break;
+    }
 
     // ---- set-up: y, h = B^T y, w = h, x = 0 ----------------------------------
     bool fin = true;

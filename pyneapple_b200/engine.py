@@ -221,7 +221,7 @@ def rtr_band(reg_matrix: np.ndarray):
 
 
 def nnls_fit(basis, reg_matrix, signal, max_iter: int, *, device: int = 0, chunk_vox: int = 0,
-             out: dict | None = None):
+             out: dict | None = None, algorithm: str = "auto"):
     """Batched ``scipy.optimize.nnls([basis; reg_matrix], [signal; 0], maxiter=max_iter)``.
 
     ``signal``: numpy ``(n_vox, n_b)`` (host path) or CUDA tensor (device path).
@@ -234,6 +234,10 @@ def nnls_fit(basis, reg_matrix, signal, max_iter: int, *, device: int = 0, chunk
     band, W = rtr_band(reg_matrix)
     prob = _lib.NnlsProblem()
     prob.n_b, prob.n_bins, prob.rtr_halfband, prob.max_iter = n_b, n_bins, W, int(max_iter)
+    if algorithm not in ("auto", "robust"):
+        raise ValueError("algorithm must be 'auto' or 'robust'")
+    # an un-regularised dictionary is far too ill-conditioned for the inverse-update fast path
+    prob.algorithm = 1 if (algorithm == "robust" or not np.any(band)) else 0
     if _is_torch_cuda(signal):
         import torch
 

@@ -45,6 +45,7 @@ class NNLSSolver(BaseSolver):
         self.device = solver_kwargs.pop("device", 0)
         self.chunk_vox = solver_kwargs.pop("chunk_vox", 0)
         self.pinned_outputs = solver_kwargs.pop("pinned_outputs", False)
+        self.algorithm = solver_kwargs.pop("algorithm", "auto")
         self._out_cache = None
         self.reg_order = reg_order
         self.mu = mu
@@ -86,7 +87,7 @@ class NNLSSolver(BaseSolver):
                     r2=_lib.pinned_empty((self.n_pixels,))))
             out = self._out_cache[1]
         res = engine.nnls_fit(basis, reg, signal, self.max_iter, device=self.device,
-                              chunk_vox=self.chunk_vox, out=out)
+                              chunk_vox=self.chunk_vox, out=out, algorithm=self.algorithm)
         if on_device:
             res = {k: v.cpu().numpy() for k, v in res.items()}
         status = res["status"]

@@ -16,16 +16,17 @@ CASES = ["nnls_c3_reg2", "nnls_c3_reg0", "nnls_c3_reg1", "nnls_c3_reg3", "nnls_c
          "nnls_c3_maxiter5", "nnls_c3_maxiter20", "nnls_small_reg1"]
 
 
-def _solver(g):
+def _solver(g, **kw):
     model = models.NNLSModel(d_range=tuple(float(v) for v in g["d_range"]), n_bins=int(g["n_bins"]))
     return NNLSSolver(model=model, reg_order=int(g["reg_order"]), mu=float(g["mu"]),
-                      max_iter=int(g["max_iter"]))
+                      max_iter=int(g["max_iter"]), **kw)
 
 
 @pytest.mark.parametrize("name", CASES)
-def test_golden_parity(name):
+@pytest.mark.parametrize("algorithm", ["auto", "robust"])
+def test_golden_parity(name, algorithm):
     g = load(name)
-    s = _solver(g).fit(g["b"], g["y"])
+    s = _solver(g, algorithm=algorithm).fit(g["b"], g["y"])
     coef, res = s.params_["coefficients"], s.diagnostics_["residual"]
     success = np.array([pr.success for pr in s.pixel_results_])
     assert (success == g["success"]).all()
@@ -79,6 +80,23 @@ def test_large_active_set_overflows_to_global_scratch():
     Bx = np.concatenate([y, np.zeros((y.shape[0], 250))], axis=1)
     ref = c_oracle.nnls(A, Bx, 750)
     assert (ref["x"] > 0).sum(axis=1).max() > 64  # the case does exercise the overflow path
+    assert ((s.status_ == 1) == (ref["status"] == 1)).all()
+    assert np.abs(s.params_["coefficients"] - ref["x"]).max() <= 1e-6
+
+
+@pytest.mark.parametrize("order,mu", [(2, 1e-3), (2, 2e-4), (1, 2e-4), (2, 1e-5)])
+def test_weak_regularisation_falls_back_to_the_robust_path(order, mu):
+    """The inverse-update fast path certifies its own result; weakly regularised voxels are
+    re-solved by the Cholesky kernel, so the 1e-6 tolerance holds for any mu."""
+    from oracle import c_oracle, ref_port
+    from pyneapple_b200 import synth
+
+    b, y, _ = synth.sample_voxels(synth.CONFIGS["C3"], 256, z=11)
+    model = models.NNLSModel(d_range=(0.0008, 0.5), n_bins=250)
+    s = NNLSSolver(model=model, reg_order=order, mu=mu, max_iter=750).fit(b, y)
+    A = np.concatenate([ref_port.nnls_basis(b, model.bins), ref_port.regularization_matrix(250, order, mu)])
+    Bx = np.concatenate([y, np.zeros((y.shape[0], 250))], axis=1)
+    ref = c_oracle.nnls(A, Bx, 750)
     assert ((s.status_ == 1) == (ref["status"] == 1)).all()
     assert np.abs(s.params_["coefficients"] - ref["x"]).max() <= 1e-6
 
