@@ -141,6 +141,9 @@ typedef struct pnb_nnls_problem {
 int pnb_nnls_fit_device(const pnb_nnls_problem *prob, void *cuda_stream);
 int pnb_nnls_fit_host(const pnb_nnls_problem *prob, int device, int64_t chunk_vox);
 int pnb_sizeof_nnls_problem(void);
+/* voxels of the most recent auto-mode launch on `device` that were re-solved by the robust path
+ * (synchronises the device) */
+int64_t pnb_nnls_last_redo_count(int device);
 
 /*
  * In-plane (x, y) resampling of an (H, W, inner) array for all `inner` =

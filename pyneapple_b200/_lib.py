@@ -139,6 +139,8 @@ def load():
     lib.pnb_resize2d_device.restype = C.c_int
     lib.pnb_resize2d_host.argtypes = [C.POINTER(ResizeProblem), C.c_int]
     lib.pnb_resize2d_host.restype = C.c_int
+    lib.pnb_nnls_last_redo_count.argtypes = [C.c_int]
+    lib.pnb_nnls_last_redo_count.restype = C.c_int64
     lib.pnb_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_int64]
     lib.pnb_host_free.argtypes = [C.c_void_p]
     lib.pnb_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]

@@ -19,6 +19,7 @@ struct NnlsCtx {
   size_t scratch_cap = 0;
   int *redo_list = nullptr;
   size_t redo_cap = 0;
+  unsigned long long *last_redo = nullptr;  // device counter of the most recent auto-mode launch
   // host pipeline
   cudaStream_t streams[2] = {nullptr, nullptr};
   double *y[2] = {nullptr, nullptr}, *coef[2] = {nullptr, nullptr}, *rn[2] = {nullptr, nullptr}, *r2[2] = {nullptr, nullptr};
@@ -100,6 +101,7 @@ int launch(NnlsCtx &C, const pnb_nnls_problem *p, const double *B, const double 
   a.B = B; a.rtr = rtr; a.y = y; a.coef = coef; a.rnorm = rn; a.status = st; a.iters = it; a.r2 = r2;
   a.scratch = C.scratch;
   a.redo_count = ctr + 1; a.redo_list = C.redo_list;
+  C.last_redo = (p->algorithm == 0) ? ctr + 1 : nullptr;
   if (p->algorithm == 0) {
     long long grid = (long long)bps_fast * sms;
     if (want < grid) grid = want;
@@ -193,3 +195,14 @@ extern "C" int pnb_nnls_fit_host(const pnb_nnls_problem *p, int device, int64_t 
 }
 
 extern "C" int pnb_sizeof_nnls_problem(void) { return (int)sizeof(pnb_nnls_problem); }
+
+extern "C" int64_t pnb_nnls_last_redo_count(int device) {
+  if (device < 0 || device > 15) return -1;
+  std::lock_guard<std::mutex> lk(g_mu);
+  NnlsCtx &C = g_ctx[device];
+  if (!C.last_redo) return 0;
+  unsigned long long v = 0;
+  if (cudaSetDevice(device) != cudaSuccess) return -1;
+  if (cudaMemcpy(&v, C.last_redo, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return (int64_t)v;
+}

@@ -20,7 +20,7 @@
 // counts (scripts/proto_nnls_inverse.py).  A voxel is handed to the robust
 // Cholesky kernel instead (status kNnlsRedo) when
 //   * its active set outgrows the shared-memory inverse,
-//   * the first polish step moves the solution by more than 1e-3 relative or the
+//   * the first polish step moves the solution by more than 5e-5 relative or the
 //     refinement has not converged to 1e-10 after four steps, or
 //   * the polished point violates the Kuhn-Tucker conditions,
 // which is what happens for weakly / un-regularised problems (mu <~ 5e-4).
@@ -83,14 +83,23 @@ __global__ void __launch_bounds__(WARPS * 32) nnls_fast_kernel(const NnlsDeviceA
     // dst = H src over the k active slots (symmetric packed storage, two accumulators per row)
     auto matvec = [&](const double *src, double *dst) {
       for (int i = lane; i < k; i += 32) {
-        double a0 = 0.0, a1 = 0.0;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
         const int rb = (i * (i + 1)) / 2;
         int c = 0;
-        for (; c + 1 <= i; c += 2) { a0 += H[rb + c] * src[c]; a1 += H[rb + c + 1] * src[c + 1]; }
-        if (c <= i) a0 += H[rb + c] * src[c];
+        for (; c + 3 <= i; c += 4) {
+          a0 += H[rb + c] * src[c]; a1 += H[rb + c + 1] * src[c + 1];
+          a2 += H[rb + c + 2] * src[c + 2]; a3 += H[rb + c + 3] * src[c + 3];
+        }
+        for (; c <= i; c++) a0 += H[rb + c] * src[c];
         int idx = ((i + 1) * (i + 2)) / 2 + i;
-        for (int r = i + 1; r < k; r++) { a1 += H[idx] * src[r]; idx += r + 1; }
-        dst[i] = a0 + a1;
+        int r = i + 1;
+        for (; r + 1 < k; r += 2) {
+          a1 += H[idx] * src[r];
+          a2 += H[idx + r + 1] * src[r + 1];
+          idx += 2 * r + 3;
+        }
+        if (r < k) a3 += H[idx] * src[r];
+        dst[i] = (a0 + a1) + (a2 + a3);
       }
       __syncwarp();
     };
@@ -107,6 +116,7 @@ __global__ void __launch_bounds__(WARPS * 32) nnls_fast_kernel(const NnlsDeviceA
       for (int i = lane; i < k; i += 32) {
         const double gi = gs[i] * dinv;
         const int rb = (i * (i + 1)) / 2;
+#pragma unroll 4
         for (int c = 0; c <= i; c++) H[rb + c] -= gi * gs[c];
         zs[i] -= gi * zq;
       }
@@ -125,12 +135,57 @@ __global__ void __launch_bounds__(WARPS * 32) nnls_fast_kernel(const NnlsDeviceA
     };
     // r = y - B_P z ;  returns nothing, rs filled
     auto residual = [&]() {
-      for (int b = lane; b < m; b += 32) {
-        double acc = ys[b];
-        for (int i = 0; i < k; i++) acc -= B_s[b * n + P[i]] * zs[i];
-        rs[b] = acc;
+      if (m <= 16) {
+        const int b = lane & 15, half = lane >> 4;
+        const int mid = (k + 1) >> 1;
+        const int i0 = half ? mid : 0, i1 = half ? k : mid;
+        double a0 = 0.0, a1 = 0.0;
+        if (b < m) {
+          int i = i0;
+          for (; i + 1 < i1; i += 2) {
+            a0 += B_s[b * n + P[i]] * zs[i];
+            a1 += B_s[b * n + P[i + 1]] * zs[i + 1];
+          }
+          if (i < i1) a0 += B_s[b * n + P[i]] * zs[i];
+        }
+        double acc = a0 + a1;
+        acc += __shfl_xor_sync(FULL, acc, 16);
+        if (half == 0 && b < m) rs[b] = ys[b] - acc;
+      } else {
+        for (int b = lane; b < m; b += 32) {
+          double a0 = 0.0, a1 = 0.0;
+          int i = 0;
+          for (; i + 1 < k; i += 2) {
+            a0 += B_s[b * n + P[i]] * zs[i];
+            a1 += B_s[b * n + P[i + 1]] * zs[i + 1];
+          }
+          if (i < k) a0 += B_s[b * n + P[i]] * zs[i];
+          rs[b] = ys[b] - (a0 + a1);
+        }
       }
       __syncwarp();
+    };
+    // duals of four bins of this lane at once (independent accumulation chains)
+    auto dual4 = [&](int j0, double (&w4)[4]) {
+      double a[4] = {0.0, 0.0, 0.0, 0.0};
+      int jj[4];
+#pragma unroll
+      for (int t = 0; t < 4; t++) jj[t] = (j0 + 32 * t < n) ? j0 + 32 * t : j0;
+#pragma unroll 4
+      for (int b = 0; b < m; b++) {
+        const double rb = rs[b];
+        const double *row = B_s + b * n;
+#pragma unroll
+        for (int t = 0; t < 4; t++) a[t] += row[jj[t]] * rb;
+      }
+#pragma unroll
+      for (int t = 0; t < 4; t++) {
+        const int j = jj[t];
+        const int lo = (j - W < 0) ? 0 : j - W, hi = (j + W > n - 1) ? n - 1 : j + W;
+        double acc = 0.0;
+        for (int jn = lo; jn <= hi; jn++) acc += rtr_s[j * BW + (jn - j) + W] * xs[jn];
+        w4[t] = a[t] - acc;
+      }
     };
     auto dual_of = [&](int j) -> double {
       double a0 = 0.0, a1 = 0.0;
@@ -163,8 +218,16 @@ __global__ void __launch_bounds__(WARPS * 32) nnls_fast_kernel(const NnlsDeviceA
         const int j = bj;
         for (int i = lane; i < k; i += 32) {
           const int p = P[i];
-          double acc = 0.0;
-          for (int b = 0; b < m; b++) acc += B_s[b * n + p] * B_s[b * n + j];
+          double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+          int b = 0;
+          for (; b + 3 < m; b += 4) {
+            a0 += B_s[b * n + p] * B_s[b * n + j];
+            a1 += B_s[(b + 1) * n + p] * B_s[(b + 1) * n + j];
+            a2 += B_s[(b + 2) * n + p] * B_s[(b + 2) * n + j];
+            a3 += B_s[(b + 3) * n + p] * B_s[(b + 3) * n + j];
+          }
+          for (; b < m; b++) a0 += B_s[b * n + p] * B_s[b * n + j];
+          double acc = (a0 + a1) + (a2 + a3);
           const int d = j - p;
           if (d >= -W && d <= W) acc += rtr_s[p * BW + d + W];
           gs[i] = acc;
@@ -198,6 +261,7 @@ __global__ void __launch_bounds__(WARPS * 32) nnls_fast_kernel(const NnlsDeviceA
         for (int i = lane; i < k; i += 32) {
           const double vi = vs[i] * sinv;
           const int rb = (i * (i + 1)) / 2;
+#pragma unroll 4
           for (int c = 0; c <= i; c++) H[rb + c] += vi * vs[c];
           zs[i] -= vs[i] * zeta;
         }
@@ -249,7 +313,13 @@ __global__ void __launch_bounds__(WARPS * 32) nnls_fast_kernel(const NnlsDeviceA
       for (int i = lane; i < k; i += 32) xs[P[i]] = zs[i];
       __syncwarp();
       residual();
-      for (int j = lane, q = 0; j < n; j += 32, q++) ws[j] = ((inP >> q) & 1u) ? 0.0 : dual_of(j);
+      for (int j0 = lane, q0 = 0; j0 < n; j0 += 128, q0 += 4) {
+        double w4[4];
+        dual4(j0, w4);
+#pragma unroll
+        for (int t = 0; t < 4; t++)
+          if (j0 + 32 * t < n) ws[j0 + 32 * t] = ((inP >> (q0 + t)) & 1u) ? 0.0 : w4[t];
+      }
       __syncwarp();
     }
 
@@ -275,9 +345,9 @@ __global__ void __launch_bounds__(WARPS * 32) nnls_fast_kernel(const NnlsDeviceA
           zmax = fmax(zmax, __shfl_xor_sync(FULL, zmax, o));
         }
         rel = dmax / zmax;
-        // each pass shrinks the error by ~the relative error of the carried inverse: a first
-        // correction above 1e-3 means the active-set decisions themselves were made on bad numbers
-        if ((pass == 0 && rel > 1e-3) || !pos) { mode = kNnlsRedo; break; }
+        // the first correction measures how far the carried solution had drifted while the
+        // active-set decisions were being made; wrong results only appeared above 3e-4
+        if ((pass == 0 && rel > 5e-5) || !pos) { mode = kNnlsRedo; break; }
         for (int i = lane; i < k; i += 32) { zs[i] += vs[i]; xs[P[i]] = zs[i]; }
         __syncwarp();
         if (rel < 1e-13) break;
@@ -286,11 +356,16 @@ __global__ void __launch_bounds__(WARPS * 32) nnls_fast_kernel(const NnlsDeviceA
       if (mode == 1) {
         residual();
         double wmax = 0.0;
-        for (int j = lane, q = 0; j < n; j += 32, q++)
-          if (!((inP >> q) & 1u) && k < n) wmax = fmax(wmax, dual_of(j));
+        for (int j0 = lane, q0 = 0; j0 < n; j0 += 128, q0 += 4) {
+          double w4[4];
+          dual4(j0, w4);
+#pragma unroll
+          for (int t = 0; t < 4; t++)
+            if (j0 + 32 * t < n && !((inP >> (q0 + t)) & 1u)) wmax = fmax(wmax, w4[t]);
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) wmax = fmax(wmax, __shfl_xor_sync(FULL, wmax, o));
-        if (wmax > 1e-9 * hmax) mode = kNnlsRedo;  // not a Kuhn-Tucker point after all
+        if (wmax > 1e-12 * hmax) mode = kNnlsRedo;  // not (to rounding) a Kuhn-Tucker point
       }
     }
 

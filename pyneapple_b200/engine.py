@@ -236,8 +236,11 @@ def nnls_fit(basis, reg_matrix, signal, max_iter: int, *, device: int = 0, chunk
     prob.n_b, prob.n_bins, prob.rtr_halfband, prob.max_iter = n_b, n_bins, W, int(max_iter)
     if algorithm not in ("auto", "robust"):
         raise ValueError("algorithm must be 'auto' or 'robust'")
-    # an un-regularised dictionary is far too ill-conditioned for the inverse-update fast path
-    prob.algorithm = 1 if (algorithm == "robust" or not np.any(band)) else 0
+    # an un- or barely regularised dictionary is too ill-conditioned for the inverse-update fast
+    # path (the minimiser is then numerically non-unique and only the Cholesky path follows
+    # SciPy's choice): go straight to the robust kernel below a relative weight of 1e-8
+    reg_weight = float(np.abs(band[:, W]).max()) / float((B * B).sum(axis=0).max())
+    prob.algorithm = 1 if (algorithm == "robust" or reg_weight < 1e-8) else 0
     if _is_torch_cuda(signal):
         import torch
 

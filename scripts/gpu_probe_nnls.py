@@ -16,4 +16,6 @@ for order in (2, 0, 1, 3):
         e0.record(); r = engine.nnls_fit(B, R, y, 250); e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     it = r["iterations"].cpu().numpy(); st = r["status"].cpu().numpy(); k = (r["coefficients"] > 0).sum(1).cpu().numpy()
-    print(f"reg{order}: {y.shape[0]} vox {ms:.1f} ms -> {y.shape[0]/ms*1e3/1e6:.2f} Mvox/s; iters mean {it.mean():.1f} max {it.max()}; active mean {k.mean():.1f} max {k.max()}; ok {np.mean(st==1):.4f}")
+    from pyneapple_b200 import _lib
+    redo = _lib.load().pnb_nnls_last_redo_count(0)
+    print(f"reg{order}: redo {redo} {y.shape[0]} vox {ms:.1f} ms -> {y.shape[0]/ms*1e3/1e6:.2f} Mvox/s; iters mean {it.mean():.1f} max {it.max()}; active mean {k.mean():.1f} max {k.max()}; ok {np.mean(st==1):.4f}")
