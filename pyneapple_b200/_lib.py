@@ -15,7 +15,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-SO_PATH = os.path.join(CSRC, "libpnb200.so")
+SO_PATH = os.environ.get("PNB_LIB") or os.path.join(CSRC, "libpnb200.so")
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "pyneapple_b200.h")
 
 _lib = None

@@ -9,7 +9,14 @@
 
 namespace {
 
-constexpr int kWarps = 8;
+#ifndef PNB_NNLS_WARPS
+#define PNB_NNLS_WARPS 8
+#endif
+constexpr int kWarps = PNB_NNLS_WARPS;        // robust kernel
+#ifndef PNB_NNLS_FAST_WARPS
+#define PNB_NNLS_FAST_WARPS 8
+#endif
+constexpr int kFastWarps = PNB_NNLS_FAST_WARPS;  // fast kernel
 constexpr size_t kSmemBudget = 220 * 1024;
 
 struct NnlsCtx {
@@ -46,36 +53,54 @@ int check(const pnb_nnls_problem *p) {
 }
 
 // the largest active-set size whose factor fits shared memory next to everything else
-int pick_kmax(int m, int n, int W) {
+int pick_kmax(int m, int n, int W, int warps) {
   int k = n;
-  while (k > 8 && pnb::nnls_smem_bytes(m, n, W, k, kWarps) > kSmemBudget) k--;
+  while (k > 8 && pnb::nnls_smem_bytes(m, n, W, k, warps) > kSmemBudget) k--;
+  return k;
+}
+constexpr int kRedoWarps = 2;  // the few voxels the fast path hands over have large active sets:
+                               // fewer warps per SM, but a factor that stays in shared memory
+
+int pick_mt(int m) { return m <= 8 ? 8 : (m <= 16 ? 16 : (m <= 24 ? 24 : (m <= 32 ? 32 : 0))); }
+
+int pick_kcap_fast(int mt, int n, int W) {
+  int k = n < 96 ? n : 96;
+  while (k > 8 && pnb::nnls_fast_smem_bytes(mt, n, W, k, kFastWarps) > kSmemBudget) k--;
   return k;
 }
 
-int pick_kcap_fast(int m, int n, int W) {
-  int k = n < 96 ? n : 96;
-  while (k > 8 && pnb::nnls_fast_smem_bytes(m, n, W, k, kWarps) > kSmemBudget) k--;
-  return k;
+using FastKernel = void (*)(const pnb::NnlsDeviceArgs);
+FastKernel fast_kernel_for(int mt) {
+  switch (mt) {
+    case 8: return pnb::nnls_fast_kernel<kFastWarps, 8>;
+    case 16: return pnb::nnls_fast_kernel<kFastWarps, 16>;
+    case 24: return pnb::nnls_fast_kernel<kFastWarps, 24>;
+    case 32: return pnb::nnls_fast_kernel<kFastWarps, 32>;
+  }
+  return nullptr;
 }
 
 int launch(NnlsCtx &C, const pnb_nnls_problem *p, const double *B, const double *rtr, const double *y,
            long long n_vox, double *coef, double *rn, int *st, int *it, double *r2, cudaStream_t stream) {
   const int m = p->n_b, n = p->n_bins, W = p->rtr_halfband;
-  const int kmax = pick_kmax(m, n, W);
+  const int kmax = pick_kmax(m, n, W, kWarps);
   const size_t smem = pnb::nnls_smem_bytes(m, n, W, kmax, kWarps);
   if (smem > 227 * 1024) return pnbi::fail(PNB_E_UNSUPPORTED, "n_b x n_bins too large for shared memory");
   auto robust = pnb::nnls_kernel<kWarps>;
-  auto fast = pnb::nnls_fast_kernel<kWarps>;
-  const int kcap = pick_kcap_fast(m, n, W);
-  const size_t smem_fast = pnb::nnls_fast_smem_bytes(m, n, W, kcap, kWarps);
+  const int mt = pick_mt(m);
+  FastKernel fast = fast_kernel_for(mt);
+  const bool use_fast = p->algorithm == 0 && fast != nullptr;  // more than 32 measurements: robust only
+  const int kcap = use_fast ? pick_kcap_fast(mt, n, W) : 0;
+  const size_t smem_fast = use_fast ? pnb::nnls_fast_smem_bytes(mt, n, W, kcap, kFastWarps) : 0;
   PNBI_CUDA(cudaFuncSetAttribute(robust, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  PNBI_CUDA(cudaFuncSetAttribute(fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast));
+  if (use_fast) PNBI_CUDA(cudaFuncSetAttribute(fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast));
   int dev = 0, sms = 0, bps = 0, bps_fast = 0;
   PNBI_CUDA(cudaGetDevice(&dev));
   PNBI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   PNBI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, robust, kWarps * 32, smem));
-  PNBI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_fast, fast, kWarps * 32, smem_fast));
-  if (bps < 1 || bps_fast < 1) return pnbi::fail(PNB_E_UNSUPPORTED, "NNLS kernel does not fit on this device");
+  if (use_fast)
+    PNBI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_fast, fast, kFastWarps * 32, smem_fast));
+  if (bps < 1 || (use_fast && bps_fast < 1)) return pnbi::fail(PNB_E_UNSUPPORTED, "NNLS kernel does not fit on this device");
   const long long want = (n_vox + kWarps - 1) / kWarps;
   const size_t per_warp = (size_t)n * (n + 1) / 2 + 5 * (size_t)n;
   const size_t need = (size_t)bps * sms * kWarps * per_warp;
@@ -101,18 +126,26 @@ int launch(NnlsCtx &C, const pnb_nnls_problem *p, const double *B, const double 
   a.B = B; a.rtr = rtr; a.y = y; a.coef = coef; a.rnorm = rn; a.status = st; a.iters = it; a.r2 = r2;
   a.scratch = C.scratch;
   a.redo_count = ctr + 1; a.redo_list = C.redo_list;
-  C.last_redo = (p->algorithm == 0) ? ctr + 1 : nullptr;
-  if (p->algorithm == 0) {
+  C.last_redo = use_fast ? ctr + 1 : nullptr;
+  if (use_fast) {
     long long grid = (long long)bps_fast * sms;
-    if (want < grid) grid = want;
+    const long long want_fast = (n_vox + kFastWarps - 1) / kFastWarps;
+    if (want_fast < grid) grid = want_fast;
     if (grid < 1) grid = 1;
     a.counter = ctr; a.kmax = kcap; a.work_list = nullptr; a.work_count = nullptr;
-    fast<<<(unsigned)grid, kWarps * 32, smem_fast, stream>>>(a);
+    fast<<<(unsigned)grid, kFastWarps * 32, smem_fast, stream>>>(a);
     PNBI_CUDA(cudaGetLastError());
     pnbi::count_launch();
     // voxels the fast path could not certify (the count stays on the device)
-    a.counter = ctr + 2; a.kmax = kmax; a.work_list = C.redo_list; a.work_count = ctr + 1;
-    robust<<<(unsigned)((long long)bps * sms), kWarps * 32, smem, stream>>>(a);
+    auto redo = pnb::nnls_kernel<kRedoWarps>;
+    const int kmax_redo = pick_kmax(m, n, W, kRedoWarps);
+    const size_t smem_redo = pnb::nnls_smem_bytes(m, n, W, kmax_redo, kRedoWarps);
+    PNBI_CUDA(cudaFuncSetAttribute(redo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_redo));
+    int bps_redo = 0;
+    PNBI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_redo, redo, kRedoWarps * 32, smem_redo));
+    if (bps_redo < 1) return pnbi::fail(PNB_E_UNSUPPORTED, "NNLS redo kernel does not fit on this device");
+    a.counter = ctr + 2; a.kmax = kmax_redo; a.work_list = C.redo_list; a.work_count = ctr + 1;
+    redo<<<(unsigned)((long long)bps_redo * sms), kRedoWarps * 32, smem_redo, stream>>>(a);
     PNBI_CUDA(cudaGetLastError());
     pnbi::count_launch();
   } else {

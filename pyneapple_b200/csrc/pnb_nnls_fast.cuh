@@ -13,17 +13,26 @@
 // the Cholesky kernel latency bound, and slots need no ordering, so a leaving
 // variable is replaced by the last slot instead of shifting a factor.
 //
+// Data placement (the first profile of this kernel showed 10 % DFMA against 60 %
+// address / branch instructions, so the hot loops are written for a compile-
+// time measurement count MT): the dictionary is kept bin-major in shared memory,
+// Bt[bin][MT + 2] (zero padded; the +2 makes the 128-bit loads of consecutive
+// lanes bank-conflict free), so one bin's column is MT/2 LDS.128 with constant
+// offsets; the voxel's signal, the residual and the candidate column live in
+// registers; the coefficient vector is zero padded by W on both sides so the
+// banded regulariser needs no bounds checks.
+//
 // Updating an inverse is less stable than updating a factor.  For the
-// regularised dictionaries this path is meant for (cond(G_PP) ~ 1e6..1e8) the
-// solution is polished with up to four steps of iterative refinement against the true
-// residual at the end and agrees with SciPy to ~2e-11 with identical iteration
-// counts (scripts/proto_nnls_inverse.py).  A voxel is handed to the robust
-// Cholesky kernel instead (status kNnlsRedo) when
+// regularised dictionaries this path is meant for the solution is polished with
+// up to four steps of iterative refinement against the true residual at the end
+// and agrees with SciPy to ~2e-11 with identical iteration counts
+// (scripts/proto_nnls_inverse.py).  A voxel is handed to the robust Cholesky
+// kernel instead (status kNnlsRedo) when
 //   * its active set outgrows the shared-memory inverse,
 //   * the first polish step moves the solution by more than 5e-5 relative or the
 //     refinement has not converged to 1e-10 after four steps, or
 //   * the polished point violates the Kuhn-Tucker conditions,
-// which is what happens for weakly / un-regularised problems (mu <~ 5e-4).
+// which is what happens for weakly regularised problems (mu <~ 5e-4).
 #pragma once
 #include "pnb_nnls_kernel.cuh"
 
@@ -33,25 +42,49 @@ constexpr int kNnlsRedo = 4;  // status: re-run this voxel with the robust kerne
 
 __device__ __forceinline__ int hpos(int i, int c) { return (i * (i + 1)) / 2 + c; }  // i >= c
 
-template <int WARPS>
+// doubles of shared memory one warp needs (kept even so every sub-array stays 16-byte aligned)
+__host__ __device__ inline int nnls_fast_per_warp(int n, int W, int mt, int kcap) {
+  const int nx = (n + 2 * W + 1) & ~1, nw = (n + 1) & ~1, kc = (kcap + 1) & ~1;
+  const int htri = (kcap * (kcap + 1) / 2 + 1) & ~1;
+  return nx + nw + htri + 3 * kc + kc / 2 + 2;
+}
+
+template <int WARPS, int MT>
 __global__ void __launch_bounds__(WARPS * 32) nnls_fast_kernel(const NnlsDeviceArgs a) {
+  static_assert(MT % 2 == 0 && MT <= 32, "MT must be even and at most 32");
   extern __shared__ double smem[];
+  constexpr int LD = MT + 2;  // row stride of the bin-major dictionary
   const int m = a.m, n = a.n, W = a.W, BW = 2 * a.W + 1;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int kcap = a.kmax;
   const unsigned FULL = 0xffffffffu;
-  double *B_s = smem;
-  double *rtr_s = B_s + (size_t)m * n;
-  const int htri = kcap * (kcap + 1) / 2;
-  const int per_warp = 2 * n + 2 * m + htri + 3 * kcap + (kcap + 1) / 2 + 2;
-  double *base = rtr_s + (size_t)n * BW + (size_t)wid * per_warp;
-  double *xs = base, *ws = xs + n, *ys = ws + n, *rs = ys + m;
-  double *H = rs + m;
-  double *zs = H + htri, *gs = zs + kcap, *vs = gs + kcap;
-  int *P = reinterpret_cast<int *>(vs + kcap);
-  for (int i = threadIdx.x; i < m * n; i += WARPS * 32) B_s[i] = a.B[i];
+  // CTA-shared: Bt[n][LD], rtr[n][BW], gdiag[n]
+  double *Bt = smem;
+  double *rtr_s = Bt + (size_t)n * LD;
+  double *gdiag = rtr_s + (((size_t)n * BW + 1) & ~(size_t)1);
+  const int nx = (n + 2 * W + 1) & ~1, nw = (n + 1) & ~1, kc = (kcap + 1) & ~1;
+  const int htri = (kcap * (kcap + 1) / 2 + 1) & ~1;
+  double *base = gdiag + nw + (size_t)wid * nnls_fast_per_warp(n, W, MT, kcap);
+  double *xs_raw = base, *ws = xs_raw + nx;
+  double *H = ws + nw;
+  double *zs = H + htri, *gs = zs + kc, *vs = gs + kc;
+  int *P = reinterpret_cast<int *>(vs + kc);
+  double *xs = xs_raw + W;  // xs[-W .. n-1+W], the padding stays zero
+  for (int i = threadIdx.x; i < n * LD; i += WARPS * 32) {
+    const int j = i / LD, b = i - j * LD;
+    Bt[i] = (b < m) ? a.B[(size_t)b * n + j] : 0.0;
+  }
   for (int i = threadIdx.x; i < n * BW; i += WARPS * 32) rtr_s[i] = a.rtr[i];
   __syncthreads();
+  for (int j = threadIdx.x; j < n; j += WARPS * 32) {
+    double acc = rtr_s[j * BW + W];
+    for (int b = 0; b < MT; b++) acc += Bt[j * LD + b] * Bt[j * LD + b];
+    gdiag[j] = acc;
+  }
+  for (int i = lane; i < nx; i += 32) xs_raw[i] = 0.0;
+  __syncthreads();
+
+  double yr[MT], rr[MT];  // signal and residual of the current voxel, replicated in every lane
 
   for (;;) {
     unsigned long long vq = 0;
@@ -60,18 +93,35 @@ __global__ void __launch_bounds__(WARPS * 32) nnls_fast_kernel(const NnlsDeviceA
     if (vox >= a.n_vox) break;
 
     bool fin = true;
-    for (int b = lane; b < m; b += 32) {
-      const double v = a.y[vox * m + b];
-      ys[b] = v;
-      fin = fin && finite_d(v);
+    {
+      const double v = (lane < m) ? a.y[vox * m + lane] : 0.0;
+      fin = __all_sync(FULL, finite_d(v));
+#pragma unroll
+      for (int b = 0; b < MT; b++) yr[b] = __shfl_sync(FULL, v, b);
     }
-    fin = __all_sync(FULL, fin);
-    __syncwarp();
+    // one bin's column dotted with a register vector
+    auto col_dot = [&](int j, const double (&vec)[MT]) -> double {
+      const double2 *bp = reinterpret_cast<const double2 *>(Bt + j * LD);
+      double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+      for (int t = 0; t < MT / 2; t++) {
+        const double2 v = bp[t];
+        a0 += v.x * vec[2 * t];
+        a1 += v.y * vec[2 * t + 1];
+      }
+      return a0 + a1;
+    };
+    auto band_dot = [&](int j) -> double {
+      const double *rp = rtr_s + j * BW;
+      const double *xp = xs + (j - W);
+      double acc = 0.0;
+      for (int t = 0; t < BW; t++) acc += rp[t] * xp[t];
+      return acc;
+    };
     double hmax = 0.0;
     for (int j = lane; j < n; j += 32) {
-      double acc = 0.0;
-      for (int b = 0; b < m; b++) acc += B_s[b * n + j] * ys[b];
-      ws[j] = acc; xs[j] = 0.0;
+      const double acc = col_dot(j, yr);
+      ws[j] = acc;
       hmax = fmax(hmax, fabs(acc));
     }
 #pragma unroll
@@ -80,26 +130,17 @@ __global__ void __launch_bounds__(WARPS * 32) nnls_fast_kernel(const NnlsDeviceA
     int k = 0, iter = 0, mode = fin ? 1 : 2;
     __syncwarp();
 
-    // dst = H src over the k active slots (symmetric packed storage, two accumulators per row)
+    // dst = H src over the k active slots (symmetric packed storage)
     auto matvec = [&](const double *src, double *dst) {
       for (int i = lane; i < k; i += 32) {
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        const int rb = (i * (i + 1)) / 2;
+        double a0 = 0.0, a1 = 0.0;
+        const double *hp = H + (i * (i + 1)) / 2;
         int c = 0;
-        for (; c + 3 <= i; c += 4) {
-          a0 += H[rb + c] * src[c]; a1 += H[rb + c + 1] * src[c + 1];
-          a2 += H[rb + c + 2] * src[c + 2]; a3 += H[rb + c + 3] * src[c + 3];
-        }
-        for (; c <= i; c++) a0 += H[rb + c] * src[c];
-        int idx = ((i + 1) * (i + 2)) / 2 + i;
-        int r = i + 1;
-        for (; r + 1 < k; r += 2) {
-          a1 += H[idx] * src[r];
-          a2 += H[idx + r + 1] * src[r + 1];
-          idx += 2 * r + 3;
-        }
-        if (r < k) a3 += H[idx] * src[r];
-        dst[i] = (a0 + a1) + (a2 + a3);
+        for (; c + 1 <= i; c += 2) { a0 += hp[c] * src[c]; a1 += hp[c + 1] * src[c + 1]; }
+        if (c <= i) a0 += hp[c] * src[c];
+        hp += 2 * i + 1;  // element (i+1, i)
+        for (int r = i + 1; r < k; r++) { a1 += hp[0] * src[r]; hp += r + 1; }
+        dst[i] = a0 + a1;
       }
       __syncwarp();
     };
@@ -115,9 +156,8 @@ __global__ void __launch_bounds__(WARPS * 32) nnls_fast_kernel(const NnlsDeviceA
       const double dinv = 1.0 / dq;
       for (int i = lane; i < k; i += 32) {
         const double gi = gs[i] * dinv;
-        const int rb = (i * (i + 1)) / 2;
-#pragma unroll 4
-        for (int c = 0; c <= i; c++) H[rb + c] -= gi * gs[c];
+        double *hp = H + (i * (i + 1)) / 2;
+        for (int c = 0; c <= i; c++) hp[c] -= gi * gs[c];
         zs[i] -= gi * zq;
       }
       __syncwarp();
@@ -133,68 +173,48 @@ __global__ void __launch_bounds__(WARPS * 32) nnls_fast_kernel(const NnlsDeviceA
       k -= 1;
       __syncwarp();
     };
-    // r = y - B_P z ;  returns nothing, rs filled
+    // rr = y - B_P z, replicated in every lane
     auto residual = [&]() {
-      if (m <= 16) {
+      double acc;
+      if (MT <= 16) {
         const int b = lane & 15, half = lane >> 4;
         const int mid = (k + 1) >> 1;
-        const int i0 = half ? mid : 0, i1 = half ? k : mid;
+        const int i1 = half ? k : mid;
         double a0 = 0.0, a1 = 0.0;
-        if (b < m) {
-          int i = i0;
-          for (; i + 1 < i1; i += 2) {
-            a0 += B_s[b * n + P[i]] * zs[i];
-            a1 += B_s[b * n + P[i + 1]] * zs[i + 1];
-          }
-          if (i < i1) a0 += B_s[b * n + P[i]] * zs[i];
+        int i = half ? mid : 0;
+        for (; i + 1 < i1; i += 2) {
+          a0 += Bt[P[i] * LD + b] * zs[i];
+          a1 += Bt[P[i + 1] * LD + b] * zs[i + 1];
         }
-        double acc = a0 + a1;
+        if (i < i1) a0 += Bt[P[i] * LD + b] * zs[i];
+        acc = a0 + a1;
         acc += __shfl_xor_sync(FULL, acc, 16);
-        if (half == 0 && b < m) rs[b] = ys[b] - acc;
       } else {
-        for (int b = lane; b < m; b += 32) {
-          double a0 = 0.0, a1 = 0.0;
-          int i = 0;
-          for (; i + 1 < k; i += 2) {
-            a0 += B_s[b * n + P[i]] * zs[i];
-            a1 += B_s[b * n + P[i + 1]] * zs[i + 1];
-          }
-          if (i < k) a0 += B_s[b * n + P[i]] * zs[i];
-          rs[b] = ys[b] - (a0 + a1);
+        const int b = lane < MT ? lane : 0;
+        double a0 = 0.0, a1 = 0.0;
+        int i = 0;
+        for (; i + 1 < k; i += 2) {
+          a0 += Bt[P[i] * LD + b] * zs[i];
+          a1 += Bt[P[i + 1] * LD + b] * zs[i + 1];
         }
+        if (i < k) a0 += Bt[P[i] * LD + b] * zs[i];
+        acc = a0 + a1;
       }
-      __syncwarp();
+#pragma unroll
+      for (int b = 0; b < MT; b++) rr[b] = yr[b] - __shfl_sync(FULL, acc, b);
     };
-    // duals of four bins of this lane at once (independent accumulation chains)
-    auto dual4 = [&](int j0, double (&w4)[4]) {
-      double a[4] = {0.0, 0.0, 0.0, 0.0};
-      int jj[4];
+    auto write_r2 = [&](double ss_res) {
+      double sm = 0.0;
 #pragma unroll
-      for (int t = 0; t < 4; t++) jj[t] = (j0 + 32 * t < n) ? j0 + 32 * t : j0;
-#pragma unroll 4
-      for (int b = 0; b < m; b++) {
-        const double rb = rs[b];
-        const double *row = B_s + b * n;
+      for (int b = 0; b < MT; b++) sm += yr[b];
+      const double mean = sm / (double)m;
+      double st = 0.0;
 #pragma unroll
-        for (int t = 0; t < 4; t++) a[t] += row[jj[t]] * rb;
+      for (int b = 0; b < MT; b++) {
+        const double d = yr[b] - mean;
+        if (b < m) st += d * d;
       }
-#pragma unroll
-      for (int t = 0; t < 4; t++) {
-        const int j = jj[t];
-        const int lo = (j - W < 0) ? 0 : j - W, hi = (j + W > n - 1) ? n - 1 : j + W;
-        double acc = 0.0;
-        for (int jn = lo; jn <= hi; jn++) acc += rtr_s[j * BW + (jn - j) + W] * xs[jn];
-        w4[t] = a[t] - acc;
-      }
-    };
-    auto dual_of = [&](int j) -> double {
-      double a0 = 0.0, a1 = 0.0;
-      int b = 0;
-      for (; b + 1 < m; b += 2) { a0 += B_s[b * n + j] * rs[b]; a1 += B_s[(b + 1) * n + j] * rs[b + 1]; }
-      if (b < m) a0 += B_s[b * n + j] * rs[b];
-      const int lo = (j - W < 0) ? 0 : j - W, hi = (j + W > n - 1) ? n - 1 : j + W;
-      for (int jn = lo; jn <= hi; jn++) a1 -= rtr_s[j * BW + (jn - j) + W] * xs[jn];
-      return a0 + a1;
+      if (lane == 0) a.r2[vox] = (st > 0.0) ? 1.0 - ss_res / st : nan("");
     };
 
     while (mode == 1 && k < n) {
@@ -216,24 +236,23 @@ __global__ void __launch_bounds__(WARPS * 32) nnls_fast_kernel(const NnlsDeviceA
         }
         if (bj < 0) break;
         const int j = bj;
+        double cj[MT];  // candidate column in registers
+        {
+          const double2 *bp = reinterpret_cast<const double2 *>(Bt + j * LD);
+#pragma unroll
+          for (int t = 0; t < MT / 2; t++) { const double2 v = bp[t]; cj[2 * t] = v.x; cj[2 * t + 1] = v.y; }
+        }
         for (int i = lane; i < k; i += 32) {
           const int p = P[i];
-          double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-          int b = 0;
-          for (; b + 3 < m; b += 4) {
-            a0 += B_s[b * n + p] * B_s[b * n + j];
-            a1 += B_s[(b + 1) * n + p] * B_s[(b + 1) * n + j];
-            a2 += B_s[(b + 2) * n + p] * B_s[(b + 2) * n + j];
-            a3 += B_s[(b + 3) * n + p] * B_s[(b + 3) * n + j];
-          }
-          for (; b < m; b++) a0 += B_s[b * n + p] * B_s[b * n + j];
-          double acc = (a0 + a1) + (a2 + a3);
+          double acc = col_dot(p, cj);
           const int d = j - p;
           if (d >= -W && d <= W) acc += rtr_s[p * BW + d + W];
           gs[i] = acc;
         }
-        double gjj = rtr_s[j * BW + W], hj = 0.0;
-        for (int b = 0; b < m; b++) { const double bj2 = B_s[b * n + j]; gjj += bj2 * bj2; hj += bj2 * ys[b]; }
+        double hj = 0.0;
+#pragma unroll
+        for (int b = 0; b < MT; b++) hj += cj[b] * yr[b];
+        const double gjj = gdiag[j];
         __syncwarp();
         matvec(gs, vs);
         double p0 = 0.0, p1 = 0.0;
@@ -260,14 +279,13 @@ __global__ void __launch_bounds__(WARPS * 32) nnls_fast_kernel(const NnlsDeviceA
         const double sinv = 1.0 / s_new;
         for (int i = lane; i < k; i += 32) {
           const double vi = vs[i] * sinv;
-          const int rb = (i * (i + 1)) / 2;
-#pragma unroll 4
-          for (int c = 0; c <= i; c++) H[rb + c] += vi * vs[c];
+          double *hp = H + (i * (i + 1)) / 2;
+          for (int c = 0; c <= i; c++) hp[c] += vi * vs[c];
           zs[i] -= vs[i] * zeta;
         }
-        const int rb = (k * (k + 1)) / 2;
-        for (int c = lane; c < k; c += 32) H[rb + c] = -vs[c] * sinv;
-        if (lane == 0) { H[rb + k] = sinv; zs[k] = zeta; P[k] = jsel; ws[jsel] = 0.0; }
+        double *hk = H + (k * (k + 1)) / 2;
+        for (int c = lane; c < k; c += 32) hk[c] = -vs[c] * sinv;
+        if (lane == 0) { hk[k] = sinv; zs[k] = zeta; P[k] = jsel; ws[jsel] = 0.0; }
         if ((jsel & 31) == lane) inP |= 1u << (jsel >> 5);
         k += 1;
         __syncwarp();
@@ -286,13 +304,13 @@ __global__ void __launch_bounds__(WARPS * 32) nnls_fast_kernel(const NnlsDeviceA
             if (alpha > t) { alpha = t; jj = i; }
           }
         }
+        if (!__any_sync(FULL, jj >= 0)) break;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
           const double oa = __shfl_xor_sync(FULL, alpha, o);
           const int oj = __shfl_xor_sync(FULL, jj, o);
           if (oj >= 0 && (jj < 0 || oa < alpha || (oa == alpha && oj < jj))) { alpha = oa; jj = oj; }
         }
-        if (jj < 0) break;
         for (int i = lane; i < k; i += 32) {
           const int p = P[i];
           xs[p] += alpha * (zs[i] - xs[p]);
@@ -303,9 +321,9 @@ __global__ void __launch_bounds__(WARPS * 32) nnls_fast_kernel(const NnlsDeviceA
           int bad = n;
           for (int i = lane; i < k; i += 32)
             if (xs[P[i]] <= 0.0 && i < bad) bad = i;
+          if (!__any_sync(FULL, bad < n)) break;
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) bad = min(bad, __shfl_xor_sync(FULL, bad, o));
-          if (bad >= n) break;
           remove_at(bad);
         }
       }
@@ -313,22 +331,17 @@ __global__ void __launch_bounds__(WARPS * 32) nnls_fast_kernel(const NnlsDeviceA
       for (int i = lane; i < k; i += 32) xs[P[i]] = zs[i];
       __syncwarp();
       residual();
-      for (int j0 = lane, q0 = 0; j0 < n; j0 += 128, q0 += 4) {
-        double w4[4];
-        dual4(j0, w4);
-#pragma unroll
-        for (int t = 0; t < 4; t++)
-          if (j0 + 32 * t < n) ws[j0 + 32 * t] = ((inP >> (q0 + t)) & 1u) ? 0.0 : w4[t];
-      }
+      for (int j = lane, q = 0; j < n; j += 32, q++)
+        ws[j] = ((inP >> q) & 1u) ? 0.0 : col_dot(j, rr) - band_dot(j);
       __syncwarp();
     }
 
-    // ---- polish: two refinement steps with the true residual, then verify ------------
+    // ---- polish: refinement steps with the true residual, then verify ----------------
     if (mode == 1 && k > 0) {
       double rel = 1.0;
       for (int pass = 0; pass < 4 && mode == 1; pass++) {
         residual();
-        for (int i = lane; i < k; i += 32) gs[i] = dual_of(P[i]);
+        for (int i = lane; i < k; i += 32) { const int p = P[i]; gs[i] = col_dot(p, rr) - band_dot(p); }
         __syncwarp();
         matvec(gs, vs);
         bool pos = true;
@@ -353,16 +366,11 @@ __global__ void __launch_bounds__(WARPS * 32) nnls_fast_kernel(const NnlsDeviceA
         if (rel < 1e-13) break;
       }
       if (mode == 1 && rel > 1e-10) mode = kNnlsRedo;  // refinement did not converge
-      if (mode == 1) {
+      if (mode == 1 && k < n) {
         residual();
         double wmax = 0.0;
-        for (int j0 = lane, q0 = 0; j0 < n; j0 += 128, q0 += 4) {
-          double w4[4];
-          dual4(j0, w4);
-#pragma unroll
-          for (int t = 0; t < 4; t++)
-            if (j0 + 32 * t < n && !((inP >> (q0 + t)) & 1u)) wmax = fmax(wmax, w4[t]);
-        }
+        for (int j = lane, q = 0; j < n; j += 32, q++)
+          if (!((inP >> q) & 1u)) wmax = fmax(wmax, col_dot(j, rr) - band_dot(j));
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) wmax = fmax(wmax, __shfl_xor_sync(FULL, wmax, o));
         if (wmax > 1e-12 * hmax) mode = kNnlsRedo;  // not (to rounding) a Kuhn-Tucker point
@@ -371,47 +379,30 @@ __global__ void __launch_bounds__(WARPS * 32) nnls_fast_kernel(const NnlsDeviceA
 
     double *out = a.coef + vox * (long long)n;
     if (mode == 1) {
-      if (k == 0) residual();
-      double part = 0.0, top = 0.0;
-      for (int b = lane; b < m; b += 32) top += rs[b] * rs[b];
+      residual();
+      double top = 0.0;
+#pragma unroll
+      for (int b = 0; b < MT; b++) top += rr[b] * rr[b];
+      double part = 0.0;
       for (int j = lane; j < n; j += 32) {
         const double xj = xs[j];
         out[j] = xj;
-        if (xj != 0.0) {
-          const int lo = (j - W < 0) ? 0 : j - W, hi = (j + W > n - 1) ? n - 1 : j + W;
-          double acc = 0.0;
-          for (int jn = lo; jn <= hi; jn++) acc += rtr_s[j * BW + (jn - j) + W] * xs[jn];
-          part += xj * acc;
-        }
+        if (xj != 0.0) part += xj * band_dot(j);
       }
-      top = warp_sum(top);
       const double tot = top + warp_sum(part);
       if (lane == 0) a.rnorm[vox] = sqrt(tot > 0.0 ? tot : 0.0);
-      if (a.r2) {
-        double sm = 0.0;
-        for (int b = lane; b < m; b += 32) sm += ys[b];
-        const double mean = warp_sum(sm) / (double)m;
-        double st = 0.0;
-        for (int b = lane; b < m; b += 32) { const double d = ys[b] - mean; st += d * d; }
-        st = warp_sum(st);
-        if (lane == 0) a.r2[vox] = (st > 0.0) ? 1.0 - top / st : nan("");
-      }
+      if (a.r2) write_r2(top);
     } else if (mode != kNnlsRedo) {
-      double part = 0.0;
-      for (int b = lane; b < m; b += 32) part += ys[b] * ys[b];
+      double tot = 0.0;
+#pragma unroll
+      for (int b = 0; b < MT; b++) tot += yr[b] * yr[b];
       for (int j = lane; j < n; j += 32) out[j] = 0.0;
-      const double tot = warp_sum(part);
       if (lane == 0) a.rnorm[vox] = sqrt(tot);
-      if (a.r2) {
-        double sm = 0.0;
-        for (int b = lane; b < m; b += 32) sm += ys[b];
-        const double mean = warp_sum(sm) / (double)m;
-        double st = 0.0;
-        for (int b = lane; b < m; b += 32) { const double d = ys[b] - mean; st += d * d; }
-        st = warp_sum(st);
-        if (lane == 0) a.r2[vox] = (st > 0.0) ? 1.0 - tot / st : nan("");
-      }
+      if (a.r2) write_r2(tot);
     }
+    // leave the coefficient scratch clean for the next voxel
+    __syncwarp();
+    for (int i = lane; i < k; i += 32) xs[P[i]] = 0.0;
     if (lane == 0) {
       a.status[vox] = mode;
       a.iters[vox] = iter;
@@ -424,9 +415,9 @@ __global__ void __launch_bounds__(WARPS * 32) nnls_fast_kernel(const NnlsDeviceA
   }
 }
 
-inline size_t nnls_fast_smem_bytes(int m, int n, int W, int kcap, int warps) {
-  const size_t per_warp = 2 * (size_t)n + 2 * m + (size_t)kcap * (kcap + 1) / 2 + 3 * (size_t)kcap + (kcap + 1) / 2 + 2;
-  return sizeof(double) * ((size_t)m * n + (size_t)n * (2 * W + 1) + warps * per_warp);
+inline size_t nnls_fast_smem_bytes(int mt, int n, int W, int kcap, int warps) {
+  const size_t shared = (size_t)n * (mt + 2) + (((size_t)n * (2 * W + 1) + 1) & ~(size_t)1) + ((n + 1) & ~1);
+  return sizeof(double) * (shared + (size_t)warps * nnls_fast_per_warp(n, W, mt, kcap));
 }
 
 }  // namespace pnb

@@ -5,10 +5,17 @@ usage: ncu_hotspots.py <sass.csv from `ncu -i rep --page source --csv --print-so
 import csv, re, sys, collections
 
 sass_csv, disasm = sys.argv[1], sys.argv[2]
+func = sys.argv[3] if len(sys.argv) > 3 else None  # substring of the mangled kernel name
 # address -> (file, line) with inline context collapsed to innermost
 addr2line = {}
 cur = None
+in_func = func is None
 for ln in open(disasm):
+    if ln.startswith("//--------------------- .text."):
+        in_func = func is None or func in ln
+        continue
+    if not in_func:
+        continue
     m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
     if m:
         cur = (m.group(1).split("/")[-1], int(m.group(2)))

@@ -101,6 +101,27 @@ def test_weak_regularisation_falls_back_to_the_robust_path(order, mu):
     assert np.abs(s.params_["coefficients"] - ref["x"]).max() <= 1e-6
 
 
+@pytest.mark.parametrize("n_b", [7, 24, 30, 40])
+def test_other_measurement_counts(n_b):
+    """Fast-path specialisations for <= 8 / 16 / 24 / 32 measurements, robust path beyond."""
+    from oracle import c_oracle, ref_port
+
+    rng = np.random.default_rng(n_b)
+    b = np.sort(rng.uniform(0, 1500, n_b))
+    b[0] = 0.0
+    n = 192
+    f = rng.uniform(0.05, 0.4, n)[:, None]
+    y = 1000 * (f * np.exp(-b * rng.uniform(0.01, 0.1, n)[:, None]) +
+                (1 - f) * np.exp(-b * rng.uniform(5e-4, 2.5e-3, n)[:, None])) + rng.normal(0, 10, (n, n_b))
+    model = models.NNLSModel(d_range=(0.0005, 0.3), n_bins=120)
+    s = NNLSSolver(model=model, reg_order=2, mu=0.05, max_iter=360).fit(b, y)
+    A = np.concatenate([ref_port.nnls_basis(b, model.bins), ref_port.regularization_matrix(120, 2, 0.05)])
+    ref = c_oracle.nnls(A, np.concatenate([y, np.zeros((n, 120))], axis=1), 360)
+    assert ((s.status_ == 1) == (ref["status"] == 1)).all()
+    assert np.abs(s.params_["coefficients"] - ref["x"]).max() <= 1e-6
+    assert np.abs(s.diagnostics_["residual"] - ref["rnorm"]).max() <= 1e-8
+
+
 def test_single_voxel_and_device_path():
     import torch
 
