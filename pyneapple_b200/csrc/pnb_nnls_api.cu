@@ -133,6 +133,7 @@ int launch(NnlsCtx &C, const pnb_nnls_problem *p, const double *B, const double 
     if (want_fast < grid) grid = want_fast;
     if (grid < 1) grid = 1;
     a.counter = ctr; a.kmax = kcap; a.work_list = nullptr; a.work_count = nullptr;
+    a.work_min = 0; a.work_max = ~0ULL;
     fast<<<(unsigned)grid, kFastWarps * 32, smem_fast, stream>>>(a);
     PNBI_CUDA(cudaGetLastError());
     pnbi::count_launch();
@@ -144,15 +145,23 @@ int launch(NnlsCtx &C, const pnb_nnls_problem *p, const double *B, const double 
     int bps_redo = 0;
     PNBI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_redo, redo, kRedoWarps * 32, smem_redo));
     if (bps_redo < 1) return pnbi::fail(PNB_E_UNSUPPORTED, "NNLS redo kernel does not fit on this device");
+    // few voxels: 2-warp CTAs whose factor stays in shared memory; many: the 8-warp shape
+    const unsigned long long few = 8ULL * bps_redo * sms * kRedoWarps;
     a.counter = ctr + 2; a.kmax = kmax_redo; a.work_list = C.redo_list; a.work_count = ctr + 1;
+    a.work_min = 1; a.work_max = few;
     redo<<<(unsigned)((long long)bps_redo * sms), kRedoWarps * 32, smem_redo, stream>>>(a);
     PNBI_CUDA(cudaGetLastError());
+    a.kmax = kmax; a.work_min = few + 1; a.work_max = ~0ULL;
+    robust<<<(unsigned)((long long)bps * sms), kWarps * 32, smem, stream>>>(a);
+    PNBI_CUDA(cudaGetLastError());
+    pnbi::count_launch();
     pnbi::count_launch();
   } else {
     long long grid = (long long)bps * sms;
     if (want < grid) grid = want;
     if (grid < 1) grid = 1;
     a.counter = ctr; a.kmax = kmax; a.work_list = nullptr; a.work_count = nullptr;
+    a.work_min = 0; a.work_max = ~0ULL;
     robust<<<(unsigned)grid, kWarps * 32, smem, stream>>>(a);
     PNBI_CUDA(cudaGetLastError());
     pnbi::count_launch();

@@ -58,6 +58,9 @@ struct NnlsDeviceArgs {
   int *redo_list;
   const int *work_list;
   const unsigned long long *work_count;
+  // a work-list launch only runs when work_count lies in [work_min, work_max] (lets the host
+  // enqueue two differently shaped launches and have the device pick one without a sync)
+  unsigned long long work_min, work_max;
 };
 
 // column-major packed lower triangle with leading dimension ld: element (i, c), i >= c
@@ -89,6 +92,10 @@ __global__ void __launch_bounds__(WARPS * 32) nnls_kernel(const NnlsDeviceArgs a
   for (int i = threadIdx.x; i < m * n; i += WARPS * 32) B_s[i] = a.B[i];
   for (int i = threadIdx.x; i < n * BW; i += WARPS * 32) rtr_s[i] = a.rtr[i];
   __syncthreads();
+  if (a.work_list) {
+    const unsigned long long cnt = a.work_count[0];
+    if (cnt < a.work_min || cnt > a.work_max) return;
+  }
   const long long gwarp = (long long)blockIdx.x * WARPS + wid;
   double *scratch = a.scratch + gwarp * ((size_t)n * (n + 1) / 2 + 5 * (size_t)n);
 
