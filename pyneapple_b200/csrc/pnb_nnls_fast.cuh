@@ -293,7 +293,8 @@ __global__ void __launch_bounds__(WARPS * 32) nnls_fast_kernel(const NnlsDeviceA
       // ---- secondary loop ----------------------------------------------------------
       for (;;) {
         iter += 1;
-        if (iter >= a.maxiter) { mode = 3; break; }
+        // reaching the cap is only believed from the robust path, whose iteration count is SciPy's
+        if (iter >= a.maxiter) { mode = kNnlsRedo; break; }
         double alpha = 2.0;
         int jj = -1;
         for (int i = lane; i < k; i += 32) {
