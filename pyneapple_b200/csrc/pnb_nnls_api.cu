@@ -22,10 +22,11 @@ constexpr size_t kSmemBudget = 220 * 1024;
 struct NnlsCtx {
   unsigned long long *counters = nullptr;  // ring
   int next = 0;
-  double *scratch = nullptr;
-  size_t scratch_cap = 0;
-  int *redo_list = nullptr;
-  size_t redo_cap = 0;
+  // one set per concurrently running launch (the host pipeline alternates two streams)
+  double *scratch[2] = {nullptr, nullptr};
+  size_t scratch_cap[2] = {0, 0};
+  int *redo_list[2] = {nullptr, nullptr};
+  size_t redo_cap[2] = {0, 0};
   unsigned long long *last_redo = nullptr;  // device counter of the most recent auto-mode launch
   // host pipeline
   cudaStream_t streams[2] = {nullptr, nullptr};
@@ -81,7 +82,8 @@ FastKernel fast_kernel_for(int mt) {
 }
 
 int launch(NnlsCtx &C, const pnb_nnls_problem *p, const double *B, const double *rtr, const double *y,
-           long long n_vox, double *coef, double *rn, int *st, int *it, double *r2, cudaStream_t stream) {
+           long long n_vox, double *coef, double *rn, int *st, int *it, double *r2, cudaStream_t stream,
+           int slot) {
   const int m = p->n_b, n = p->n_bins, W = p->rtr_halfband;
   const int kmax = pick_kmax(m, n, W, kWarps);
   const size_t smem = pnb::nnls_smem_bytes(m, n, W, kmax, kWarps);
@@ -104,17 +106,17 @@ int launch(NnlsCtx &C, const pnb_nnls_problem *p, const double *B, const double 
   const long long want = (n_vox + kWarps - 1) / kWarps;
   const size_t per_warp = (size_t)n * (n + 1) / 2 + 5 * (size_t)n;
   const size_t need = (size_t)bps * sms * kWarps * per_warp;
-  if (need > C.scratch_cap) {
-    if (C.scratch) PNBI_CUDA(cudaFree(C.scratch));
-    C.scratch = nullptr; C.scratch_cap = 0;
-    PNBI_CUDA(cudaMalloc(&C.scratch, need * sizeof(double)));
-    C.scratch_cap = need;
+  if (need > C.scratch_cap[slot]) {
+    if (C.scratch[slot]) PNBI_CUDA(cudaFree(C.scratch[slot]));
+    C.scratch[slot] = nullptr; C.scratch_cap[slot] = 0;
+    PNBI_CUDA(cudaMalloc(&C.scratch[slot], need * sizeof(double)));
+    C.scratch_cap[slot] = need;
   }
-  if ((size_t)n_vox > C.redo_cap) {
-    if (C.redo_list) PNBI_CUDA(cudaFree(C.redo_list));
-    C.redo_list = nullptr; C.redo_cap = 0;
-    PNBI_CUDA(cudaMalloc(&C.redo_list, (size_t)n_vox * sizeof(int)));
-    C.redo_cap = (size_t)n_vox;
+  if ((size_t)n_vox > C.redo_cap[slot]) {
+    if (C.redo_list[slot]) PNBI_CUDA(cudaFree(C.redo_list[slot]));
+    C.redo_list[slot] = nullptr; C.redo_cap[slot] = 0;
+    PNBI_CUDA(cudaMalloc(&C.redo_list[slot], (size_t)n_vox * sizeof(int)));
+    C.redo_cap[slot] = (size_t)n_vox;
   }
   if (!C.counters) PNBI_CUDA(cudaMalloc(&C.counters, 64 * sizeof(unsigned long long)));
   // three consecutive counters per call: fast work queue, redo count, robust work queue
@@ -124,8 +126,8 @@ int launch(NnlsCtx &C, const pnb_nnls_problem *p, const double *B, const double 
   pnb::NnlsDeviceArgs a;
   a.m = m; a.n = n; a.W = W; a.maxiter = p->max_iter; a.n_vox = n_vox;
   a.B = B; a.rtr = rtr; a.y = y; a.coef = coef; a.rnorm = rn; a.status = st; a.iters = it; a.r2 = r2;
-  a.scratch = C.scratch;
-  a.redo_count = ctr + 1; a.redo_list = C.redo_list;
+  a.scratch = C.scratch[slot];
+  a.redo_count = ctr + 1; a.redo_list = C.redo_list[slot];
   C.last_redo = use_fast ? ctr + 1 : nullptr;
   if (use_fast) {
     long long grid = (long long)bps_fast * sms;
@@ -147,7 +149,7 @@ int launch(NnlsCtx &C, const pnb_nnls_problem *p, const double *B, const double 
     if (bps_redo < 1) return pnbi::fail(PNB_E_UNSUPPORTED, "NNLS redo kernel does not fit on this device");
     // few voxels: 2-warp CTAs whose factor stays in shared memory; many: the 8-warp shape
     const unsigned long long few = 8ULL * bps_redo * sms * kRedoWarps;
-    a.counter = ctr + 2; a.kmax = kmax_redo; a.work_list = C.redo_list; a.work_count = ctr + 1;
+    a.counter = ctr + 2; a.kmax = kmax_redo; a.work_list = C.redo_list[slot]; a.work_count = ctr + 1;
     a.work_min = 1; a.work_max = few;
     redo<<<(unsigned)((long long)bps_redo * sms), kRedoWarps * 32, smem_redo, stream>>>(a);
     PNBI_CUDA(cudaGetLastError());
@@ -178,7 +180,7 @@ extern "C" int pnb_nnls_fit_device(const pnb_nnls_problem *p, void *cuda_stream)
   PNBI_CUDA(cudaGetDevice(&dev));
   std::lock_guard<std::mutex> lk(g_mu);
   return launch(g_ctx[dev & 15], p, p->basis, p->rtr_band, p->signal, p->n_vox, p->coefficients,
-                p->residual, p->status, p->iterations, p->r_squared, (cudaStream_t)cuda_stream);
+                p->residual, p->status, p->iterations, p->r_squared, (cudaStream_t)cuda_stream, 0);
 }
 
 extern "C" int pnb_nnls_fit_host(const pnb_nnls_problem *p, int device, int64_t chunk_vox) {
@@ -224,7 +226,7 @@ extern "C" int pnb_nnls_fit_host(const pnb_nnls_problem *p, int device, int64_t 
     const size_t nv = (NV - start < Cn) ? NV - start : Cn;
     cudaStream_t st = C.streams[s];
     PNBI_CUDA(cudaMemcpyAsync(C.y[s], p->signal + start * m, nv * m * sizeof(double), cudaMemcpyHostToDevice, st));
-    if (int rc = launch(C, p, C.B, C.rtr, C.y[s], (long long)nv, C.coef[s], C.rn[s], C.st[s], C.it[s], p->r_squared ? C.r2[s] : nullptr, st)) return rc;
+    if (int rc = launch(C, p, C.B, C.rtr, C.y[s], (long long)nv, C.coef[s], C.rn[s], C.st[s], C.it[s], p->r_squared ? C.r2[s] : nullptr, st, s)) return rc;
     PNBI_CUDA(cudaMemcpyAsync(p->coefficients + start * n, C.coef[s], nv * n * sizeof(double), cudaMemcpyDeviceToHost, st));
     PNBI_CUDA(cudaMemcpyAsync(p->residual + start, C.rn[s], nv * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (p->r_squared)

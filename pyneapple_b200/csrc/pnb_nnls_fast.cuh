@@ -269,9 +269,12 @@ __global__ void __launch_bounds__(WARPS * 32) nnls_fast_kernel(const NnlsDeviceA
         double zt = 0.0;
         if (ok) { zt = (hj - p1) / piv2; ok = zt > 0.0; }
         if (ok) { accepted = true; jsel = j; s_new = piv2; zeta = zt; break; }
-        if (lane == 0) ws[j] = 0.0;
-        __syncwarp();
+        // a rejected candidate is a borderline decision (pivot or z-test at rounding level) that
+        // SciPy's arithmetic may take the other way: let the robust path decide this voxel
+        mode = kNnlsRedo;
+        break;
       }
+      if (mode != 1) break;
       if (!accepted) break;
       if (k == kcap) { mode = kNnlsRedo; break; }
       // ---- bordering update ----------------------------------------------------
@@ -374,7 +377,10 @@ __global__ void __launch_bounds__(WARPS * 32) nnls_fast_kernel(const NnlsDeviceA
           if (!((inP >> q) & 1u)) wmax = fmax(wmax, col_dot(j, rr) - band_dot(j));
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) wmax = fmax(wmax, __shfl_xor_sync(FULL, wmax, o));
-        if (wmax > 1e-12 * hmax) mode = kNnlsRedo;  // not (to rounding) a Kuhn-Tucker point
+        // SciPy stops on w <= 0 exactly: a dual that is still positive (a candidate this path
+        // rejected, or a near-degenerate bin) is decided by the robust path
+        // (this includes duals within 1e-9 of zero from below: SciPy may see them as positive)
+        if (wmax > -1e-9 * hmax) mode = kNnlsRedo;
       }
     }
 

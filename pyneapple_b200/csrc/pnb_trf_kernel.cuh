@@ -59,8 +59,12 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 constexpr int kTrfClaim = 64;  // voxel indices claimed per warp-level atomicAdd
 
+#ifndef PNB_TRF_MINBLOCKS
+#define PNB_TRF_MINBLOCKS 1
+#endif
+
 template <class M, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) trf_kernel(const TrfDeviceArgs a) {
+__global__ void __launch_bounds__(BLOCK, PNB_TRF_MINBLOCKS) trf_kernel(const TrfDeviceArgs a) {
   constexpr int N = M::NP;
   constexpr unsigned FULL = 0xffffffffu;
   extern __shared__ double smem[];

@@ -122,6 +122,19 @@ def test_other_measurement_counts(n_b):
     assert np.abs(s.diagnostics_["residual"] - ref["rnorm"]).max() <= 1e-8
 
 
+def test_chunked_host_pipeline_equals_single_launch():
+    """Many small chunks on alternating streams (each with its own scratch / hand-over list)."""
+    from pyneapple_b200 import synth
+
+    b, y, _ = synth.sample_voxels(synth.CONFIGS["C3"], 8192, z=21)
+    model = models.NNLSModel(d_range=(0.0008, 0.5), n_bins=250)
+    one = NNLSSolver(model=model, reg_order=2, mu=0.02, max_iter=250).fit(b, y)
+    many = NNLSSolver(model=model, reg_order=2, mu=0.02, max_iter=250, chunk_vox=257).fit(b, y)
+    assert (one.status_ == 1).all() and (many.status_ == 1).all()
+    assert np.array_equal(one.params_["coefficients"], many.params_["coefficients"])
+    assert np.array_equal(one.iterations_, many.iterations_)
+
+
 def test_single_voxel_and_device_path():
     import torch
 

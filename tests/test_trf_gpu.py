@@ -113,6 +113,18 @@ def test_against_c_oracle_large():
     assert np.abs(solver.nfev_ - ref["nfev"]).mean() < 0.05
 
 
+def test_chunked_host_pipeline_equals_single_launch():
+    P = full_problem("trf_biexp_s0_c2")
+    a, _ = _make_solver("trf_biexp_s0_c2", "biexp", "s0", P)
+    c, _ = _make_solver("trf_biexp_s0_c2", "biexp", "s0", P, chunk_vox=129)
+    a.fit(P["b"], P["y"])
+    c.fit(P["b"], P["y"])
+    for n in P["free_names"]:
+        assert np.array_equal(a.params_[n], c.params_[n])
+    assert np.array_equal(a.diagnostics_["pcov"], c.diagnostics_["pcov"])
+    assert np.array_equal(a.status_, c.status_) and np.array_equal(a.r_squared_, c.r_squared_)
+
+
 def test_single_voxel_shapes():
     P = full_problem("trf_mono_c1")
     solver, _ = _make_solver("trf_mono_c1", "monoexp", "s0", P)
