@@ -496,7 +496,7 @@ PNB_HD void trf_evaluate(const double (&xe)[M::NP], const TrfOptions &O, int m, 
       for (int k = 0; k < N; k++) {
         gr[k] = 0.0;
         if (!((O.frozen >> k) & 1u))
-          gr[k] = ((M::template value_perturbed<0>(pk[k], bv, e, k) - yv) - f) / dx[k];
+          gr[k] = ((M::template value_perturbed<0>(pk[k], pt, bv, e, k) - yv) - f) / dx[k];
       }
 #pragma unroll
       for (int i = 0; i < N; i++) {

@@ -30,24 +30,51 @@ class _PixelFitResult:
 
 
 class PixelResults(Sequence):
-    """Array-backed, lazily materialised list of :class:`_PixelFitResult`."""
+    """Array-backed, lazily materialised list of :class:`_PixelFitResult`.
+
+    ``params`` is either an ``(n_vox, n_values)`` array or a list of ``n_values`` row vectors of
+    length ``n_vox`` (views into the solver's parameter-major output: no copy is made).
+    """
 
     def __init__(self, params, covariance=None, success=None, messages=None,
-                 n_iterations=None, residual=None):
-        self.params = np.asarray(params)  # (n_vox, n_values)
+                 n_iterations=None, residual=None, status=None):
+        if isinstance(params, (list, tuple)):
+            self._rows = [np.asarray(r) for r in params]
+            self._matrix = None
+            self._n = self._rows[0].shape[0] if self._rows else 0
+        else:
+            self._rows = None
+            self._matrix = np.asarray(params)
+            self._n = self._matrix.shape[0]
         self.covariance = covariance      # (n_vox, n, n) | None
-        n = self.params.shape[0]
-        self.success = np.ones(n, bool) if success is None else np.asarray(success, bool)
+        self._success = None if success is None else np.asarray(success, bool)
+        self._status = status             # success = status > 0 when given instead of `success`
         self.messages = messages          # callable(i) -> str | None, or None
         self.n_iterations = n_iterations  # (n_vox,) | None
         self.residual = residual          # (n_vox,) | None
 
+    @property
+    def success(self) -> np.ndarray:
+        if self._success is None:
+            self._success = (np.ones(self._n, bool) if self._status is None
+                             else np.asarray(self._status) > 0)
+        return self._success
+
+    @property
+    def params(self) -> np.ndarray:
+        """``(n_vox, n_values)`` matrix (materialised on first use when built from rows)."""
+        if self._matrix is None:
+            self._matrix = np.stack(self._rows, axis=1)
+        return self._matrix
+
     def __len__(self) -> int:
-        return self.params.shape[0]
+        return self._n
 
     def _one(self, i: int) -> _PixelFitResult:
+        p = (self._matrix[i] if self._matrix is not None
+             else np.array([r[i] for r in self._rows], dtype=np.float64))
         return _PixelFitResult(
-            params=self.params[i],
+            params=p,
             covariance=None if self.covariance is None else self.covariance[i],
             success=bool(self.success[i]),
             message=None if self.messages is None else self.messages(i),

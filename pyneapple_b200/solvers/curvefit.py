@@ -285,25 +285,24 @@ class CurveFitSolver(BaseSolver):
         return self._out_cache[1]
 
     def _store(self, res, free_names, n_pixels):
-        popt = res["params"][self._free_rows]  # (n_free, n_pixels)
+        rows = [res["params"][r] for r in self._free_rows]  # views of the (n_all, n_vox) output
         pcov = res["cov"]
         status = res["status"]
         self.status_, self.nfev_, self.cost_ = status, res["nfev"], res["cost"]
         self.njev_ = res["njev"]
         self.r_squared_ = res.get("r2")
-        success = status > 0
         if pcov is None:
             pcov = np.full((n_pixels, len(free_names), len(free_names)), np.nan)
         self.pixel_results_ = PixelResults(
-            params=popt.T, covariance=pcov, success=success,
+            params=rows, covariance=pcov, status=status,
             messages=lambda i, s=status: engine.STATUS_MESSAGES[int(s[i])] if s[i] <= 0 else None,
         )
         self.params_ = {
-            name: [float(popt[i, 0])] if n_pixels == 1 else popt[i]
+            name: [float(rows[i][0])] if n_pixels == 1 else rows[i]
             for i, name in enumerate(free_names)
         }
         self.diagnostics_ = {"pcov": pcov[0] if n_pixels == 1 else pcov, "n_pixels": n_pixels}
-        n_fail = int((~success).sum())
+        n_fail = int(np.count_nonzero(status <= 0))
         if n_fail:
             log.warning("%d of %d voxel fits failed (see pixel_results_[i].message)", n_fail, n_pixels)
 
