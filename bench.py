@@ -422,7 +422,7 @@ def main():
     e2e_value = n_vox * world * e2e_steps / e2e_s
     clocks = sampler.stop() if rank == 0 else None
     h2d = y_host.nbytes + b.nbytes + 3 * 4 * 8
-    d2h = n_vox * (4 * 8 + 16 * 8 + 4 + 4 + 4 + 8)
+    d2h = n_vox * (4 * 8 + 16 * 8 + 4 + 4 + 4 + 8 + 8)
 
     del y_pin, solver, y_dev
     torch.cuda.empty_cache()
@@ -440,7 +440,7 @@ def main():
         hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
     fp64_peak = _lib.measure_fp64_peak(local_rank)
     flops = algorithmic_flops(4, n_b, 2, nfev_sum, njev_sum)
-    alg_bytes = n_vox * (8 * n_b + 8 * 4 + 8 * 16 + 4 + 4 + 4 + 8)
+    alg_bytes = n_vox * (8 * n_b + 8 * 4 + 8 * 16 + 4 + 4 + 4 + 8 + 8)
     achieved_tf = flops / (kernel_ms * 1e-3) / 1e12
     achieved_gbs = alg_bytes / (kernel_ms * 1e-3) / 1e9
     traffic = None
