@@ -6,6 +6,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/pyneapple_b200.h"
@@ -39,6 +40,28 @@ namespace pnbi {
 int fail(int code, const std::string &msg) { return ::fail(code, msg); }
 int cuda_fail(cudaError_t e, const char *what) { return ::cuda_fail(e, what); }
 void count_launch() { g_launches.fetch_add(1); }
+
+bool is_pageable(const void *ptr) {
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, ptr) != cudaSuccess) { cudaGetLastError(); return true; }
+  return attr.type == cudaMemoryTypeUnregistered;
+}
+
+void parallel_memcpy(void *dst, const void *src, size_t bytes) {
+  static const unsigned hw = std::thread::hardware_concurrency();
+  unsigned nt = hw > 8 ? 8 : (hw ? hw : 1);
+  if (bytes < (4u << 20) || nt < 2) { std::memcpy(dst, src, bytes); return; }
+  const size_t part = ((bytes / nt) + 4095) & ~(size_t)4095;
+  std::vector<std::thread> th;
+  for (unsigned t = 1; t < nt; t++) {
+    const size_t off = part * t;
+    if (off >= bytes) break;
+    const size_t len = (off + part > bytes) ? bytes - off : part;
+    th.emplace_back([=] { std::memcpy((char *)dst + off, (const char *)src + off, len); });
+  }
+  std::memcpy(dst, src, part < bytes ? part : bytes);
+  for (auto &t : th) t.join();
+}
 }  // namespace pnbi
 
 #define PNB_DECL(id, t1) extern "C" cudaError_t pnb_trf_launch_##id##_##t1(const pnb::TrfDeviceArgs *, cudaStream_t);
@@ -180,6 +203,10 @@ struct Slot {
   int *status = nullptr, *nfev = nullptr, *njev = nullptr;
   unsigned long long *counter = nullptr;
   size_t cap_y = 0, cap_p = 0, cap_cov = 0, cap_v = 0;
+  // page-locked staging block for pageable caller memory
+  char *pin = nullptr;
+  size_t cap_pin = 0;
+  size_t pend_start = 0, pend_n = 0;  // chunk whose results still sit in the staging block
 };
 
 struct Pipeline {
@@ -269,22 +296,73 @@ extern "C" int pnb_trf_fit_host(const pnb_trf_problem *p, int device, int64_t ch
   const pnb::TrfOptions opt = make_options(p);
   LaunchFn launch = trf_launcher(p->model_id, p->t1_mode);
   const size_t NV = (size_t)p->n_vox;
+  // pageable caller memory is staged through page-locked blocks with multi-threaded host copies
+  const bool staged = pnbi::is_pageable(p->ydata) || pnbi::is_pageable(p->params);
+  const size_t D = sizeof(double), I = sizeof(int);
+  const size_t o_y = 0, o_p0 = o_y + C * nb * D, o_lb = o_p0 + C * np * D, o_ub = o_lb + C * np * D;
+  const size_t o_par = o_ub + C * np * D, o_cov = o_par + C * np * D;
+  const size_t o_cost = o_cov + C * nfree * nfree * D, o_r2 = o_cost + C * D, o_st = o_r2 + C * D;
+  const size_t o_nf = o_st + C * I, o_nj = o_nf + C * I, pin_bytes = o_nj + C * I;
+  if (staged) {
+    for (auto &s : P.slots) {
+      s.pend_n = 0;
+      if (pin_bytes > s.cap_pin) {
+        if (s.pin) PNB_CUDA(cudaFreeHost(s.pin));
+        s.pin = nullptr; s.cap_pin = 0;
+        PNB_CUDA(cudaHostAlloc((void **)&s.pin, pin_bytes, cudaHostAllocDefault));
+        s.cap_pin = pin_bytes;
+      }
+    }
+  }
+  // copy a finished chunk from the slot's staging block to the caller's arrays
+  auto drain = [&](Slot &s) -> int {
+    if (!s.pend_n) return 0;
+    PNB_CUDA(cudaStreamSynchronize(s.stream));
+    const size_t st = s.pend_start, n = s.pend_n;
+    for (int k = 0; k < np; k++)
+      pnbi::parallel_memcpy(p->params + (size_t)k * NV + st, s.pin + o_par + (size_t)k * n * D, n * D);
+    if (p->cov) pnbi::parallel_memcpy(p->cov + st * nfree * nfree, s.pin + o_cov, n * nfree * nfree * D);
+    std::memcpy(p->status + st, s.pin + o_st, n * I);
+    std::memcpy(p->nfev + st, s.pin + o_nf, n * I);
+    if (p->njev) std::memcpy(p->njev + st, s.pin + o_nj, n * I);
+    if (p->cost) std::memcpy(p->cost + st, s.pin + o_cost, n * D);
+    if (p->r_squared) std::memcpy(p->r_squared + st, s.pin + o_r2, n * D);
+    s.pend_n = 0;
+    return 0;
+  };
   int slot = 0;
   for (size_t start = 0; start < NV; start += C, slot = (slot + 1) % Pipeline::kSlots) {
     Slot &s = P.slots[slot];
     const size_t n = (NV - start < C) ? NV - start : C;
+    const double *src_y = p->ydata + start * nb, *src_p0 = p->p0 + start, *src_lb = p->lb + start,
+                 *src_ub = p->ub + start;
+    size_t pitch = NV * D;  // row pitch of the caller's (n_params, n_vox) arrays
+    if (staged) {
+      if (int rc = drain(s)) return rc;  // also waits until the slot's previous chunk is done
+      pnbi::parallel_memcpy(s.pin + o_y, src_y, n * nb * D);
+      src_y = reinterpret_cast<const double *>(s.pin + o_y);
+      if (p->p0_per_voxel) {
+        for (int k = 0; k < np; k++) std::memcpy(s.pin + o_p0 + (size_t)k * n * D, p->p0 + (size_t)k * NV + start, n * D);
+        src_p0 = reinterpret_cast<const double *>(s.pin + o_p0);
+      }
+      if (p->bounds_per_voxel) {
+        for (int k = 0; k < np; k++) {
+          std::memcpy(s.pin + o_lb + (size_t)k * n * D, p->lb + (size_t)k * NV + start, n * D);
+          std::memcpy(s.pin + o_ub + (size_t)k * n * D, p->ub + (size_t)k * NV + start, n * D);
+        }
+        src_lb = reinterpret_cast<const double *>(s.pin + o_lb);
+        src_ub = reinterpret_cast<const double *>(s.pin + o_ub);
+      }
+      pitch = n * D;
+    }
     // the slot's previous chunk has been fully enqueued on the same stream, so
-    // stream order already protects the buffers; no host sync needed here.
-    PNB_CUDA(cudaMemcpyAsync(s.y, p->ydata + start * nb, sizeof(double) * n * nb,
-                             cudaMemcpyHostToDevice, s.stream));
+    // stream order already protects the device buffers; no host sync needed here.
+    PNB_CUDA(cudaMemcpyAsync(s.y, src_y, D * n * nb, cudaMemcpyHostToDevice, s.stream));
     if (p->p0_per_voxel)
-      PNB_CUDA(cudaMemcpy2DAsync(s.p0, n * sizeof(double), p->p0 + start, NV * sizeof(double),
-                                 n * sizeof(double), np, cudaMemcpyHostToDevice, s.stream));
+      PNB_CUDA(cudaMemcpy2DAsync(s.p0, n * D, src_p0, pitch, n * D, np, cudaMemcpyHostToDevice, s.stream));
     if (p->bounds_per_voxel) {
-      PNB_CUDA(cudaMemcpy2DAsync(s.lb, n * sizeof(double), p->lb + start, NV * sizeof(double),
-                                 n * sizeof(double), np, cudaMemcpyHostToDevice, s.stream));
-      PNB_CUDA(cudaMemcpy2DAsync(s.ub, n * sizeof(double), p->ub + start, NV * sizeof(double),
-                                 n * sizeof(double), np, cudaMemcpyHostToDevice, s.stream));
+      PNB_CUDA(cudaMemcpy2DAsync(s.lb, n * D, src_lb, pitch, n * D, np, cudaMemcpyHostToDevice, s.stream));
+      PNB_CUDA(cudaMemcpy2DAsync(s.ub, n * D, src_ub, pitch, n * D, np, cudaMemcpyHostToDevice, s.stream));
     }
     pnb::TrfDeviceArgs a;
     a.n_b = nb; a.n_vox = (long long)n; a.b = P.b; a.y = s.y;
@@ -303,20 +381,36 @@ extern "C" int pnb_trf_fit_host(const pnb_trf_problem *p, int device, int64_t ch
     cudaError_t e = launch(&a, s.stream);
     if (e != cudaSuccess) return cuda_fail(e, "trf kernel launch");
     g_launches.fetch_add(1);
-    PNB_CUDA(cudaMemcpy2DAsync(p->params + start, NV * sizeof(double), s.params, n * sizeof(double),
-                               n * sizeof(double), np, cudaMemcpyDeviceToHost, s.stream));
+    if (staged) {
+      PNB_CUDA(cudaMemcpyAsync(s.pin + o_par, s.params, D * n * np, cudaMemcpyDeviceToHost, s.stream));
+      if (p->cov)
+        PNB_CUDA(cudaMemcpyAsync(s.pin + o_cov, s.cov, D * n * nfree * nfree, cudaMemcpyDeviceToHost, s.stream));
+      PNB_CUDA(cudaMemcpyAsync(s.pin + o_st, s.status, I * n, cudaMemcpyDeviceToHost, s.stream));
+      PNB_CUDA(cudaMemcpyAsync(s.pin + o_nf, s.nfev, I * n, cudaMemcpyDeviceToHost, s.stream));
+      if (p->njev) PNB_CUDA(cudaMemcpyAsync(s.pin + o_nj, s.njev, I * n, cudaMemcpyDeviceToHost, s.stream));
+      if (p->cost) PNB_CUDA(cudaMemcpyAsync(s.pin + o_cost, s.cost, D * n, cudaMemcpyDeviceToHost, s.stream));
+      if (p->r_squared) PNB_CUDA(cudaMemcpyAsync(s.pin + o_r2, s.r2, D * n, cudaMemcpyDeviceToHost, s.stream));
+      s.pend_start = start; s.pend_n = n;
+      continue;
+    }
+    PNB_CUDA(cudaMemcpy2DAsync(p->params + start, NV * D, s.params, n * D, n * D, np, cudaMemcpyDeviceToHost, s.stream));
     if (p->cov)
-      PNB_CUDA(cudaMemcpyAsync(p->cov + start * nfree * nfree, s.cov,
-                               sizeof(double) * n * nfree * nfree, cudaMemcpyDeviceToHost, s.stream));
-    PNB_CUDA(cudaMemcpyAsync(p->status + start, s.status, sizeof(int) * n, cudaMemcpyDeviceToHost, s.stream));
-    PNB_CUDA(cudaMemcpyAsync(p->nfev + start, s.nfev, sizeof(int) * n, cudaMemcpyDeviceToHost, s.stream));
+      PNB_CUDA(cudaMemcpyAsync(p->cov + start * nfree * nfree, s.cov, D * n * nfree * nfree,
+                               cudaMemcpyDeviceToHost, s.stream));
+    PNB_CUDA(cudaMemcpyAsync(p->status + start, s.status, I * n, cudaMemcpyDeviceToHost, s.stream));
+    PNB_CUDA(cudaMemcpyAsync(p->nfev + start, s.nfev, I * n, cudaMemcpyDeviceToHost, s.stream));
     if (p->njev)
-      PNB_CUDA(cudaMemcpyAsync(p->njev + start, s.njev, sizeof(int) * n, cudaMemcpyDeviceToHost, s.stream));
+      PNB_CUDA(cudaMemcpyAsync(p->njev + start, s.njev, I * n, cudaMemcpyDeviceToHost, s.stream));
     if (p->cost)
-      PNB_CUDA(cudaMemcpyAsync(p->cost + start, s.cost, sizeof(double) * n, cudaMemcpyDeviceToHost, s.stream));
+      PNB_CUDA(cudaMemcpyAsync(p->cost + start, s.cost, D * n, cudaMemcpyDeviceToHost, s.stream));
     if (p->r_squared)
-      PNB_CUDA(cudaMemcpyAsync(p->r_squared + start, s.r2, sizeof(double) * n, cudaMemcpyDeviceToHost, s.stream));
+      PNB_CUDA(cudaMemcpyAsync(p->r_squared + start, s.r2, D * n, cudaMemcpyDeviceToHost, s.stream));
   }
+  if (staged)
+    for (int k = 0; k < Pipeline::kSlots; k++) {
+      // drain in submission order so the copies overlap the chunks still running
+      if (int rc = drain(P.slots[(slot + k) % Pipeline::kSlots])) return rc;
+    }
   for (auto &s : P.slots) PNB_CUDA(cudaStreamSynchronize(s.stream));
   return 0;
 }

@@ -8,6 +8,11 @@ namespace pnbi {
 int fail(int code, const std::string &msg);
 int cuda_fail(cudaError_t e, const char *what);
 void count_launch();
+// true for ordinary (pageable) host memory: cudaMemcpyAsync on it is staged by the driver at a
+// fraction of PCIe speed and blocks the host, so the host pipelines stage it themselves
+bool is_pageable(const void *ptr);
+// memcpy split over a few host threads (one thread does ~10 GB/s, PCIe 5 x16 moves ~55 GB/s)
+void parallel_memcpy(void *dst, const void *src, size_t bytes);
 }  // namespace pnbi
 
 #define PNBI_CUDA(call)                                       \

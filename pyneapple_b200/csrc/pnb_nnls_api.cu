@@ -1,6 +1,7 @@
 // C ABI of the batched NNLS solver (see include/pyneapple_b200.h).
 #include <cuda_runtime.h>
 
+#include <cstring>
 #include <mutex>
 
 #include "../../include/pyneapple_b200.h"
@@ -35,6 +36,10 @@ struct NnlsCtx {
   size_t cap_vox = 0, cap_m = 0, cap_n = 0;
   double *B = nullptr, *rtr = nullptr;
   size_t cap_B = 0, cap_rtr = 0;
+  // page-locked staging blocks for pageable caller memory
+  char *pin[2] = {nullptr, nullptr};
+  size_t cap_pin[2] = {0, 0};
+  size_t pend_start[2] = {0, 0}, pend_n[2] = {0, 0};
 };
 NnlsCtx g_ctx[16];
 std::mutex g_mu;
@@ -221,18 +226,63 @@ extern "C" int pnb_nnls_fit_host(const pnb_nnls_problem *p, int device, int64_t 
   PNBI_CUDA(cudaMemcpy(C.B, p->basis, (size_t)m * n * sizeof(double), cudaMemcpyHostToDevice));
   PNBI_CUDA(cudaMemcpy(C.rtr, p->rtr_band, (size_t)n * BW * sizeof(double), cudaMemcpyHostToDevice));
   const size_t NV = (size_t)p->n_vox;
+  const bool staged = pnbi::is_pageable(p->signal) || pnbi::is_pageable(p->coefficients);
+  const size_t D = sizeof(double), I = sizeof(int);
+  const size_t o_y = 0, o_coef = o_y + Cn * m * D, o_rn = o_coef + Cn * n * D, o_r2 = o_rn + Cn * D;
+  const size_t o_st = o_r2 + Cn * D, o_it = o_st + Cn * I, pin_bytes = o_it + Cn * I;
+  if (staged)
+    for (int k = 0; k < 2; k++) {
+      C.pend_n[k] = 0;
+      if (pin_bytes > C.cap_pin[k]) {
+        if (C.pin[k]) PNBI_CUDA(cudaFreeHost(C.pin[k]));
+        C.pin[k] = nullptr; C.cap_pin[k] = 0;
+        PNBI_CUDA(cudaHostAlloc((void **)&C.pin[k], pin_bytes, cudaHostAllocDefault));
+        C.cap_pin[k] = pin_bytes;
+      }
+    }
+  auto drain = [&](int k) -> int {
+    if (!C.pend_n[k]) return 0;
+    PNBI_CUDA(cudaStreamSynchronize(C.streams[k]));
+    const size_t st0 = C.pend_start[k], nv = C.pend_n[k];
+    pnbi::parallel_memcpy(p->coefficients + st0 * n, C.pin[k] + o_coef, nv * n * D);
+    std::memcpy(p->residual + st0, C.pin[k] + o_rn, nv * D);
+    if (p->r_squared) std::memcpy(p->r_squared + st0, C.pin[k] + o_r2, nv * D);
+    std::memcpy(p->status + st0, C.pin[k] + o_st, nv * I);
+    std::memcpy(p->iterations + st0, C.pin[k] + o_it, nv * I);
+    C.pend_n[k] = 0;
+    return 0;
+  };
   int s = 0;
   for (size_t start = 0; start < NV; start += Cn, s ^= 1) {
     const size_t nv = (NV - start < Cn) ? NV - start : Cn;
     cudaStream_t st = C.streams[s];
-    PNBI_CUDA(cudaMemcpyAsync(C.y[s], p->signal + start * m, nv * m * sizeof(double), cudaMemcpyHostToDevice, st));
+    const double *src_y = p->signal + start * m;
+    if (staged) {
+      if (int rc = drain(s)) return rc;
+      pnbi::parallel_memcpy(C.pin[s] + o_y, src_y, nv * m * D);
+      src_y = reinterpret_cast<const double *>(C.pin[s] + o_y);
+    }
+    PNBI_CUDA(cudaMemcpyAsync(C.y[s], src_y, nv * m * D, cudaMemcpyHostToDevice, st));
     if (int rc = launch(C, p, C.B, C.rtr, C.y[s], (long long)nv, C.coef[s], C.rn[s], C.st[s], C.it[s], p->r_squared ? C.r2[s] : nullptr, st, s)) return rc;
+    if (staged) {
+      PNBI_CUDA(cudaMemcpyAsync(C.pin[s] + o_coef, C.coef[s], nv * n * D, cudaMemcpyDeviceToHost, st));
+      PNBI_CUDA(cudaMemcpyAsync(C.pin[s] + o_rn, C.rn[s], nv * D, cudaMemcpyDeviceToHost, st));
+      if (p->r_squared) PNBI_CUDA(cudaMemcpyAsync(C.pin[s] + o_r2, C.r2[s], nv * D, cudaMemcpyDeviceToHost, st));
+      PNBI_CUDA(cudaMemcpyAsync(C.pin[s] + o_st, C.st[s], nv * I, cudaMemcpyDeviceToHost, st));
+      PNBI_CUDA(cudaMemcpyAsync(C.pin[s] + o_it, C.it[s], nv * I, cudaMemcpyDeviceToHost, st));
+      C.pend_start[s] = start; C.pend_n[s] = nv;
+      continue;
+    }
     PNBI_CUDA(cudaMemcpyAsync(p->coefficients + start * n, C.coef[s], nv * n * sizeof(double), cudaMemcpyDeviceToHost, st));
     PNBI_CUDA(cudaMemcpyAsync(p->residual + start, C.rn[s], nv * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (p->r_squared)
       PNBI_CUDA(cudaMemcpyAsync(p->r_squared + start, C.r2[s], nv * sizeof(double), cudaMemcpyDeviceToHost, st));
     PNBI_CUDA(cudaMemcpyAsync(p->status + start, C.st[s], nv * sizeof(int), cudaMemcpyDeviceToHost, st));
     PNBI_CUDA(cudaMemcpyAsync(p->iterations + start, C.it[s], nv * sizeof(int), cudaMemcpyDeviceToHost, st));
+  }
+  if (staged) {
+    if (int rc = drain(s)) return rc;
+    if (int rc = drain(s ^ 1)) return rc;
   }
   for (auto &st : C.streams) PNBI_CUDA(cudaStreamSynchronize(st));
   return 0;
