@@ -22,18 +22,40 @@ from ..result import FitResult
 
 
 class PixelIndices(Sequence):
-    """``list[tuple[int, int, int]]`` look-alike backed by an ``(n, 3)`` index array."""
+    """``list[tuple[int, int, int]]`` look-alike backed by an ``(n, ndim)`` index array.
 
-    def __init__(self, coords: np.ndarray):
-        self.array = np.ascontiguousarray(coords, dtype=np.int64)  # (n, ndim)
+    For an unmasked volume only the spatial shape is kept and the coordinates are generated on
+    demand (4.19 M voxels: a 100 MB table nobody may ever look at).
+    """
+
+    def __init__(self, coords: np.ndarray | None = None, full_shape: tuple | None = None):
+        self._array = None if coords is None else np.ascontiguousarray(coords, dtype=np.int64)
+        self._shape = None if full_shape is None else tuple(int(v) for v in full_shape)
+
+    @property
+    def array(self) -> np.ndarray:
+        if self._array is None:
+            n = int(np.prod(self._shape))
+            self._array = np.stack(np.unravel_index(np.arange(n), self._shape), axis=1).astype(np.int64)
+        return self._array
 
     def __len__(self):
-        return self.array.shape[0]
+        return int(np.prod(self._shape)) if self._array is None else self._array.shape[0]
 
     def __getitem__(self, i):
         if isinstance(i, slice):
-            return [tuple(int(v) for v in row) for row in self.array[i]]
-        return tuple(int(v) for v in self.array[i])
+            if self._array is None:
+                idx = np.arange(len(self))[i]
+                return [tuple(int(v) for v in np.unravel_index(j, self._shape)) for j in idx]
+            return [tuple(int(v) for v in row) for row in self._array[i]]
+        if self._array is None:
+            n = len(self)
+            if i < 0:
+                i += n
+            if not 0 <= i < n:
+                raise IndexError(i)
+            return tuple(int(v) for v in np.unravel_index(i, self._shape))
+        return tuple(int(v) for v in self._array[i])
 
     def __iter__(self):
         for row in self.array:
@@ -106,12 +128,13 @@ class BaseFitter:
             self.pixel_indices = PixelIndices(np.argwhere(mask))
         else:
             pixel_to_fit = image.reshape(-1, self.n_measurements)
-            self.pixel_indices = PixelIndices(
-                np.stack(np.unravel_index(np.arange(pixel_to_fit.shape[0]), image.shape[:-1]), axis=1)
-            )
+            self.pixel_indices = PixelIndices(full_shape=image.shape[:-1])
         return pixel_to_fit
 
     def _reconstruct_volume(self, flat_values, pixel_indices, spatial_shape) -> np.ndarray:
+        if isinstance(pixel_indices, PixelIndices) and pixel_indices._array is None:
+            # unmasked volume: the flat order is the C order of the volume
+            return np.asarray(flat_values, dtype=np.float64).reshape(spatial_shape).copy()
         vol = np.zeros(spatial_shape, dtype=np.float64)
         coords = pixel_indices.array if isinstance(pixel_indices, PixelIndices) else np.asarray(list(pixel_indices))
         if coords.size:
