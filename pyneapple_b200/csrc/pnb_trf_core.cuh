@@ -100,6 +100,7 @@ PNB_HD double bilinear(const double (&B)[N][N], const double (&a)[N], const doub
 template <int N>
 PNB_HD bool ldlt(const double (&B)[N][N], double alpha, double (&L)[N][N], double (&dinv)[N]) {
   bool ok = true;
+  double dd[N];  // D itself (dinv holds 1 / D)
 #pragma unroll
   for (int j = 0; j < N; j++) {
     const double ajj = B[j][j] + alpha;
@@ -107,10 +108,11 @@ PNB_HD bool ldlt(const double (&B)[N][N], double alpha, double (&L)[N][N], doubl
     double ld[N];  // L[j][k] * D[k]
 #pragma unroll
     for (int k = 0; k < j; k++) {
-      ld[k] = L[j][k] / dinv[k];
+      ld[k] = L[j][k] * dd[k];
       dj -= L[j][k] * ld[k];
     }
     if (!(dj > 4.0 * N * kEps * ajj)) { ok = false; dj = (ajj > 0.0) ? ajj : 1.0; }
+    dd[j] = dj;
     dinv[j] = 1.0 / dj;
 #pragma unroll
     for (int i = j + 1; i < N; i++) {
@@ -481,7 +483,7 @@ PNB_HD void trf_evaluate(const double (&xe)[M::NP], const TrfOptions &O, int m, 
 #pragma unroll
       for (int j = 0; j < N; j++) xt[j] = xe[j];
       xt[k] = xk + h;
-      dx[k] = xt[k] - xk;
+      dx[k] = 1.0 / (xt[k] - xk);  // the quotient below multiplies (<= 1 ulp from SciPy's division)
       M::prepare(xt, O.tr, O.tm, pk[k]);
     }
     for (int r = 0; r < m; r++) {
@@ -496,7 +498,7 @@ PNB_HD void trf_evaluate(const double (&xe)[M::NP], const TrfOptions &O, int m, 
       for (int k = 0; k < N; k++) {
         gr[k] = 0.0;
         if (!((O.frozen >> k) & 1u))
-          gr[k] = ((M::template value_perturbed<0>(pk[k], pt, bv, e, k) - yv) - f) / dx[k];
+          gr[k] = ((M::template value_perturbed<0>(pk[k], pt, bv, e, k) - yv) - f) * dx[k];
       }
 #pragma unroll
       for (int i = 0; i < N; i++) {
