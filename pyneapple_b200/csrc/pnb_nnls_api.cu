@@ -1,6 +1,7 @@
 // C ABI of the batched NNLS solver (see include/pyneapple_b200.h).
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -42,6 +43,8 @@ struct NnlsCtx {
   size_t pend_start[2] = {0, 0}, pend_n[2] = {0, 0};
 };
 NnlsCtx g_ctx[16];
+// PNB_NNLS_NO_V3=1 in the environment keeps the second-generation fast kernel (A/B measurements)
+const bool g_disable_v3 = [] { const char *e = std::getenv("PNB_NNLS_NO_V3"); return e && e[0] == '1'; }();
 std::mutex g_mu;
 
 int check(const pnb_nnls_problem *p) {
@@ -75,6 +78,19 @@ int pick_kcap_fast(int mt, int n, int W) {
   return k;
 }
 
+// v3 fast kernel (n_bins <= 256): one translation unit per (MT, WK), see pnb_nnls_v3_inst.cu
+#define PNB_V3_DECL(mt, wk) extern "C" cudaError_t pnb_nnls_v3_launch_##mt##_##wk(const pnb::NnlsDeviceArgs *, cudaStream_t);
+#define PNB_V3_ALL(X) X(8, 0) X(8, 2) X(8, 4) X(16, 0) X(16, 2) X(16, 4) X(24, 0) X(24, 2) X(24, 4) X(32, 0) X(32, 2) X(32, 4)
+PNB_V3_ALL(PNB_V3_DECL)
+using V3Launch = cudaError_t (*)(const pnb::NnlsDeviceArgs *, cudaStream_t);
+V3Launch v3_launcher_for(int mt, int n, int W) {
+  if (n > 256 || W > 4 || mt == 0) return nullptr;
+  const int wk = W == 0 ? 0 : (W <= 2 ? 2 : 4);
+#define PNB_V3_PICK(m_, w_) if (mt == m_ && wk == w_) return pnb_nnls_v3_launch_##m_##_##w_;
+  PNB_V3_ALL(PNB_V3_PICK)
+  return nullptr;
+}
+
 using FastKernel = void (*)(const pnb::NnlsDeviceArgs);
 FastKernel fast_kernel_for(int mt) {
   switch (mt) {
@@ -97,6 +113,7 @@ int launch(NnlsCtx &C, const pnb_nnls_problem *p, const double *B, const double 
   const int mt = pick_mt(m);
   FastKernel fast = fast_kernel_for(mt);
   const bool use_fast = p->algorithm == 0 && fast != nullptr;  // more than 32 measurements: robust only
+  V3Launch v3 = (use_fast && !g_disable_v3) ? v3_launcher_for(mt, n, W) : nullptr;
   const int kcap = use_fast ? pick_kcap_fast(mt, n, W) : 0;
   const size_t smem_fast = use_fast ? pnb::nnls_fast_smem_bytes(mt, n, W, kcap, kFastWarps) : 0;
   PNBI_CUDA(cudaFuncSetAttribute(robust, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -141,8 +158,12 @@ int launch(NnlsCtx &C, const pnb_nnls_problem *p, const double *B, const double 
     if (grid < 1) grid = 1;
     a.counter = ctr; a.kmax = kcap; a.work_list = nullptr; a.work_count = nullptr;
     a.work_min = 0; a.work_max = ~0ULL;
-    fast<<<(unsigned)grid, kFastWarps * 32, smem_fast, stream>>>(a);
-    PNBI_CUDA(cudaGetLastError());
+    if (v3) {
+      PNBI_CUDA(v3(&a, stream));
+    } else {
+      fast<<<(unsigned)grid, kFastWarps * 32, smem_fast, stream>>>(a);
+      PNBI_CUDA(cudaGetLastError());
+    }
     pnbi::count_launch();
     // voxels the fast path could not certify (the count stays on the device)
     auto redo = pnb::nnls_kernel<kRedoWarps>;

@@ -1,0 +1,595 @@
+// Third generation of the fast NNLS path (n_bins <= 256, n_b <= 32, half-bandwidth <= 4).
+//
+// Same mathematics as pnb_nnls_fast.cuh — Lawson-Hanson with the active block
+// carried as its explicit inverse H = (G_PP)^-1, bordering update when a bin
+// enters, rank-one downdate when one leaves, polish by iterative refinement and
+// self-certification with hand-over to the robust Cholesky kernel — rewritten
+// around what the ncu source profile of that kernel showed (profiles/r1_summary.md:
+// 84 k warp instructions per voxel spread evenly over a dozen generic loops,
+// 8 warps per SM because every warp reserved a 64 x 64 inverse):
+//
+//   * lane l owns the 8 CONSECUTIVE bins 8l .. 8l+7.  Their duals live in
+//     registers; the banded regulariser reads one window x[8l-W .. 8l+7+W] of the
+//     coefficient vector instead of 2W+1 values per bin; the whole dual pass is
+//     one fully unrolled block (8 x (MT/2 + 3) LDS.128, 8 x (MT + 2W+1) DFMA) that
+//     also tracks the lane's best candidate, and the warp-wide arg-max is two
+//     redux.sync on the halves of the (positive) double instead of a 5-step
+//     (value, index) shuffle butterfly.
+//     The dictionary is stored bin-permuted (row q*32 + l holds bin 8l + q) so the
+//     128-bit loads of consecutive lanes stay bank-conflict free.
+//   * L&H's z-test numerator h_j - G_jP z is the dual w_j that selected the
+//     candidate, so no second dot product / reduction is needed, and the
+//     independence test only takes its two square roots when the pivot is within
+//     1e-18 of being absorbed.
+//   * rows >= k of H and z are kept at zero, which turns the bordering update into
+//     the same rank-one update as every other row (u = [v; -1]).
+//   * shared memory per warp holds rows 0 .. KB-1 of the packed inverse (KB = 40
+//     covers 89 % of the voxels of config C3); a warp whose active set outgrows
+//     that borrows one of E extension areas (rows KB .. 63) from a CTA-wide pool
+//     and returns it when the voxel is done.  12 warps per SM instead of 8.
+//
+// Status / hand-over protocol, iteration counter, certification thresholds:
+// identical to pnb_nnls_fast.cuh (see there).
+#pragma once
+#include "pnb_nnls_fast.cuh"
+
+namespace pnb {
+
+#ifndef PNB_V3_KB
+#define PNB_V3_KB 40
+#endif
+#ifndef PNB_V3_MAXWARPS
+#define PNB_V3_MAXWARPS 12
+#endif
+
+template <int MT, int WK> struct NnlsV3Cfg {
+  static constexpr int NQ = 8;                 // bins per lane
+  static constexpr int NR = 32 * NQ;           // dictionary rows
+  static constexpr int LD = MT + 2;            // row stride of the dictionary (doubles)
+  static constexpr int BWK = 2 * WK + 1;       // band width the kernel is compiled for
+  static constexpr int LB = (WK == 0) ? 0 : ((BWK + 1) & ~1);  // padded band row
+  static constexpr int WP = (WK + 1) & ~1;     // zero padding of the coefficient vector, each side
+  static constexpr int XW = NQ + 2 * WP;       // coefficient window of one lane
+  static constexpr int NX = NR + 2 * WP;
+  static constexpr int KC = 64;                // slots
+  static constexpr int KB = PNB_V3_KB;         // rows of H in the warp's own shared memory
+  static constexpr int TB = (KB * (KB + 1) / 2 + 1) & ~1;
+  static constexpr int TX = ((KC * (KC + 1) / 2 - KB * (KB + 1) / 2) + 1) & ~1;  // one extension area
+  static constexpr int PER_WARP = NX + 3 * KC + MT + KC + TB;
+  static constexpr int SHARED = NR * LD + NR * LB + NR + 2;
+  __host__ __device__ static constexpr size_t smem_doubles(int warps, int ext) {
+    return (size_t)SHARED + (size_t)ext * TX + (size_t)warps * PER_WARP;
+  }
+};
+
+template <int MT, int WK>
+__global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const NnlsDeviceArgs a, const int n_ext) {
+  using C = NnlsV3Cfg<MT, WK>;
+  constexpr int NQ = C::NQ, NR = C::NR, LD = C::LD, LB = C::LB, WP = C::WP, KC = C::KC, KB = C::KB;
+  extern __shared__ __align__(16) double smem_v3[];
+  double *smem = smem_v3;
+  const int m = a.m, n = a.n, W = a.W;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int nthreads = blockDim.x;
+  const unsigned FULL = 0xffffffffu;
+  // ---- CTA-shared data ----------------------------------------------------------
+  double *Bt = smem;                       // [NR][LD], bin-permuted rows
+  double *rtrs = Bt + NR * LD;             // [NR][LB], same row order, taps centred on WK
+  double *gdiag = rtrs + NR * LB;          // [NR], natural bin order
+  int *pool_mask = reinterpret_cast<int *>(gdiag + NR);
+  double *pool = gdiag + NR + 2;           // n_ext areas of TX doubles
+  double *wbase = pool + (size_t)n_ext * C::TX + (size_t)wid * C::PER_WARP;
+  double *xs_raw = wbase;                  // NX, x[j] at xs_raw[j + WP]
+  double *gsm = xs_raw + C::NX;            // KC
+  double *usm = gsm + KC;                  // KC
+  double *zs = usm + KC;                   // KC
+  double *rs = zs + KC;                    // MT: residual y - B x (or y)
+  int *ro = reinterpret_cast<int *>(rs + MT);  // KC: dictionary row of the slot's bin
+  int *Pb = ro + KC;                           // KC: bin of the slot
+  double *Hb = rs + MT + KC;               // packed rows 0 .. KB-1
+  double *xs = xs_raw + WP;
+
+  for (int i = threadIdx.x; i < NR * LD; i += nthreads) {
+    const int row = i / LD, b = i - row * LD;
+    const int j = NQ * (row & 31) + (row >> 5);
+    Bt[i] = (j < n && b < m) ? a.B[(size_t)b * n + j] : 0.0;
+  }
+  if (LB > 0) {
+    for (int i = threadIdx.x; i < NR * LB; i += nthreads) {
+      const int row = i / LB, t = i - row * LB;
+      const int j = NQ * (row & 31) + (row >> 5);
+      const int d = t - WK;  // column offset of this tap
+      rtrs[i] = (j < n && d >= -W && d <= W) ? a.rtr[(size_t)j * (2 * W + 1) + d + W] : 0.0;
+    }
+  }
+  if (threadIdx.x == 0) *pool_mask = 0;
+  __syncthreads();
+  for (int j = threadIdx.x; j < NR; j += nthreads) {
+    const int row = (j & 7) * 32 + (j >> 3);
+    double acc = (j < n) ? a.rtr[(size_t)j * (2 * W + 1) + W] : 0.0;
+    for (int b = 0; b < MT; b++) acc += Bt[row * LD + b] * Bt[row * LD + b];
+    gdiag[j] = acc;
+  }
+  for (int i = lane; i < C::NX; i += 32) xs_raw[i] = 0.0;
+  for (int i = lane; i < KC; i += 32) zs[i] = 0.0;
+  for (int i = lane; i < C::TB; i += 32) Hb[i] = 0.0;
+  __syncthreads();
+
+  const int kcap = n_ext > 0 ? KC : KB;
+  enum { PH_INIT = 0, PH_ITER = 1, PH_POLISH = 2, PH_VERIFY = 3 };
+
+  // Every voxel is a sequence of TRIPS through one loop body whose big blocks (residual, dual,
+  // H * vector, rank-one update of H) exist exactly once in the instruction stream: the first
+  // version of this kernel inlined them at every use, grew to 178 KB of SASS and spent 44 % of
+  // its warp samples waiting for instruction fetch (profiles/r1_nnls_v3.md).
+  for (;;) {
+    unsigned long long vq = 0;
+    if (lane == 0) vq = atomicAdd(a.counter, 1ULL);
+    const long long vox = (long long)__shfl_sync(FULL, vq, 0);
+    if (vox >= a.n_vox) break;
+
+    const double yv = (lane < m) ? a.y[vox * m + lane] : 0.0;  // lane b holds y_b
+    const bool fin = __all_sync(FULL, finite_d(yv));
+
+    unsigned inP = 0;    // bit q: bin 8 lane + q is active
+    unsigned rej = 0;    // bit q: bin 8 lane + q was rejected as a candidate since the last addition
+    int k = 0, iter = 0, mode = fin ? 1 : 2;
+    int ext = -1;
+    double *Hx = nullptr;  // extension area, biased so that Hx + i (i + 1) / 2 is row i >= KB
+    int phase = PH_INIT, pass = 0;
+    bool do_dual = true;
+    double hmax = 0.0, rel = 1.0;
+
+    auto Hrow = [&](int i) -> double * { return (i < KB ? Hb : Hx) + (i * (i + 1)) / 2; };
+    // one dictionary row dotted with a register vector
+    auto col_dot = [&](int row, const double (&vec)[MT]) -> double {
+      const double2 *bp = reinterpret_cast<const double2 *>(Bt + row * LD);
+      double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+      for (int t = 0; t < MT / 2; t++) {
+        const double2 v = bp[t];
+        a0 += v.x * vec[2 * t];
+        a1 += v.y * vec[2 * t + 1];
+      }
+      return a0 + a1;
+    };
+    // (mu^2 R^T R x)_j for an arbitrary bin
+    auto band_at = [&](int row, int j) -> double {
+      double acc = 0.0;
+      if (LB > 0) {
+        const double *rp = rtrs + row * LB;
+        const double *xp = xs + (j - WK);
+#pragma unroll
+        for (int t = 0; t < C::BWK; t++) acc += rp[t] * xp[t];
+      }
+      return acc;
+    };
+
+    if (mode == 1) for (;;) {
+      // ---- rs = y - B_P z (k = 0: rs = y) ----------------------------------------------------
+      {
+        constexpr int G = (MT <= 8) ? 4 : (MT <= 16 ? 2 : 1);  // lane groups sharing the slots
+        const int b = lane % MT, grp = lane / MT;
+        double a0 = 0.0, a1 = 0.0;
+        if (grp < G) {
+          int i = grp;
+#pragma unroll 1
+          for (; i + G < k; i += 2 * G) {
+            a0 += Bt[ro[i] * LD + b] * zs[i];
+            a1 += Bt[ro[i + G] * LD + b] * zs[i + G];
+          }
+          if (i < k) a0 += Bt[ro[i] * LD + b] * zs[i];
+        }
+        double acc = a0 + a1;
+        if (G >= 2) acc += __shfl_xor_sync(FULL, acc, MT);
+        if (G >= 4) acc += __shfl_xor_sync(FULL, acc, 2 * MT);
+        __syncwarp();
+        if (lane < MT) rs[lane] = yv - acc;
+        __syncwarp();
+      }
+      double rr[MT];  // the residual, replicated
+      {
+        const double2 *rp = reinterpret_cast<const double2 *>(rs);
+#pragma unroll
+        for (int t = 0; t < MT / 2; t++) { const double2 v = rp[t]; rr[2 * t] = v.x; rr[2 * t + 1] = v.y; }
+      }
+      // ---- duals of this lane's bins, best positive one ----------------------------------------
+      double best = 0.0;
+      int bq = -1;
+      if (do_dual) {
+        double xw[C::XW > 0 ? C::XW : 1];
+        if (LB > 0) {
+          const double2 *xp = reinterpret_cast<const double2 *>(xs_raw + NQ * lane);
+#pragma unroll
+          for (int t = 0; t < C::XW / 2; t++) { const double2 v = xp[t]; xw[2 * t] = v.x; xw[2 * t + 1] = v.y; }
+        }
+        const unsigned skip = inP | rej;
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+          const int row = q * 32 + lane;
+          double acc = col_dot(row, rr);
+          if (LB > 0) {
+            const double2 *rp = reinterpret_cast<const double2 *>(rtrs + row * LB);
+            double b0 = 0.0, b1 = 0.0;
+#pragma unroll
+            for (int t = 0; t < LB / 2; t++) {
+              const double2 v = rp[t];
+              b0 += v.x * xw[q + WP - WK + 2 * t];
+              if (2 * t + 1 < C::BWK) b1 += v.y * xw[q + WP - WK + 2 * t + 1];
+            }
+            acc -= b0 + b1;
+          }
+          if (!((skip >> q) & 1u) && acc > best) { best = acc; bq = q; }
+        }
+      }
+      int j = -1, jrow = 0;
+      double wj = 0.0;
+      if (phase != PH_POLISH) {
+        // warp-wide arg-max of the positive duals; the lowest bin wins ties
+        const unsigned hi = (unsigned)__double2hiint(best);
+        const unsigned mhi = __reduce_max_sync(FULL, hi);
+        const unsigned lo = (hi == mhi) ? (unsigned)__double2loint(best) : 0u;
+        const unsigned mlo = __reduce_max_sync(FULL, lo);
+        const unsigned win = __ballot_sync(FULL, bq >= 0 && hi == mhi && lo == mlo);
+        if (win) {
+          j = __shfl_sync(FULL, NQ * lane + bq, __ffs(win) - 1);
+          wj = __hiloint2double((int)mhi, (int)mlo);
+        }
+        if (phase == PH_INIT) { hmax = wj; phase = PH_ITER; }
+        if (phase == PH_VERIFY) {
+          // duals of bins that sit at the optimum are zero to rounding (+-1e-13 relative) in every
+          // voxel; anything clearly positive means this is not a Kuhn-Tucker point
+          if (wj > 1e-12 * hmax) mode = kNnlsRedo;
+          break;
+        }
+        if (j < 0) {  // Kuhn-Tucker point of the carried solution: polish it
+          if (k == 0) break;
+          phase = PH_POLISH; pass = 0; do_dual = false; rej = 0;
+          continue;
+        }
+        // candidate column in registers, gsm = G_Pj
+        jrow = (j & 7) * 32 + (j >> 3);
+        double cj[MT];
+        {
+          const double2 *bp = reinterpret_cast<const double2 *>(Bt + jrow * LD);
+#pragma unroll
+          for (int t = 0; t < MT / 2; t++) { const double2 c2 = bp[t]; cj[2 * t] = c2.x; cj[2 * t + 1] = c2.y; }
+        }
+#pragma unroll 1
+        for (int i = lane; i < k; i += 32) {
+          const int row = ro[i];
+          double acc = col_dot(row, cj);
+          if (LB > 0) {
+            const int d = j - Pb[i];
+            if (d >= -WK && d <= WK) acc += rtrs[row * LB + d + WK];
+          }
+          gsm[i] = acc;
+        }
+      } else {
+        // gradient on P from the true residual
+#pragma unroll 1
+        for (int i = lane; i < k; i += 32) gsm[i] = col_dot(ro[i], rr) - band_at(ro[i], Pb[i]);
+      }
+      __syncwarp();
+      // ---- usm = H gsm, p0 = gsm . usm ----------------------------------------------------------
+      double p0 = 0.0;
+#pragma unroll 1
+      for (int i = lane; i < k; i += 32) {
+        double a0 = 0.0, a1 = 0.0;
+        const double *hp = Hrow(i);
+        int c = 0;
+#pragma unroll 1
+        for (; c + 1 <= i; c += 2) { a0 += hp[c] * gsm[c]; a1 += hp[c + 1] * gsm[c + 1]; }
+        if (c <= i) a0 += hp[c] * gsm[c];
+        int r = i + 1;
+        const int kb = k < KB ? k : KB;
+        if (r < kb) {
+          const double *cp = Hb + (r * (r + 1)) / 2 + i;
+#pragma unroll 1
+          for (; r + 1 < kb; r += 2) {
+            a0 += cp[0] * gsm[r];
+            a1 += cp[r + 1] * gsm[r + 1];
+            cp += 2 * r + 3;
+          }
+          if (r < kb) { a0 += cp[0] * gsm[r]; r++; }
+        }
+        if (k > KB) {
+          if (r < KB) r = KB;
+          const double *cp = Hx + (r * (r + 1)) / 2 + i;
+#pragma unroll 1
+          for (; r < k; r++) { a1 += cp[0] * gsm[r]; cp += r + 1; }
+        }
+        const double vi = a0 + a1;
+        usm[i] = vi;
+        p0 += gsm[i] * vi;
+      }
+      if (phase == PH_POLISH) {
+        // one refinement step: z += H grad
+        bool pos = true;
+        double dmax_ = 0.0, zmax = 0.0;
+#pragma unroll 1
+        for (int i = lane; i < k; i += 32) {
+          const double z = zs[i], dz = usm[i];
+          pos = pos && (z + dz > 0.0);
+          dmax_ = fmax(dmax_, fabs(dz));
+          zmax = fmax(zmax, fabs(z));
+        }
+        pos = __all_sync(FULL, pos);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          dmax_ = fmax(dmax_, __shfl_xor_sync(FULL, dmax_, o));
+          zmax = fmax(zmax, __shfl_xor_sync(FULL, zmax, o));
+        }
+        rel = dmax_ / zmax;
+        // the first correction measures how far the carried solution had drifted while the
+        // active-set decisions were being made; wrong results only appeared above 3e-4
+        if ((pass == 0 && rel > 5e-5) || !pos) { mode = kNnlsRedo; break; }
+#pragma unroll 1
+        for (int i = lane; i < k; i += 32) { const double z = zs[i] + usm[i]; zs[i] = z; xs[Pb[i]] = z; }
+        __syncwarp();
+        pass += 1;
+        if (rel < 1e-13 || pass == 4) {
+          if (rel > 1e-10) { mode = kNnlsRedo; break; }  // refinement did not converge
+          phase = PH_VERIFY;
+          do_dual = k < n;
+        }
+        continue;
+      }
+      // ---- PH_ITER: Lawson-Hanson's independence and z tests for candidate j ------------------
+      p0 = warp_sum(p0);
+      double sinv = 0.0, zeta = 0.0;
+      {
+        const double unorm2 = p0 > 0.0 ? p0 : 0.0;
+        const double piv2 = gdiag[j] - unorm2;
+        bool ok = piv2 > 1e-18 * unorm2 && piv2 > 0.0;
+        if (!ok && piv2 > 0.0) {
+          // the test taken literally when the pivot is close to being absorbed
+          const double av = sqrt(piv2), unorm = sqrt(unorm2);
+          ok = ((unorm + av * 0.01) - unorm) > 0.0;
+        }
+        if (ok) {
+          sinv = 1.0 / piv2;
+          zeta = wj * sinv;  // h_j - G_jP z is the dual that selected j
+          ok = zeta > 0.0;
+        }
+        if (!ok) {
+          // not a candidate again before the next addition
+          if ((j >> 3) == lane) rej |= 1u << (j & 7);
+          continue;
+        }
+      }
+      rej = 0;
+      if (k == kcap) { mode = kNnlsRedo; break; }
+      if (k == KB && ext < 0) {
+        // borrow an extension area for rows KB .. KC-1 (holders always finish, so waiting is safe)
+        int e = 0;
+        if (lane == 0) {
+          const int all = (1 << n_ext) - 1;
+          for (;;) {
+            const int cur = *reinterpret_cast<volatile int *>(pool_mask);
+            const int freeb = ~cur & all;
+            if (freeb) {
+              e = __ffs(freeb) - 1;
+              if (atomicCAS(pool_mask, cur, cur | (1 << e)) == cur) break;
+            } else {
+              __nanosleep(200);
+            }
+          }
+        }
+        ext = __shfl_sync(FULL, e, 0);
+        double *area = pool + (size_t)ext * C::TX;
+#pragma unroll 1
+        for (int i = lane; i < C::TX; i += 32) area[i] = 0.0;
+        Hx = area - (KB * (KB + 1)) / 2;
+      }
+      // ---- rank-one operations on H and z: the bordering update H += u u^T / s with
+      //      u = [H g; -1], then Lawson-Hanson's secondary loop (each removal is a downdate) ---
+      {
+        if (lane == 0) { usm[k] = -1.0; Pb[k] = j; ro[k] = jrow; }
+        if ((j >> 3) == lane) inP |= 1u << (j & 7);
+        double scale = sinv, zfac = zeta;
+        int kk = k + 1;  // rows the operation touches
+        int q = -1;      // slot being removed; -1: the bordering update prepared above
+        for (;;) {
+          if (q >= 0) {
+            // usm = column q of H; H -= usm usm^T / H_qq, z -= usm z_q / H_qq
+            const int idx = Pb[q];
+            if ((idx >> 3) == lane) inP &= ~(1u << (idx & 7));
+            const double dq = Hrow(q)[q], zq = zs[q];
+#pragma unroll 1
+            for (int i = lane; i < k; i += 32) usm[i] = (i >= q) ? Hrow(i)[q] : Hrow(q)[i];
+            if (lane == 0) xs[idx] = 0.0;
+            const double dinv = 1.0 / dq;
+            scale = -dinv;
+            zfac = zq * dinv;
+            kk = k;
+          }
+          __syncwarp();
+#pragma unroll 1
+          for (int i = lane; i < kk; i += 32) {
+            const double ui = usm[i];
+            const double coef = ui * scale;
+            double *hp = Hrow(i);
+            int c = 0;
+#pragma unroll 1
+            for (; c + 3 <= i; c += 4) {
+              const double h0 = hp[c], h1 = hp[c + 1], h2 = hp[c + 2], h3 = hp[c + 3];
+              const double u0 = usm[c], u1 = usm[c + 1], u2 = usm[c + 2], u3 = usm[c + 3];
+              hp[c] = h0 + coef * u0;
+              hp[c + 1] = h1 + coef * u1;
+              hp[c + 2] = h2 + coef * u2;
+              hp[c + 3] = h3 + coef * u3;
+            }
+#pragma unroll 1
+            for (; c <= i; c++) hp[c] += coef * usm[c];
+            zs[i] -= ui * zfac;
+          }
+          __syncwarp();
+          if (q < 0) {
+            k = kk;
+          } else {
+            // the last slot takes the place of q; the vacated last row / z entry return to zero
+            const int last = k - 1;
+            double mv[2];  // element (last, c) for c = lane, lane + 32
+#pragma unroll
+            for (int t = 0; t < 2; t++) {
+              const int c = lane + 32 * t;
+              mv[t] = (c <= last) ? Hrow(last)[c] : 0.0;
+            }
+            const double zl = zs[last];
+            const int pl = Pb[last], rl = ro[last];
+            __syncwarp();
+#pragma unroll
+            for (int t = 0; t < 2; t++) {
+              const int c = lane + 32 * t;
+              if (c <= last) {
+                Hrow(last)[c] = 0.0;
+                if (q != last) {
+                  if (c == last) Hrow(q)[q] = mv[t];
+                  else if (c < q) Hrow(q)[c] = mv[t];
+                  else if (c > q) Hrow(c)[q] = mv[t];
+                }
+              }
+            }
+            if (lane == 0) {
+              zs[last] = 0.0;
+              if (q != last) { zs[q] = zl; Pb[q] = pl; ro[q] = rl; }
+            }
+            k -= 1;
+            __syncwarp();
+            // anything else pushed to (or below) zero by the step?
+            int bad = KC;
+#pragma unroll 1
+            for (int i = lane; i < k; i += 32)
+              if (xs[Pb[i]] <= 0.0 && i < bad) bad = i;
+            bad = __reduce_min_sync(FULL, bad);
+            if (bad < KC) { q = bad; continue; }
+          }
+          iter += 1;
+          // reaching the cap is only believed from the robust path, whose iteration count is SciPy's
+          if (iter >= a.maxiter) { mode = kNnlsRedo; break; }
+          bool neg = false;
+#pragma unroll 1
+          for (int i = lane; i < k; i += 32) neg = neg || (zs[i] <= 0.0);
+          if (!__any_sync(FULL, neg)) break;
+          double alpha = 2.0;
+          int jj = -1;
+#pragma unroll 1
+          for (int i = lane; i < k; i += 32) {
+            const double z = zs[i];
+            if (z <= 0.0) {
+              const double xv = xs[Pb[i]];
+              const double t = -xv / (z - xv);
+              if (alpha > t) { alpha = t; jj = i; }
+            }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const double oa = __shfl_xor_sync(FULL, alpha, o);
+            const int oj = __shfl_xor_sync(FULL, jj, o);
+            if (oj >= 0 && (jj < 0 || oa < alpha || (oa == alpha && oj < jj))) { alpha = oa; jj = oj; }
+          }
+#pragma unroll 1
+          for (int i = lane; i < k; i += 32) {
+            const int p = Pb[i];
+            xs[p] += alpha * (zs[i] - xs[p]);
+          }
+          __syncwarp();
+          q = jj;
+        }
+      }
+      if (mode != 1) break;
+#pragma unroll 1
+      for (int i = lane; i < k; i += 32) xs[Pb[i]] = zs[i];
+      __syncwarp();
+    }
+
+    // rs is the residual of the final coefficients (last trip: verification, or k = 0)
+    double *out = a.coef + vox * (long long)n;
+    if (mode != kNnlsRedo) {
+      double ss = 0.0, part = 0.0;
+      if (mode == 1) {
+#pragma unroll
+        for (int b = 0; b < MT; b++) ss += rs[b] * rs[b];
+#pragma unroll 2
+        for (int jx = lane; jx < n; jx += 32) {
+          const double xj = xs[jx];
+          out[jx] = xj;
+          if (xj != 0.0) part += xj * band_at((jx & 7) * 32 + (jx >> 3), jx);
+        }
+      } else {
+        part = yv * yv;  // failure: zeros and ||y||
+#pragma unroll 2
+        for (int jx = lane; jx < n; jx += 32) out[jx] = 0.0;
+      }
+      const double mean = warp_sum(yv) / (double)m;
+      const double d = (lane < m) ? yv - mean : 0.0;
+      double red[2] = {part, d * d};
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        red[0] += __shfl_xor_sync(FULL, red[0], o);
+        red[1] += __shfl_xor_sync(FULL, red[1], o);
+      }
+      const double tot = ss + red[0];
+      const double ss_res = (mode == 1) ? ss : tot;
+      if (lane == 0) {
+        a.rnorm[vox] = sqrt(tot > 0.0 ? tot : 0.0);
+        if (a.r2) a.r2[vox] = (red[1] > 0.0) ? 1.0 - ss_res / red[1] : nan("");
+      }
+    }
+    // leave the scratch clean for the next voxel: x = 0, z = 0, rows < k of H = 0
+    __syncwarp();
+#pragma unroll 1
+    for (int i = lane; i < k; i += 32) { xs[Pb[i]] = 0.0; zs[i] = 0.0; }
+    {
+      const int kb = k < KB ? k : KB;
+      const int nb = (kb * (kb + 1)) / 2;
+#pragma unroll 1
+      for (int i = lane; i < nb; i += 32) Hb[i] = 0.0;
+    }
+    if (lane == 0) {
+      if (ext >= 0) atomicAnd(pool_mask, ~(1 << ext));
+      a.status[vox] = mode;
+      a.iters[vox] = iter;
+      if (mode == kNnlsRedo) {
+        const unsigned long long slot = atomicAdd(a.redo_count, 1ULL);
+        a.redo_list[slot] = (int)vox;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace pnb
+
+namespace pnb {
+// Launch one CTA per SM with as many warps (<= PNB_V3_MAXWARPS) and extension areas (<= 4) as
+// shared memory holds.  Returns cudaErrorInvalidConfiguration when not even 4 warps fit.
+template <int MT, int WK>
+cudaError_t nnls_v3_launch(const NnlsDeviceArgs &a, cudaStream_t stream) {
+  using C = NnlsV3Cfg<MT, WK>;
+  constexpr size_t budget = 227 * 1024;
+  int warps = PNB_V3_MAXWARPS, ext = 4;
+  while (warps > 4 && C::smem_doubles(warps, ext) * sizeof(double) > budget) warps--;
+  while (ext > 0 && C::smem_doubles(warps, ext) * sizeof(double) > budget) ext--;
+  const size_t smem = C::smem_doubles(warps, ext) * sizeof(double);
+  if (smem > budget) return cudaErrorInvalidConfiguration;
+  auto kern = nnls_v3_kernel<MT, WK>;
+  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return err;
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    err = cudaGetDevice(&dev);
+    if (err != cudaSuccess) return err;
+    err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (err != cudaSuccess) return err;
+  }
+  long long grid = sms;
+  const long long want = (a.n_vox + warps - 1) / warps;
+  if (want < grid) grid = want;
+  if (grid < 1) grid = 1;
+  kern<<<(unsigned)grid, warps * 32, smem, stream>>>(a, ext);
+  return cudaGetLastError();
+}
+}  // namespace pnb
