@@ -56,7 +56,9 @@ template <int MT, int WK> struct NnlsV3Cfg {
   static constexpr int TB = (KB * (KB + 1) / 2 + 1) & ~1;
   static constexpr int TX = ((KC * (KC + 1) / 2 - KB * (KB + 1) / 2) + 1) & ~1;  // one extension area
   static constexpr int PER_WARP = NX + 3 * KC + MT + KC + TB;
-  static constexpr int SHARED = NR * LD + NR * LB + NR + 2;
+  static constexpr int TRI = KC * (KC + 1) / 2;                 // packed elements of a full inverse
+  static constexpr int TABD = (TRI * 2 + 7) / 8;                 // their (row, column) table, in doubles
+  static constexpr int SHARED = NR * LD + NR * LB + NR + 2 + ((TABD + 1) & ~1);
   __host__ __device__ static constexpr size_t smem_doubles(int warps, int ext) {
     return (size_t)SHARED + (size_t)ext * TX + (size_t)warps * PER_WARP;
   }
@@ -77,14 +79,15 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
   double *rtrs = Bt + NR * LD;             // [NR][LB], same row order, taps centred on WK
   double *gdiag = rtrs + NR * LB;          // [NR], natural bin order
   int *pool_mask = reinterpret_cast<int *>(gdiag + NR);
-  double *pool = gdiag + NR + 2;           // n_ext areas of TX doubles
+  unsigned short *tab = reinterpret_cast<unsigned short *>(gdiag + NR + 2);  // element e -> row | column << 8
+  double *pool = gdiag + NR + 2 + ((C::TABD + 1) & ~1);  // n_ext areas of TX doubles
   double *wbase = pool + (size_t)n_ext * C::TX + (size_t)wid * C::PER_WARP;
   double *xs_raw = wbase;                  // NX, x[j] at xs_raw[j + WP]
   double *gsm = xs_raw + C::NX;            // KC
   double *usm = gsm + KC;                  // KC
   double *zs = usm + KC;                   // KC
   double *rs = zs + KC;                    // MT: residual y - B x (or y)
-  int *ro = reinterpret_cast<int *>(rs + MT);  // KC: dictionary row of the slot's bin
+  int *ro = reinterpret_cast<int *>(rs + MT);  // KC: offset of the slot's dictionary row in Bt
   int *Pb = ro + KC;                           // KC: bin of the slot
   double *Hb = rs + MT + KC;               // packed rows 0 .. KB-1
   double *xs = xs_raw + WP;
@@ -103,6 +106,8 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
     }
   }
   if (threadIdx.x == 0) *pool_mask = 0;
+  for (int i = threadIdx.x; i < KC; i += nthreads)
+    for (int c = 0; c <= i; c++) tab[(i * (i + 1)) / 2 + c] = (unsigned short)(i | (c << 8));
   __syncthreads();
   for (int j = threadIdx.x; j < NR; j += nthreads) {
     const int row = (j & 7) * 32 + (j >> 3);
@@ -174,11 +179,17 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
         if (grp < G) {
           int i = grp;
 #pragma unroll 1
-          for (; i + G < k; i += 2 * G) {
-            a0 += Bt[ro[i] * LD + b] * zs[i];
-            a1 += Bt[ro[i + G] * LD + b] * zs[i + G];
+          for (; i + 3 * G < k; i += 4 * G) {
+            const int r0 = ro[i], r1 = ro[i + G], r2 = ro[i + 2 * G], r3 = ro[i + 3 * G];
+            const double z0 = zs[i], z1 = zs[i + G], z2 = zs[i + 2 * G], z3 = zs[i + 3 * G];
+            const double b0 = Bt[r0 + b], b1 = Bt[r1 + b], b2 = Bt[r2 + b], b3 = Bt[r3 + b];
+            a0 += b0 * z0;
+            a1 += b1 * z1;
+            a0 += b2 * z2;
+            a1 += b3 * z3;
           }
-          if (i < k) a0 += Bt[ro[i] * LD + b] * zs[i];
+#pragma unroll 1
+          for (; i < k; i += G) a0 += Bt[ro[i] + b] * zs[i];
         }
         double acc = a0 + a1;
         if (G >= 2) acc += __shfl_xor_sync(FULL, acc, MT);
@@ -257,10 +268,11 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
         }
 #pragma unroll 1
         for (int i = lane; i < k; i += 32) {
-          const int row = ro[i];
+          const int p = Pb[i];
+          const int row = (p & 7) * 32 + (p >> 3);
           double acc = col_dot(row, cj);
           if (LB > 0) {
-            const int d = j - Pb[i];
+            const int d = j - p;
             if (d >= -WK && d <= WK) acc += rtrs[row * LB + d + WK];
           }
           gsm[i] = acc;
@@ -268,36 +280,48 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
       } else {
         // gradient on P from the true residual
 #pragma unroll 1
-        for (int i = lane; i < k; i += 32) gsm[i] = col_dot(ro[i], rr) - band_at(ro[i], Pb[i]);
+        for (int i = lane; i < k; i += 32) {
+          const int p = Pb[i];
+          const int row = (p & 7) * 32 + (p >> 3);
+          gsm[i] = col_dot(row, rr) - band_at(row, p);
+        }
       }
       __syncwarp();
       // ---- usm = H gsm, p0 = gsm . usm ----------------------------------------------------------
       double p0 = 0.0;
 #pragma unroll 1
       for (int i = lane; i < k; i += 32) {
+        // element (max(i, c), min(i, c)) of the packed lower triangle, c = 0 .. k-1: the row of i up
+        // to the diagonal, then down its column — one loop, so a lane never waits for the longer
+        // row or column of another lane
         double a0 = 0.0, a1 = 0.0;
-        const double *hp = Hrow(i);
-        int c = 0;
-#pragma unroll 1
-        for (; c + 1 <= i; c += 2) { a0 += hp[c] * gsm[c]; a1 += hp[c + 1] * gsm[c + 1]; }
-        if (c <= i) a0 += hp[c] * gsm[c];
-        int r = i + 1;
+        const double *hrow = Hrow(i);
+        const double *hcol = Hb + i;
+        int c = 0, tc = 0;  // tc = c (c + 1) / 2
         const int kb = k < KB ? k : KB;
-        if (r < kb) {
-          const double *cp = Hb + (r * (r + 1)) / 2 + i;
 #pragma unroll 1
-          for (; r + 1 < kb; r += 2) {
-            a0 += cp[0] * gsm[r];
-            a1 += cp[r + 1] * gsm[r + 1];
-            cp += 2 * r + 3;
-          }
-          if (r < kb) { a0 += cp[0] * gsm[r]; r++; }
+        for (; c + 1 < kb; c += 2) {
+          const int tc1 = tc + c + 1;
+          const double *q0 = (c <= i) ? hrow + c : hcol + tc;
+          const double *q1 = (c + 1 <= i) ? hrow + c + 1 : hcol + tc1;
+          a0 += *q0 * gsm[c];
+          a1 += *q1 * gsm[c + 1];
+          tc = tc1 + c + 2;
+        }
+        if (c < kb) {
+          const double *q0 = (c <= i) ? hrow + c : hcol + tc;
+          a0 += *q0 * gsm[c];
+          tc += c + 1;
+          c += 1;
         }
         if (k > KB) {
-          if (r < KB) r = KB;
-          const double *cp = Hx + (r * (r + 1)) / 2 + i;
+          hcol = Hx + i;
 #pragma unroll 1
-          for (; r < k; r++) { a1 += cp[0] * gsm[r]; cp += r + 1; }
+          for (; c < k; c++) {
+            const double *q0 = (c <= i) ? hrow + c : hcol + tc;
+            a1 += *q0 * gsm[c];
+            tc += c + 1;
+          }
         }
         const double vi = a0 + a1;
         usm[i] = vi;
@@ -385,7 +409,7 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
       // ---- rank-one operations on H and z: the bordering update H += u u^T / s with
       //      u = [H g; -1], then Lawson-Hanson's secondary loop (each removal is a downdate) ---
       {
-        if (lane == 0) { usm[k] = -1.0; Pb[k] = j; ro[k] = jrow; }
+        if (lane == 0) { usm[k] = -1.0; Pb[k] = j; ro[k] = jrow * LD; }
         if ((j >> 3) == lane) inP |= 1u << (j & 7);
         double scale = sinv, zfac = zeta;
         int kk = k + 1;  // rows the operation touches
@@ -405,24 +429,35 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
             kk = k;
           }
           __syncwarp();
+          // gsm = scale * usm, z -= zfac * usm; then every packed element (i, c) += gsm[i] * usm[c],
+          // the elements dealt out to all 32 lanes
 #pragma unroll 1
           for (int i = lane; i < kk; i += 32) {
             const double ui = usm[i];
-            const double coef = ui * scale;
-            double *hp = Hrow(i);
-            int c = 0;
-#pragma unroll 1
-            for (; c + 3 <= i; c += 4) {
-              const double h0 = hp[c], h1 = hp[c + 1], h2 = hp[c + 2], h3 = hp[c + 3];
-              const double u0 = usm[c], u1 = usm[c + 1], u2 = usm[c + 2], u3 = usm[c + 3];
-              hp[c] = h0 + coef * u0;
-              hp[c + 1] = h1 + coef * u1;
-              hp[c + 2] = h2 + coef * u2;
-              hp[c + 3] = h3 + coef * u3;
-            }
-#pragma unroll 1
-            for (; c <= i; c++) hp[c] += coef * usm[c];
+            gsm[i] = ui * scale;
             zs[i] -= ui * zfac;
+          }
+          __syncwarp();
+          {
+            const int ne = (kk * (kk + 1)) / 2;
+            constexpr int NB = (KB * (KB + 1)) / 2;
+            int e = lane;
+#pragma unroll 1
+            for (; e + 32 < ne; e += 64) {
+              const unsigned t0 = tab[e], t1 = tab[e + 32];
+              double *h0 = (e < NB ? Hb : Hx) + e;
+              double *h1 = (e + 32 < NB ? Hb : Hx) + e + 32;
+              const double s0 = gsm[t0 & 255u], s1 = gsm[t1 & 255u];
+              const double u0 = usm[t0 >> 8], u1 = usm[t1 >> 8];
+              const double v0 = *h0, v1 = *h1;
+              *h0 = v0 + s0 * u0;
+              *h1 = v1 + s1 * u1;
+            }
+            if (e < ne) {
+              const unsigned t0 = tab[e];
+              double *h0 = (e < NB ? Hb : Hx) + e;
+              *h0 += gsm[t0 & 255u] * usm[t0 >> 8];
+            }
           }
           __syncwarp();
           if (q < 0) {

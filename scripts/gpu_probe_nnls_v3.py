@@ -25,6 +25,8 @@ for order in orders:
     it_eq = (r["iterations"] == ref["iterations"]).double().mean().item()
     st_eq = (r["status"] == ref["status"]).double().mean().item()
     dr = (r["residual"] - ref["residual"]).abs().max().item()
+    kf = (ref["coefficients"] > 0).sum(dim=1)
+    print(f"   final active set: >64 {(kf > 64).sum().item()}, >60 {(kf > 60).sum().item()}, >96 {(kf > 96).sum().item()}, max {kf.max().item()}; iters >=200: {(ref['iterations'] >= 200).sum().item()}")
     print(f"reg{order}: {y.shape[0]} vox {ms:.1f} ms -> {y.shape[0]/ms*1e3/1e6:.2f} Mvox/s redo {redo}; "
           f"max|dc| {d.max().item():.2e} n(>1e-6) {(d > 1e-6).sum().item()} n(>1e-9) {(d > 1e-9).sum().item()}; "
           f"iters equal {it_eq:.5f} status equal {st_eq:.5f} max|dres| {dr:.2e}", flush=True)
