@@ -36,7 +36,10 @@
 namespace pnb {
 
 #ifndef PNB_V3_KB
-#define PNB_V3_KB 40
+#define PNB_V3_KB 36
+#endif
+#ifndef PNB_V3_K1
+#define PNB_V3_K1 56
 #endif
 #ifndef PNB_V3_MAXWARPS
 #define PNB_V3_MAXWARPS 12
@@ -51,23 +54,23 @@ template <int MT, int WK> struct NnlsV3Cfg {
   static constexpr int WP = (WK + 1) & ~1;     // zero padding of the coefficient vector, each side
   static constexpr int XW = NQ + 2 * WP;       // coefficient window of one lane
   static constexpr int NX = NR + 2 * WP;
-  static constexpr int KC = 64;                // slots
+  static constexpr int KC = 96;                // slots
   static constexpr int KB = PNB_V3_KB;         // rows of H in the warp's own shared memory
+  static constexpr int K1 = PNB_V3_K1;         // rows KB .. K1-1: tier-1 extension, K1 .. KC-1: tier 2
   static constexpr int TB = (KB * (KB + 1) / 2 + 1) & ~1;
-  static constexpr int TX = ((KC * (KC + 1) / 2 - KB * (KB + 1) / 2) + 1) & ~1;  // one extension area
+  static constexpr int T1 = ((K1 * (K1 + 1) / 2 - KB * (KB + 1) / 2) + 1) & ~1;  // one tier-1 area
+  static constexpr int T2 = ((KC * (KC + 1) / 2 - K1 * (K1 + 1) / 2) + 1) & ~1;  // one tier-2 area
   static constexpr int PER_WARP = NX + 3 * KC + MT + KC + TB;
-  static constexpr int TRI = KC * (KC + 1) / 2;                 // packed elements of a full inverse
-  static constexpr int TABD = (TRI * 2 + 7) / 8;                 // their (row, column) table, in doubles
-  static constexpr int SHARED = NR * LD + NR * LB + NR + 2 + ((TABD + 1) & ~1);
-  __host__ __device__ static constexpr size_t smem_doubles(int warps, int ext) {
-    return (size_t)SHARED + (size_t)ext * TX + (size_t)warps * PER_WARP;
+  static constexpr int SHARED = NR * LD + NR * LB + NR + 2;
+  __host__ __device__ static constexpr size_t smem_doubles(int warps, int e1, int e2) {
+    return (size_t)SHARED + (size_t)e1 * T1 + (size_t)e2 * T2 + (size_t)warps * PER_WARP;
   }
 };
 
 template <int MT, int WK>
-__global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const NnlsDeviceArgs a, const int n_ext) {
+__global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const NnlsDeviceArgs a, const int n_e1, const int n_e2) {
   using C = NnlsV3Cfg<MT, WK>;
-  constexpr int NQ = C::NQ, NR = C::NR, LD = C::LD, LB = C::LB, WP = C::WP, KC = C::KC, KB = C::KB;
+  constexpr int NQ = C::NQ, NR = C::NR, LD = C::LD, LB = C::LB, WP = C::WP, KC = C::KC, KB = C::KB, K1 = C::K1;
   extern __shared__ __align__(16) double smem_v3[];
   double *smem = smem_v3;
   const int m = a.m, n = a.n, W = a.W;
@@ -79,9 +82,9 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
   double *rtrs = Bt + NR * LD;             // [NR][LB], same row order, taps centred on WK
   double *gdiag = rtrs + NR * LB;          // [NR], natural bin order
   int *pool_mask = reinterpret_cast<int *>(gdiag + NR);
-  unsigned short *tab = reinterpret_cast<unsigned short *>(gdiag + NR + 2);  // element e -> row | column << 8
-  double *pool = gdiag + NR + 2 + ((C::TABD + 1) & ~1);  // n_ext areas of TX doubles
-  double *wbase = pool + (size_t)n_ext * C::TX + (size_t)wid * C::PER_WARP;
+  double *pool1 = gdiag + NR + 2;                      // n_e1 areas of T1 doubles (rows KB .. K1-1)
+  double *pool2 = pool1 + (size_t)n_e1 * C::T1;        // n_e2 areas of T2 doubles (rows K1 .. KC-1)
+  double *wbase = pool2 + (size_t)n_e2 * C::T2 + (size_t)wid * C::PER_WARP;
   double *xs_raw = wbase;                  // NX, x[j] at xs_raw[j + WP]
   double *gsm = xs_raw + C::NX;            // KC
   double *usm = gsm + KC;                  // KC
@@ -105,9 +108,7 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
       rtrs[i] = (j < n && d >= -W && d <= W) ? a.rtr[(size_t)j * (2 * W + 1) + d + W] : 0.0;
     }
   }
-  if (threadIdx.x == 0) *pool_mask = 0;
-  for (int i = threadIdx.x; i < KC; i += nthreads)
-    for (int c = 0; c <= i; c++) tab[(i * (i + 1)) / 2 + c] = (unsigned short)(i | (c << 8));
+  if (threadIdx.x == 0) { pool_mask[0] = 0; pool_mask[1] = 0; }
   __syncthreads();
   for (int j = threadIdx.x; j < NR; j += nthreads) {
     const int row = (j & 7) * 32 + (j >> 3);
@@ -120,7 +121,7 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
   for (int i = lane; i < C::TB; i += 32) Hb[i] = 0.0;
   __syncthreads();
 
-  const int kcap = n_ext > 0 ? KC : KB;
+  const int kcap = n_e1 > 0 ? (n_e2 > 0 ? KC : K1) : KB;
   enum { PH_INIT = 0, PH_ITER = 1, PH_POLISH = 2, PH_VERIFY = 3 };
 
   // Every voxel is a sequence of TRIPS through one loop body whose big blocks (residual, dual,
@@ -139,13 +140,14 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
     unsigned inP = 0;    // bit q: bin 8 lane + q is active
     unsigned rej = 0;    // bit q: bin 8 lane + q was rejected as a candidate since the last addition
     int k = 0, iter = 0, mode = fin ? 1 : 2;
-    int ext = -1;
-    double *Hx = nullptr;  // extension area, biased so that Hx + i (i + 1) / 2 is row i >= KB
+    int ext1 = -1, ext2 = -1;
+    double *H1 = nullptr, *H2 = nullptr;  // extension areas, biased so that H? + i (i + 1) / 2 is row i
     int phase = PH_INIT, pass = 0;
     bool do_dual = true;
     double hmax = 0.0, rel = 1.0;
 
-    auto Hrow = [&](int i) -> double * { return (i < KB ? Hb : Hx) + (i * (i + 1)) / 2; };
+    auto Htier = [&](int i) -> double * { return i < KB ? Hb : (i < K1 ? H1 : H2); };
+    auto Hrow = [&](int i) -> double * { return Htier(i) + (i * (i + 1)) / 2; };
     // one dictionary row dotted with a register vector
     auto col_dot = [&](int row, const double (&vec)[MT]) -> double {
       const double2 *bp = reinterpret_cast<const double2 *>(Bt + row * LD);
@@ -295,32 +297,34 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
         // to the diagonal, then down its column — one loop, so a lane never waits for the longer
         // row or column of another lane
         double a0 = 0.0, a1 = 0.0;
-        const double *hrow = Hrow(i);
-        const double *hcol = Hb + i;
-        int c = 0, tc = 0;  // tc = c (c + 1) / 2
-        const int kb = k < KB ? k : KB;
+        const double *prow = Hrow(i);  // &H(i, c)
+        int c = 0, inc = 1;            // inc = c + 1: distance from H(c, i) to H(c + 1, i)
+        int off = i;                   // c (c + 1) / 2 + i
 #pragma unroll 1
-        for (; c + 1 < kb; c += 2) {
-          const int tc1 = tc + c + 1;
-          const double *q0 = (c <= i) ? hrow + c : hcol + tc;
-          const double *q1 = (c + 1 <= i) ? hrow + c + 1 : hcol + tc1;
-          a0 += *q0 * gsm[c];
-          a1 += *q1 * gsm[c + 1];
-          tc = tc1 + c + 2;
-        }
-        if (c < kb) {
-          const double *q0 = (c <= i) ? hrow + c : hcol + tc;
-          a0 += *q0 * gsm[c];
-          tc += c + 1;
-          c += 1;
-        }
-        if (k > KB) {
-          hcol = Hx + i;
+        for (int seg = 0; seg < 3; seg++) {
+          const int lim = seg == 0 ? KB : (seg == 1 ? K1 : KC);
+          const int ke = k < lim ? k : lim;
+          if (c >= ke) continue;
+          const double *pcol = (seg == 0 ? Hb : (seg == 1 ? H1 : H2)) + off;  // &H(c, i), used when c > i
 #pragma unroll 1
-          for (; c < k; c++) {
-            const double *q0 = (c <= i) ? hrow + c : hcol + tc;
-            a1 += *q0 * gsm[c];
-            tc += c + 1;
+          for (; c + 1 < ke; c += 2) {
+            const double *q0 = (c <= i) ? prow : pcol;
+            const double *q1 = (c + 1 <= i) ? prow + 1 : pcol + inc;
+            const double g0 = gsm[c], g1 = gsm[c + 1];
+            a0 += *q0 * g0;
+            a1 += *q1 * g1;
+            pcol += 2 * inc + 1;
+            off += 2 * inc + 1;
+            inc += 2;
+            prow += 2;
+          }
+          if (c < ke) {
+            const double *q0 = (c <= i) ? prow : pcol;
+            a0 += *q0 * gsm[c];
+            off += inc;
+            inc += 1;
+            prow += 1;
+            c += 1;
           }
         }
         const double vi = a0 + a1;
@@ -384,27 +388,31 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
       }
       rej = 0;
       if (k == kcap) { mode = kNnlsRedo; break; }
-      if (k == KB && ext < 0) {
-        // borrow an extension area for rows KB .. KC-1 (holders always finish, so waiting is safe)
+      if ((k == KB && ext1 < 0) || (k == K1 && ext2 < 0)) {
+        // borrow an extension area (holders always finish, so waiting is safe)
+        const bool first = k == KB;
+        int *mask = pool_mask + (first ? 0 : 1);
         int e = 0;
         if (lane == 0) {
-          const int all = (1 << n_ext) - 1;
+          const int all = (1 << (first ? n_e1 : n_e2)) - 1;
           for (;;) {
-            const int cur = *reinterpret_cast<volatile int *>(pool_mask);
+            const int cur = *reinterpret_cast<volatile int *>(mask);
             const int freeb = ~cur & all;
             if (freeb) {
               e = __ffs(freeb) - 1;
-              if (atomicCAS(pool_mask, cur, cur | (1 << e)) == cur) break;
+              if (atomicCAS(mask, cur, cur | (1 << e)) == cur) break;
             } else {
               __nanosleep(200);
             }
           }
         }
-        ext = __shfl_sync(FULL, e, 0);
-        double *area = pool + (size_t)ext * C::TX;
+        e = __shfl_sync(FULL, e, 0);
+        double *area = first ? pool1 + (size_t)e * C::T1 : pool2 + (size_t)e * C::T2;
+        const int na = first ? C::T1 : C::T2;
 #pragma unroll 1
-        for (int i = lane; i < C::TX; i += 32) area[i] = 0.0;
-        Hx = area - (KB * (KB + 1)) / 2;
+        for (int i = lane; i < na; i += 32) area[i] = 0.0;
+        if (first) { ext1 = e; H1 = area - (KB * (KB + 1)) / 2; }
+        else { ext2 = e; H2 = area - (K1 * (K1 + 1)) / 2; }
       }
       // ---- rank-one operations on H and z: the bordering update H += u u^T / s with
       //      u = [H g; -1], then Lawson-Hanson's secondary loop (each removal is a downdate) ---
@@ -439,24 +447,35 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
           }
           __syncwarp();
           {
-            const int ne = (kk * (kk + 1)) / 2;
-            constexpr int NB = (KB * (KB + 1)) / 2;
-            int e = lane;
+            // row i of H += gsm[i] * usm[0 .. i]: lane l owns columns l, l + 32, l + 64, the rows
+            // are walked by the whole warp (conflict-free, no per-lane row lengths)
+            const double u0 = usm[lane];
+            const double u1 = (kk > 32) ? usm[lane + 32] : 0.0;
+            const double u2 = (kk > 64) ? usm[lane + 64] : 0.0;
+            int i = 0;
+            {
+              const int ke = kk < 32 ? kk : 32;
+              double *hp = Hb + lane;
 #pragma unroll 1
-            for (; e + 32 < ne; e += 64) {
-              const unsigned t0 = tab[e], t1 = tab[e + 32];
-              double *h0 = (e < NB ? Hb : Hx) + e;
-              double *h1 = (e + 32 < NB ? Hb : Hx) + e + 32;
-              const double s0 = gsm[t0 & 255u], s1 = gsm[t1 & 255u];
-              const double u0 = usm[t0 >> 8], u1 = usm[t1 >> 8];
-              const double v0 = *h0, v1 = *h1;
-              *h0 = v0 + s0 * u0;
-              *h1 = v1 + s1 * u1;
+              for (; i + 1 < ke; i += 2) {
+                const double c0 = gsm[i], c1 = gsm[i + 1];
+                double *h1 = hp + i + 1;
+                if (lane <= i) *hp += c0 * u0;
+                if (lane <= i + 1) *h1 += c1 * u0;
+                hp = h1 + i + 2;
+              }
+              if (i < ke) {
+                if (lane <= i) *hp += gsm[i] * u0;
+                i += 1;
+              }
             }
-            if (e < ne) {
-              const unsigned t0 = tab[e];
-              double *h0 = (e < NB ? Hb : Hx) + e;
-              *h0 += gsm[t0 & 255u] * usm[t0 >> 8];
+#pragma unroll 1
+            for (; i < kk; i++) {
+              const double c0 = gsm[i];
+              double *hp = Hrow(i) + lane;
+              *hp += c0 * u0;
+              if (lane + 32 <= i) hp[32] += c0 * u1;
+              if (lane + 64 <= i) hp[64] += c0 * u2;
             }
           }
           __syncwarp();
@@ -465,9 +484,9 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
           } else {
             // the last slot takes the place of q; the vacated last row / z entry return to zero
             const int last = k - 1;
-            double mv[2];  // element (last, c) for c = lane, lane + 32
+            double mv[3];  // element (last, c) for c = lane, lane + 32, lane + 64
 #pragma unroll
-            for (int t = 0; t < 2; t++) {
+            for (int t = 0; t < 3; t++) {
               const int c = lane + 32 * t;
               mv[t] = (c <= last) ? Hrow(last)[c] : 0.0;
             }
@@ -475,7 +494,7 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
             const int pl = Pb[last], rl = ro[last];
             __syncwarp();
 #pragma unroll
-            for (int t = 0; t < 2; t++) {
+            for (int t = 0; t < 3; t++) {
               const int c = lane + 32 * t;
               if (c <= last) {
                 Hrow(last)[c] = 0.0;
@@ -583,7 +602,8 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
       for (int i = lane; i < nb; i += 32) Hb[i] = 0.0;
     }
     if (lane == 0) {
-      if (ext >= 0) atomicAnd(pool_mask, ~(1 << ext));
+      if (ext1 >= 0) atomicAnd(pool_mask, ~(1 << ext1));
+      if (ext2 >= 0) atomicAnd(pool_mask + 1, ~(1 << ext2));
       a.status[vox] = mode;
       a.iters[vox] = iter;
       if (mode == kNnlsRedo) {
@@ -598,16 +618,18 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
 }  // namespace pnb
 
 namespace pnb {
-// Launch one CTA per SM with as many warps (<= PNB_V3_MAXWARPS) and extension areas (<= 4) as
+// Launch one CTA per SM with as many warps (<= PNB_V3_MAXWARPS) and extension areas (3 + 1) as
 // shared memory holds.  Returns cudaErrorInvalidConfiguration when not even 4 warps fit.
 template <int MT, int WK>
 cudaError_t nnls_v3_launch(const NnlsDeviceArgs &a, cudaStream_t stream) {
   using C = NnlsV3Cfg<MT, WK>;
   constexpr size_t budget = 227 * 1024;
-  int warps = PNB_V3_MAXWARPS, ext = 4;
-  while (warps > 4 && C::smem_doubles(warps, ext) * sizeof(double) > budget) warps--;
-  while (ext > 0 && C::smem_doubles(warps, ext) * sizeof(double) > budget) ext--;
-  const size_t smem = C::smem_doubles(warps, ext) * sizeof(double);
+  int warps = PNB_V3_MAXWARPS, e1 = 3, e2 = 1;
+  while (warps > 4 && C::smem_doubles(warps, e1, e2) * sizeof(double) > budget) warps--;
+  while (e1 > 1 && C::smem_doubles(warps, e1, e2) * sizeof(double) > budget) e1--;
+  if (C::smem_doubles(warps, e1, e2) * sizeof(double) > budget) e2 = 0;
+  if (C::smem_doubles(warps, e1, e2) * sizeof(double) > budget) e1 = 0;
+  const size_t smem = C::smem_doubles(warps, e1, e2) * sizeof(double);
   if (smem > budget) return cudaErrorInvalidConfiguration;
   auto kern = nnls_v3_kernel<MT, WK>;
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -624,7 +646,7 @@ cudaError_t nnls_v3_launch(const NnlsDeviceArgs &a, cudaStream_t stream) {
   const long long want = (a.n_vox + warps - 1) / warps;
   if (want < grid) grid = want;
   if (grid < 1) grid = 1;
-  kern<<<(unsigned)grid, warps * 32, smem, stream>>>(a, ext);
+  kern<<<(unsigned)grid, warps * 32, smem, stream>>>(a, e1, e2);
   return cudaGetLastError();
 }
 }  // namespace pnb
