@@ -307,24 +307,30 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
           if (c >= ke) continue;
           const double *pcol = (seg == 0 ? Hb : (seg == 1 ? H1 : H2)) + off;  // &H(c, i), used when c > i
 #pragma unroll 1
-          for (; c + 1 < ke; c += 2) {
+          for (; c + 3 < ke; c += 4) {
             const double *q0 = (c <= i) ? prow : pcol;
             const double *q1 = (c + 1 <= i) ? prow + 1 : pcol + inc;
-            const double g0 = gsm[c], g1 = gsm[c + 1];
-            a0 += *q0 * g0;
-            a1 += *q1 * g1;
-            pcol += 2 * inc + 1;
-            off += 2 * inc + 1;
-            inc += 2;
-            prow += 2;
+            const double *q2 = (c + 2 <= i) ? prow + 2 : pcol + 2 * inc + 1;
+            const double *q3 = (c + 3 <= i) ? prow + 3 : pcol + 3 * inc + 3;
+            const double h0 = *q0, h1 = *q1, h2 = *q2, h3 = *q3;
+            const double g0 = gsm[c], g1 = gsm[c + 1], g2 = gsm[c + 2], g3 = gsm[c + 3];
+            a0 += h0 * g0;
+            a1 += h1 * g1;
+            a0 += h2 * g2;
+            a1 += h3 * g3;
+            pcol += 4 * inc + 6;
+            off += 4 * inc + 6;
+            inc += 4;
+            prow += 4;
           }
-          if (c < ke) {
+#pragma unroll 1
+          for (; c < ke; c++) {
             const double *q0 = (c <= i) ? prow : pcol;
             a0 += *q0 * gsm[c];
+            pcol += inc;
             off += inc;
             inc += 1;
             prow += 1;
-            c += 1;
           }
         }
         const double vi = a0 + a1;
@@ -457,16 +463,23 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
               const int ke = kk < 32 ? kk : 32;
               double *hp = Hb + lane;
 #pragma unroll 1
-              for (; i + 1 < ke; i += 2) {
-                const double c0 = gsm[i], c1 = gsm[i + 1];
-                double *h1 = hp + i + 1;
-                if (lane <= i) *hp += c0 * u0;
-                if (lane <= i + 1) *h1 += c1 * u0;
-                hp = h1 + i + 2;
+              for (; i + 3 < ke; i += 4) {
+                // four rows per trip, every load issued before the first store (the rows are
+                // distinct memory, which the compiler cannot know)
+                double *h1 = hp + i + 1, *h2 = h1 + i + 2, *h3 = h2 + i + 3;
+                const double c0 = gsm[i], c1 = gsm[i + 1], c2 = gsm[i + 2], c3 = gsm[i + 3];
+                const double v0 = *hp, v1 = *h1, v2 = *h2, v3 = *h3;  // lanes past the row end read the next rows
+                const double w0 = v0 + c0 * u0, w1 = v1 + c1 * u0, w2 = v2 + c2 * u0, w3 = v3 + c3 * u0;
+                if (lane <= i) *hp = w0;
+                if (lane <= i + 1) *h1 = w1;
+                if (lane <= i + 2) *h2 = w2;
+                if (lane <= i + 3) *h3 = w3;
+                hp = h3 + i + 4;
               }
-              if (i < ke) {
+#pragma unroll 1
+              for (; i < ke; i++) {
                 if (lane <= i) *hp += gsm[i] * u0;
-                i += 1;
+                hp += i + 1;
               }
             }
 #pragma unroll 1

@@ -15,12 +15,15 @@ B = model.get_basis(b)
 orders = [int(c) for c in os.environ.get('ORDERS', '2130')]
 for order in orders:
     R = regularization_matrix(250, order, 0.02)
-    ref = engine.nnls_fit(B, R, y, 250, algorithm="robust")
-    for rep in range(2):
+    ref = engine.nnls_fit(B, R, y, 250, algorithm="robust") if not os.environ.get("NOREF") else None
+    for rep in range(int(os.environ.get('REPS', '2'))):
         torch.cuda.synchronize(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record(); r = engine.nnls_fit(B, R, y, 250); e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     redo = _lib.load().pnb_nnls_last_redo_count(0)
+    if ref is None:
+        print(f"reg{order}: {y.shape[0]} vox {ms:.1f} ms -> {y.shape[0]/ms*1e3/1e6:.2f} Mvox/s redo {redo}", flush=True)
+        continue
     d = (r["coefficients"] - ref["coefficients"]).abs().amax(dim=1)
     it_eq = (r["iterations"] == ref["iterations"]).double().mean().item()
     st_eq = (r["status"] == ref["status"]).double().mean().item()
