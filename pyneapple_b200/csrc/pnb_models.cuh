@@ -116,7 +116,7 @@ template <int ID, int T1MODE> struct Model {
 
   PNB_HD static void exps(const Point &pt, double b, double (&e)[K]) {
 #pragma unroll
-    for (int k = 0; k < K; k++) e[k] = exp(b * pt.nd[k]);
+    for (int k = 0; k < K; k++) e[k] = pnb_exp(b * pt.nd[k]);
   }
   PNB_HD static double combine(const Point &pt, const double (&e)[K]) {
     double shape = 0.0;
@@ -146,7 +146,7 @@ template <int ID, int T1MODE> struct Model {
       if (L::d(k) == j) {
         const double t = b * (pk.nd[k] - p0.nd[k]);
         e[k] = (fabs(t) < 1e-4) ? e0[k] + e0[k] * (t * (1.0 + t * (0.5 + t * (1.0 / 6.0))))
-                                : exp(b * pk.nd[k]);
+                                : pnb_exp(b * pk.nd[k]);
       }
     }
     return combine(pk, e);
@@ -158,7 +158,7 @@ template <int ID, int T1MODE> struct Model {
     double shape = 0.0;
 #pragma unroll
     for (int k = 0; k < K; k++) {
-      e[k] = exp(b * pt.nd[k]);
+      e[k] = pnb_exp(b * pt.nd[k]);
       shape = (k == 0) ? pt.w[k] * e[k] : shape + pt.w[k] * e[k];
     }
 #pragma unroll

@@ -225,7 +225,10 @@ PNB_HD double step_to_bound(const double (&x)[N], const double (&s)[N], const do
 #pragma unroll
   for (int i = 0; i < N; i++) {
     steps[i] = kInf;
-    if (s[i] != 0.0) steps[i] = dmax((lb[i * lbs] - x[i]) / s[i], (ub[i * lbs] - x[i]) / s[i]);
+    // max((lb - x) / s, (ub - x) / s) is the quotient whose numerator has the sign of s
+    // (lb - x <= 0 <= ub - x; for an x a rounding error outside the box the max still picks the
+    // same quotient): one division instead of two, same bits
+    if (s[i] != 0.0) steps[i] = ((s[i] > 0.0 ? ub[i * lbs] : lb[i * lbs]) - x[i]) / s[i];
     mn = dmin(mn, steps[i]);
   }
   hits = 0;
@@ -258,7 +261,8 @@ PNB_HD bool trf_prologue(TrfLane<M> &S, const TrfOptions &O, const double *lb, c
   double diag_h[N];
 #pragma unroll
   for (int i = 0; i < N; i++) {
-    const double sc = 1.0 / S.scale_inv[i];
+    // trf.py: scale = x_scale as given, or 1 / scale_inv when it comes from the Jacobian
+    const double sc = O.x_scale_jac ? 1.0 / S.scale_inv[i] : O.x_scale[i];
     if (dv[i] != 0.0) v[i] *= S.scale_inv[i];
     S.d[i] = sqrt(v[i]) * sc;
     diag_h[i] = S.g[i] * dv[i] * sc;

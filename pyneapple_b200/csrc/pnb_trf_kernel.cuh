@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(BLOCK, PNB_TRF_MINBLOCKS) trf_kernel(const Trf
   double *lb_s = y_s + (size_t)2 * m * BLOCK;
   double *ub_s = lb_s + 2 * N * BLOCK;
   double *p0_s = ub_s + 2 * N * BLOCK;
+  exp_tab_init(tid, BLOCK);
   for (int i = tid; i < m; i += BLOCK) b_s[i] = a.b[i];
   if (!pv_bd) {
 #pragma unroll

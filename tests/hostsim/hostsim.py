@@ -69,3 +69,11 @@ def trf_fit(model_id, b, y, p0, lb, ub, frozen=None, t1_mode=0, tr=0.0, tm=0.0, 
     if rc != 0:
         raise RuntimeError(f"hostsim: unsupported model {model_id}/{t1_mode}")
     return dict(params=params, cov=cov, status=status, nfev=nfev, cost=cost)
+
+
+def exp(x):
+    """``pnb_exp`` of pnb_hd.cuh (host build of the same code the kernel runs)."""
+    x = np.ascontiguousarray(x, np.float64)
+    out = np.empty_like(x)
+    lib().pnbh_exp(C.c_long(x.size), _p(x), _p(out))
+    return out

@@ -76,3 +76,8 @@ extern "C" int pnbh_trf_fit(int model_id, int t1_mode, double tr, double tm, int
   CASE(0, 1) CASE(1, 1) CASE(3, 1) CASE(0, 2) CASE(3, 2) CASE(4, 1) CASE(6, 2)
   return -1;
 }
+
+// pnb_exp (pnb_hd.cuh) on an array — checked against libm in tests/test_hostsim_core.py
+extern "C" void pnbh_exp(long n, const double *x, double *out) {
+  for (long i = 0; i < n; i++) out[i] = pnb::pnb_exp(x[i]);
+}

@@ -79,3 +79,20 @@ def test_x_scale_jac_against_scipy():
                             bounds=(P["LB"][i], P["UB"][i]), method="trf", x_scale="jac", ftol=1e-8,
                             max_nfev=250)
         assert rel_err(r["params"][i], ref.x).max() < 1e-5
+
+
+def test_model_exp_is_within_one_ulp_of_libm():
+    """pnb_exp (table + degree-5 polynomial) replaces libdevice exp() in the signal models."""
+    rng = np.random.default_rng(11)
+    x = np.concatenate([
+        -rng.uniform(0.0, 690.0, 400_000), rng.uniform(0.0, 690.0, 100_000), -rng.uniform(0.0, 1e-3, 50_000),
+        np.array([0.0, -0.0, -1e-300, 689.999, -689.999, -690.0, -745.0, -800.0, 709.0, 710.0, np.inf, -np.inf]),
+    ])
+    got = hostsim.exp(x)
+    with np.errstate(over="ignore"):
+        ref = np.exp(x)
+    fin = np.isfinite(ref) & (ref > 0)
+    ulp = np.abs(got[fin] - ref[fin]) / np.spacing(ref[fin])
+    assert ulp.max() <= 1.0, ulp.max()
+    assert np.array_equal(got[~fin], ref[~fin])
+    assert np.isnan(hostsim.exp(np.array([np.nan]))[0])
