@@ -199,7 +199,7 @@ def bench_nnls(args, world, rank, local_rank, dev):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(y_host.nbytes),
                 "d2h_bytes_per_step": int(n_vox * (250 * 8 + 8 + 4 + 4 + 8)),
                 "api": "NNLSSolver.fit(numpy pinned) -> pnb_nnls_fit_host"},
-        "roofline": {"bound": "fp64", "kernel": "nnls_kernel<8>", "achieved": flops / (kernel_ms * 1e-3) / 1e12,
+        "roofline": {"bound": "fp64", "kernel": "nnls_v3_kernel<16,2> (+ nnls_kernel<2> for the voxels it hands over)", "achieved": flops / (kernel_ms * 1e-3) / 1e12,
                      "peak": fp64_peak, "unit": "TFLOP/s", "frac": flops / (kernel_ms * 1e-3) / 1e12 / fp64_peak,
                      "flops_per_launch": flops, "flop_model": "SURVEY.md §8(d) K4, from device iteration counters",
                      "kernel_ms": kernel_ms, "traffic": None,

@@ -20,27 +20,30 @@ constexpr int kWarps = PNB_NNLS_WARPS;        // robust kernel
 #endif
 constexpr int kFastWarps = PNB_NNLS_FAST_WARPS;  // fast kernel
 constexpr size_t kSmemBudget = 220 * 1024;
+// host pipeline depth: with three chunks in flight the next chunk's fast kernel fills the SMs while
+// the few voxels a chunk hands to the robust kernel (one long voxel = milliseconds) are re-solved
+constexpr int kSlots = 3;
 
 struct NnlsCtx {
   unsigned long long *counters = nullptr;  // ring
   int next = 0;
-  // one set per concurrently running launch (the host pipeline alternates two streams)
-  double *scratch[2] = {nullptr, nullptr};
-  size_t scratch_cap[2] = {0, 0};
-  int *redo_list[2] = {nullptr, nullptr};
-  size_t redo_cap[2] = {0, 0};
+  // one set per concurrently running launch (the host pipeline rotates over kSlots streams)
+  double *scratch[kSlots] = {};
+  size_t scratch_cap[kSlots] = {};
+  int *redo_list[kSlots] = {};
+  size_t redo_cap[kSlots] = {};
   unsigned long long *last_redo = nullptr;  // device counter of the most recent auto-mode launch
   // host pipeline
-  cudaStream_t streams[2] = {nullptr, nullptr};
-  double *y[2] = {nullptr, nullptr}, *coef[2] = {nullptr, nullptr}, *rn[2] = {nullptr, nullptr}, *r2[2] = {nullptr, nullptr};
-  int *st[2] = {nullptr, nullptr}, *it[2] = {nullptr, nullptr};
+  cudaStream_t streams[kSlots] = {};
+  double *y[kSlots] = {}, *coef[kSlots] = {}, *rn[kSlots] = {}, *r2[kSlots] = {};
+  int *st[kSlots] = {}, *it[kSlots] = {};
   size_t cap_vox = 0, cap_m = 0, cap_n = 0;
   double *B = nullptr, *rtr = nullptr;
   size_t cap_B = 0, cap_rtr = 0;
   // page-locked staging blocks for pageable caller memory
-  char *pin[2] = {nullptr, nullptr};
-  size_t cap_pin[2] = {0, 0};
-  size_t pend_start[2] = {0, 0}, pend_n[2] = {0, 0};
+  char *pin[kSlots] = {};
+  size_t cap_pin[kSlots] = {};
+  size_t pend_start[kSlots] = {}, pend_n[kSlots] = {};
 };
 NnlsCtx g_ctx[16];
 // PNB_NNLS_NO_V3=1 in the environment keeps the second-generation fast kernel (A/B measurements)
@@ -217,13 +220,13 @@ extern "C" int pnb_nnls_fit_host(const pnb_nnls_problem *p, int device, int64_t 
   std::lock_guard<std::mutex> lk(g_mu);
   NnlsCtx &C = g_ctx[device & 15];
   const int m = p->n_b, n = p->n_bins, BW = 2 * p->rtr_halfband + 1;
-  if (chunk_vox <= 0) chunk_vox = 1 << 16;
+  if (chunk_vox <= 0) chunk_vox = 1 << 18;  // long enough that the tail of a launch (its slowest voxels) stays small
   if (chunk_vox > p->n_vox) chunk_vox = p->n_vox;
   const size_t Cn = (size_t)chunk_vox;
   if (!C.streams[0])
     for (auto &s : C.streams) PNBI_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
   if (Cn > C.cap_vox || (size_t)m > C.cap_m || (size_t)n > C.cap_n) {
-    for (int s = 0; s < 2; s++) {
+    for (int s = 0; s < kSlots; s++) {
       if (C.y[s]) { cudaFree(C.y[s]); cudaFree(C.coef[s]); cudaFree(C.rn[s]); cudaFree(C.r2[s]); cudaFree(C.st[s]); cudaFree(C.it[s]); }
       PNBI_CUDA(cudaMalloc(&C.y[s], Cn * m * sizeof(double)));
       PNBI_CUDA(cudaMalloc(&C.coef[s], Cn * n * sizeof(double)));
@@ -252,7 +255,7 @@ extern "C" int pnb_nnls_fit_host(const pnb_nnls_problem *p, int device, int64_t 
   const size_t o_y = 0, o_coef = o_y + Cn * m * D, o_rn = o_coef + Cn * n * D, o_r2 = o_rn + Cn * D;
   const size_t o_st = o_r2 + Cn * D, o_it = o_st + Cn * I, pin_bytes = o_it + Cn * I;
   if (staged)
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < kSlots; k++) {
       C.pend_n[k] = 0;
       if (pin_bytes > C.cap_pin[k]) {
         if (C.pin[k]) PNBI_CUDA(cudaFreeHost(C.pin[k]));
@@ -274,7 +277,7 @@ extern "C" int pnb_nnls_fit_host(const pnb_nnls_problem *p, int device, int64_t 
     return 0;
   };
   int s = 0;
-  for (size_t start = 0; start < NV; start += Cn, s ^= 1) {
+  for (size_t start = 0; start < NV; start += Cn, s = (s + 1) % kSlots) {
     const size_t nv = (NV - start < Cn) ? NV - start : Cn;
     cudaStream_t st = C.streams[s];
     const double *src_y = p->signal + start * m;
@@ -301,10 +304,9 @@ extern "C" int pnb_nnls_fit_host(const pnb_nnls_problem *p, int device, int64_t 
     PNBI_CUDA(cudaMemcpyAsync(p->status + start, C.st[s], nv * sizeof(int), cudaMemcpyDeviceToHost, st));
     PNBI_CUDA(cudaMemcpyAsync(p->iterations + start, C.it[s], nv * sizeof(int), cudaMemcpyDeviceToHost, st));
   }
-  if (staged) {
-    if (int rc = drain(s)) return rc;
-    if (int rc = drain(s ^ 1)) return rc;
-  }
+  if (staged)
+    for (int k = 0; k < kSlots; k++)  // oldest first
+      if (int rc = drain((s + k) % kSlots)) return rc;
   for (auto &st : C.streams) PNBI_CUDA(cudaStreamSynchronize(st));
   return 0;
 }
