@@ -164,6 +164,48 @@ typedef struct pnb_resize_problem {
 int pnb_resize2d_device(const pnb_resize_problem *prob, void *cuda_stream);
 int pnb_resize2d_host(const pnb_resize_problem *prob, int device);
 
+/*
+ * Post-processing of NNLS spectra for n_vox voxels: peak detection, Gaussian peak areas and
+ * cut-off ranges.  Replaces the per-voxel loop over find_spectrum_peaks / calculate_peak_area /
+ * apply_cutoffs / geometric_mean_peak (utility/spectrum.py:13-206), i.e. one
+ * scipy.signal.find_peaks(x, height=h) + peak_widths(x, peaks, rel_height) call per voxel.
+ * Stages (each optional):
+ *   detect = 1   peaks of `spectrum` with x[peak] >= height -> n_peaks, peak_index, d_values =
+ *                bins[peak], f_values = x[peak];  detect = 0: the peak list is an input
+ *                (n_peaks, and peak_index and / or d_values, f_values)
+ *   areas = 1    f_values = height * FWHM-at-rel_height / (2 sqrt(2 ln 2)) * sqrt(2 pi)
+ *                (`regularized=True` of find_spectrum_peaks)
+ *   normalize    f_values /= sum(f_values)  (when the sum is positive)
+ *   n_cutoffs>0  d_cut, f_cut per range (lo, hi): NaN without a peak, the peak itself, or
+ *                (log10 of the weighted geometric mean, summed weight) of several;
+ *                cut_normalize: f_cut /= nansum(f_cut)
+ * At most max_peaks (<= 32) peaks are stored per voxel, NaN / -1 padded; n_peaks holds the
+ * true count, so a caller can see truncation.
+ */
+typedef struct pnb_spectrum_problem {
+  int32_t n_bins;
+  int32_t max_peaks;
+  int32_t detect, areas, normalize;
+  int32_t n_cutoffs, cut_normalize;
+  int32_t reserved;
+  double height;             /* find_peaks(height=...)                          */
+  double rel_height;         /* peak_widths(rel_height=...), 0.5 = FWHM         */
+  int64_t n_vox;
+  const double *bins;        /* (n_bins) or NULL when d_values is an input       */
+  const double *cutoffs;     /* (n_cutoffs, 2) or NULL                           */
+  const double *spectrum;    /* (n_vox, n_bins) or NULL (cut-offs of given peaks) */
+  int32_t *n_peaks;          /* (n_vox)                                          */
+  int32_t *peak_index;       /* (n_vox, max_peaks) or NULL                       */
+  double *d_values;          /* (n_vox, max_peaks) or NULL                       */
+  double *f_values;          /* (n_vox, max_peaks)                               */
+  double *d_cut;             /* (n_vox, n_cutoffs) or NULL                       */
+  double *f_cut;             /* (n_vox, n_cutoffs) or NULL                       */
+} pnb_spectrum_problem;
+
+int pnb_spectrum_peaks_device(const pnb_spectrum_problem *prob, void *cuda_stream);
+int pnb_spectrum_peaks_host(const pnb_spectrum_problem *prob, int device, int64_t chunk_vox);
+int pnb_sizeof_spectrum_problem(void);
+
 /* housekeeping */
 int pnb_abi_version(void);
 /* sizeof(struct pnb_trf_problem) as compiled, for binding self-checks */

@@ -333,6 +333,57 @@ def case_fitters():
           success=rs.success, r_squared=rs.r_squared, step1_success=fs.step1_result_.success)
 
 
+def case_spectrum():
+    """utility/spectrum.py on real regularised spectra (golden NNLS cases) and on hand-made edge cases."""
+    from pyneapple.utility.spectrum import apply_cutoffs, find_spectrum_peaks
+    from scipy import signal as scipy_signal
+
+    g2 = np.load(os.path.join(GOLD, "nnls_c3_reg2.npz"))
+    g0 = np.load(os.path.join(GOLD, "nnls_c3_reg0.npz"))
+    bins = NNLSModel(d_range=(0.0008, 0.5), n_bins=250).bins
+    rng = np.random.default_rng(7)
+    n = 250
+    edge = np.zeros((24, n))
+    edge[1, 100] = 3.0                                   # single spike
+    edge[2, 100:104] = 2.0                               # flat-topped peak (even plateau -> lower midpoint)
+    edge[3, 100:105] = 2.0                               # odd plateau
+    edge[4, 0] = 5.0; edge[4, n - 1] = 5.0               # maxima on the borders are not peaks
+    edge[5, 1] = 1.0; edge[5, n - 2] = 1.0               # next to the borders they are
+    edge[6, 50] = 1.0; edge[6, 52] = 1.0                 # two equal spikes one bin apart
+    edge[7, 60:70] = np.array([1, 2, 3, 4, 5, 5, 4, 3, 2, 1.0])      # plateau on a ramp
+    edge[8, :] = 1.0                                     # constant
+    edge[9, 40:60] = np.hanning(20) * 4; edge[9, 55:80] += np.hanning(25) * 2   # overlapping lobes
+    edge[10, 30:50] = np.hanning(20); edge[10, 120:150] = 0.5 * np.hanning(30); edge[10, 200:230] = 2 * np.hanning(30)
+    edge[11, 10:240] = np.abs(np.sin(np.arange(230) / 3.0))          # many peaks (> max_peaks)
+    edge[12, 100:110] = np.array([1, 3, 1, 3, 1, 3, 1, 3, 1, 0.0])   # equal heights, prominence ties
+    edge[13, 100] = 0.1                                  # exactly the height threshold
+    edge[14, 100] = 0.1 - 1e-12                          # just below it
+    edge[15, 80:120] = np.hanning(40) + 0.5              # peak on a pedestal with cliffs
+    edge[16, :] = np.linspace(0, 1, n)                   # monotone: no peak
+    edge[17, :] = np.linspace(1, 0, n)
+    edge[18, 100:103] = np.array([1.0, 1.0, 2.0])        # plateau followed by a rise, then a fall
+    edge[19, 5:15] = np.hanning(10) * 3; edge[19, 235:245] = np.hanning(10) * 3
+    edge[20:24] = rng.random((4, n)) * (rng.random((4, n)) > 0.93)   # sparse random
+    spectra = np.concatenate([g2["coefficients"][:96], g0["coefficients"][:32], edge])
+    cutoffs = [(0.0008, 0.003), (0.003, 0.05), (0.05, 0.5)]
+    out = {}
+    for tag, height, reg in (("h0p1_reg", 0.1, True), ("h0p1_raw", 0.1, False), ("h5_reg", 5.0, True)):
+        P = 32
+        nv = spectra.shape[0]
+        n_peaks = np.zeros(nv, np.int32); idx = np.full((nv, P), -1, np.int32)
+        d = np.full((nv, P), np.nan); f = np.full((nv, P), np.nan)
+        dc = np.full((nv, len(cutoffs)), np.nan); fc = np.full((nv, len(cutoffs)), np.nan)
+        for v in range(nv):
+            dv, fv = find_spectrum_peaks(spectra[v], bins, height=height, regularized=reg)
+            pk = scipy_signal.find_peaks(spectra[v], height=height)[0]
+            assert len(pk) == len(dv) and len(dv) <= P
+            n_peaks[v] = len(dv); idx[v, :len(dv)] = pk; d[v, :len(dv)] = dv; f[v, :len(dv)] = fv
+            dc[v], fc[v] = apply_cutoffs(dv, fv, cutoffs)
+        out.update({f"{tag}_n_peaks": n_peaks, f"{tag}_idx": idx, f"{tag}_d": d, f"{tag}_f": f,
+                    f"{tag}_d_cut": dc, f"{tag}_f_cut": fc})
+    _save("spectrum_peaks", spectra=spectra, bins=bins, cutoffs=np.array(cutoffs), **out)
+
+
 CASES = {k[5:]: v for k, v in globals().items() if k.startswith("case_")}
 
 if __name__ == "__main__":

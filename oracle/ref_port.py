@@ -385,3 +385,56 @@ def nnls_fit(xdata, signal, d_range, n_bins, reg_order=0, mu=0.02, max_iter=250,
         "residual": np.array([r[1] for r in res]),
         "success": np.array([r[2] for r in res], bool),
     }
+
+
+# --------------------------------------------------------------------------- NNLS spectrum post-processing
+def spectrum_peaks(spectra, bins, height=0.1, regularized=False, cutoffs=None, max_peaks=8):
+    """utility/spectrum.py:50-103 (find_spectrum_peaks -> calculate_peak_area :13-47) and :139-206
+    (apply_cutoffs -> geometric_mean_peak :106-136) per row of ``spectra``, with the same
+    scipy.signal.find_peaks / peak_widths calls, packed like ``find_spectrum_peaks_batch``."""
+    from scipy import signal as scipy_signal
+
+    spectra = np.atleast_2d(np.asarray(spectra, dtype=np.float64))
+    bins = np.asarray(bins, dtype=np.float64)
+    n = spectra.shape[0]
+    K = 0 if cutoffs is None else len(cutoffs)
+    out = dict(n_peaks=np.zeros(n, np.int32), peak_index=np.full((n, max_peaks), -1, np.int32),
+               d_values=np.full((n, max_peaks), np.nan), f_values=np.full((n, max_peaks), np.nan),
+               d_cut=np.full((n, K), np.nan), f_cut=np.full((n, K), np.nan))
+    for v in range(n):
+        x = spectra[v]
+        idx, props = scipy_signal.find_peaks(x, height=height)
+        k = len(idx)
+        out["n_peaks"][v] = k
+        if k:
+            raw = props["peak_heights"]
+            if regularized:
+                fw = scipy_signal.peak_widths(x, idx, rel_height=0.5)[0]
+                f = np.array([float(h * w / (2 * np.sqrt(2 * np.log(2))) * np.sqrt(2 * np.pi)) for h, w in zip(raw, fw)])
+            else:
+                f = raw.copy()
+            total = np.sum(f)
+            if total > 0:
+                f = f / total
+            d = bins[idx]
+        else:
+            d, f = np.array([]), np.array([])
+        m = min(k, max_peaks)
+        out["peak_index"][v, :m], out["d_values"][v, :m], out["f_values"][v, :m] = idx[:m], d[:m], f[:m]
+        if K:
+            new_d, new_f = [], []
+            for lo, hi in cutoffs:
+                mask = (d >= lo) & (d <= hi)
+                _d, _f = d[mask], f[mask]
+                if len(_d) == 0:
+                    new_d.append(np.nan); new_f.append(np.nan)
+                elif len(_d) == 1:
+                    new_d.append(float(_d[0])); new_f.append(float(_f[0]))
+                else:
+                    new_d.append(float(np.log10(np.prod(_d ** (_f / np.sum(_f)))))); new_f.append(float(np.sum(_f)))
+            new_d, new_f = np.array(new_d), np.array(new_f)
+            total = np.nansum(new_f)
+            if total > 0:
+                new_f = new_f / total
+            out["d_cut"][v], out["f_cut"][v] = new_d, new_f
+    return out

@@ -83,6 +83,33 @@ class NnlsProblem(C.Structure):
     ]
 
 
+class SpectrumProblem(C.Structure):
+    """Mirror of ``struct pnb_spectrum_problem``."""
+
+    _fields_ = [
+        ("n_bins", C.c_int32),
+        ("max_peaks", C.c_int32),
+        ("detect", C.c_int32),
+        ("areas", C.c_int32),
+        ("normalize", C.c_int32),
+        ("n_cutoffs", C.c_int32),
+        ("cut_normalize", C.c_int32),
+        ("reserved", C.c_int32),
+        ("height", C.c_double),
+        ("rel_height", C.c_double),
+        ("n_vox", C.c_int64),
+        ("bins", C.c_void_p),
+        ("cutoffs", C.c_void_p),
+        ("spectrum", C.c_void_p),
+        ("n_peaks", C.c_void_p),
+        ("peak_index", C.c_void_p),
+        ("d_values", C.c_void_p),
+        ("f_values", C.c_void_p),
+        ("d_cut", C.c_void_p),
+        ("f_cut", C.c_void_p),
+    ]
+
+
 class ResizeProblem(C.Structure):
     """Mirror of ``struct pnb_resize_problem``."""
 
@@ -139,6 +166,10 @@ def load():
     lib.pnb_resize2d_device.restype = C.c_int
     lib.pnb_resize2d_host.argtypes = [C.POINTER(ResizeProblem), C.c_int]
     lib.pnb_resize2d_host.restype = C.c_int
+    lib.pnb_spectrum_peaks_device.argtypes = [C.POINTER(SpectrumProblem), C.c_void_p]
+    lib.pnb_spectrum_peaks_device.restype = C.c_int
+    lib.pnb_spectrum_peaks_host.argtypes = [C.POINTER(SpectrumProblem), C.c_int, C.c_int64]
+    lib.pnb_spectrum_peaks_host.restype = C.c_int
     lib.pnb_nnls_last_redo_count.argtypes = [C.c_int]
     lib.pnb_nnls_last_redo_count.restype = C.c_int64
     lib.pnb_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_int64]

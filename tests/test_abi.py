@@ -29,6 +29,8 @@ def test_abi_version(lib):
 def test_struct_layout_matches_header(lib):
     # sizeof(pnb_trf_problem) as compiled by nvcc must equal the ctypes mirror
     assert ctypes.sizeof(_lib.TrfProblem) == lib.pnb_sizeof_trf_problem()
+    assert ctypes.sizeof(_lib.NnlsProblem) == lib.pnb_sizeof_nnls_problem()
+    assert ctypes.sizeof(_lib.SpectrumProblem) == lib.pnb_sizeof_spectrum_problem()
 
 
 def test_bad_arguments_are_rejected_without_a_device(lib):
@@ -51,3 +53,13 @@ def test_no_cpu_fallback():
     b = np.linspace(0, 1000, 8)
     with pytest.raises(_lib.EngineError):
         s.fit(b, 1000 * np.exp(-b * 1e-3))
+
+
+def test_spectrum_bad_arguments_are_rejected_without_a_device(lib):
+    prob = _lib.SpectrumProblem()
+    prob.max_peaks = 64
+    assert lib.pnb_spectrum_peaks_host(ctypes.byref(prob), 0, 0) == -1
+    assert b"max_peaks" in lib.pnb_last_error()
+    prob.max_peaks, prob.n_vox, prob.detect, prob.n_bins = 8, 4, 1, 250
+    assert lib.pnb_spectrum_peaks_host(ctypes.byref(prob), 0, 0) == -1
+    assert b"spectrum" in lib.pnb_last_error()
