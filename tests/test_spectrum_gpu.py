@@ -123,3 +123,21 @@ def test_single_spectrum_mirrors_of_the_reference_functions():
     assert d.size == 0 and f.size == 0
     dn, fn = spectrum.apply_cutoffs(d, f, [(0.001, 0.01)])
     assert np.isnan(dn).all() and np.isnan(fn).all()
+
+
+def test_solver_fit_spectrum_peaks_equals_fit_then_postprocess():
+    from pyneapple_b200 import models, spectrum, synth
+    from pyneapple_b200.solvers import NNLSSolver
+
+    cfg = synth.CONFIGS["C3"]
+    b, y, _ = synth.sample_voxels(cfg, 3000)
+    model = models.NNLSModel(d_range=(0.0008, 0.5), n_bins=250)
+    cut = [(0.0008, 0.003), (0.003, 0.05), (0.05, 0.5)]
+    solver = NNLSSolver(model=model, reg_order=2, mu=0.02, max_iter=250)
+    fused = solver.fit_spectrum_peaks(b, y, height=0.1, cutoffs=cut, chunk_vox=1024)
+    solver.fit(b, y)
+    two = spectrum.find_spectrum_peaks_batch(solver.params_["coefficients"], model.bins, 0.1, True, cutoffs=cut)
+    for k, v in two.items():
+        assert np.array_equal(fused[k], v, equal_nan=True), k
+    assert np.array_equal(fused["status"], solver.status_)
+    np.testing.assert_array_equal(fused["residual"], solver.diagnostics_["residual"])
