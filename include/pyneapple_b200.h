@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PNB_ABI_VERSION 1
+#define PNB_ABI_VERSION 2
 
 /* model_id: parameter order is the reference's `_all_param_names`
  * (models/monoexp.py:91-105, models/biexp.py:103-126, models/triexp.py:103-128) */
@@ -45,6 +45,9 @@ enum {
 };
 /* t1_mode appends the parameter T1 (model_functions/multiexp.py:210-302) */
 enum { PNB_T1_NONE = 0, PNB_T1_STANDARD = 1, PNB_T1_STEAM = 2 };
+/* SciPy least_squares method behind curve_fit (solvers/curvefit.py:295-306, `method` keyword):
+ * scipy/optimize/_lsq/trf.py (trf_bounds) or scipy/optimize/_lsq/dogbox.py */
+enum { PNB_METHOD_TRF = 0, PNB_METHOD_DOGBOX = 1 };
 
 enum {
   PNB_E_BADARG = -1,      /* inconsistent sizes / null pointers */
@@ -93,6 +96,9 @@ typedef struct pnb_trf_problem {
   double gtol;               /* SciPy default 1e-8                             */
   int32_t jac_mode;          /* 0 analytic, 1 SciPy '2-point' finite differences */
   int32_t x_scale_jac;       /* 1: x_scale='jac'                               */
+  int32_t method;            /* PNB_METHOD_TRF (curve_fit's default with bounds) or
+                                PNB_METHOD_DOGBOX: least_squares(method=...)      */
+  int32_t reserved;
   double x_scale[8];         /* per parameter, 1.0 = SciPy default             */
   /* outputs */
   double *params;            /* (n_params, n_vox); fixed rows repeat the fixed value */

@@ -384,6 +384,30 @@ def case_spectrum():
     _save("spectrum_peaks", spectra=spectra, bins=bins, cutoffs=np.array(cutoffs), **out)
 
 
+def case_dogbox():
+    """method = "dogbox" (forwarded from the TOML to curve_fit, solvers/curvefit.py:295-306)."""
+    cfg, p0, bounds = _cfg_args("C2")
+    b, y, _ = synth.sample_voxels(cfg, 512, z=3)
+    _run_curvefit("dbx_biexp_s0_c2", "biexp", {"fit_s0": True}, b, y, p0, bounds, method="dogbox")
+    # tight bounds and a start on a bound: active-set logic, variables snapped onto bounds
+    bt = dict(bounds, D1=(1e-5, 0.0012), f1=(0.01, 0.25))
+    pt = dict(p0, D1=1e-5, f1=0.25)
+    _run_curvefit("dbx_biexp_s0_onbound", "biexp", {"fit_s0": True}, b, y[:256], pt, bt, method="dogbox")
+    for mi in (1, 2, 3, 6):
+        _run_curvefit(f"dbx_biexp_s0_maxiter{mi}", "biexp", {"fit_s0": True}, b, y[:48], p0, bounds,
+                      method="dogbox", max_iter=mi)
+    rng = np.random.default_rng(78)
+    d1 = rng.uniform(8e-4, 2e-3, size=128)
+    _run_curvefit("dbx_biexp_s0_pixfixed_D1", "biexp", {"fit_s0": True}, b, y[:128], p0, bounds,
+                  pixel_fixed={"D1": d1}, method="dogbox")
+    cfg1, p01, b1 = _cfg_args("C1")
+    bb, yy, _ = synth.sample_voxels(cfg1, 256, z=2)
+    _run_curvefit("dbx_mono_c1", "monoexp", {}, bb, yy, p01, b1, method="dogbox")
+    cfg5, p05, b5 = _cfg_args("C5")
+    bb, yy, _ = synth.sample_voxels(cfg5, 128, z=2)
+    _run_curvefit("dbx_triexp_reduced", "triexp", {}, bb, yy, p05, b5, method="dogbox")
+
+
 CASES = {k[5:]: v for k, v in globals().items() if k.startswith("case_")}
 
 if __name__ == "__main__":

@@ -64,7 +64,9 @@ void parallel_memcpy(void *dst, const void *src, size_t bytes) {
 }
 }  // namespace pnbi
 
-#define PNB_DECL(id, t1) extern "C" cudaError_t pnb_trf_launch_##id##_##t1(const pnb::TrfDeviceArgs *, cudaStream_t);
+#define PNB_DECL(id, t1)                                                                            \
+  extern "C" cudaError_t pnb_trf_launch_##id##_##t1(const pnb::TrfDeviceArgs *, cudaStream_t);     \
+  extern "C" cudaError_t pnb_dogbox_launch_##id##_##t1(const pnb::TrfDeviceArgs *, cudaStream_t);
 PNB_DECL(0, 0) PNB_DECL(1, 0) PNB_DECL(2, 0) PNB_DECL(3, 0) PNB_DECL(4, 0) PNB_DECL(5, 0) PNB_DECL(6, 0)
 #ifdef PNB_WITH_T1
 PNB_DECL(0, 1) PNB_DECL(1, 1) PNB_DECL(2, 1) PNB_DECL(3, 1) PNB_DECL(4, 1) PNB_DECL(5, 1) PNB_DECL(6, 1)
@@ -73,22 +75,20 @@ PNB_DECL(0, 2) PNB_DECL(1, 2) PNB_DECL(2, 2) PNB_DECL(3, 2) PNB_DECL(4, 2) PNB_D
 
 namespace {
 
-LaunchFn trf_launcher(int model_id, int t1_mode) {
-  static const LaunchFn table[3][7] = {
-      {pnb_trf_launch_0_0, pnb_trf_launch_1_0, pnb_trf_launch_2_0, pnb_trf_launch_3_0,
-       pnb_trf_launch_4_0, pnb_trf_launch_5_0, pnb_trf_launch_6_0},
+#define PNB_ROW(name, t1) {name##_0_##t1, name##_1_##t1, name##_2_##t1, name##_3_##t1, name##_4_##t1, name##_5_##t1, name##_6_##t1}
+#define PNB_NOROW {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}
+LaunchFn trf_launcher(int model_id, int t1_mode, int method = 0) {
+  static const LaunchFn table[2][3][7] = {
 #ifdef PNB_WITH_T1
-      {pnb_trf_launch_0_1, pnb_trf_launch_1_1, pnb_trf_launch_2_1, pnb_trf_launch_3_1,
-       pnb_trf_launch_4_1, pnb_trf_launch_5_1, pnb_trf_launch_6_1},
-      {pnb_trf_launch_0_2, pnb_trf_launch_1_2, pnb_trf_launch_2_2, pnb_trf_launch_3_2,
-       pnb_trf_launch_4_2, pnb_trf_launch_5_2, pnb_trf_launch_6_2},
+      {PNB_ROW(pnb_trf_launch, 0), PNB_ROW(pnb_trf_launch, 1), PNB_ROW(pnb_trf_launch, 2)},
+      {PNB_ROW(pnb_dogbox_launch, 0), PNB_ROW(pnb_dogbox_launch, 1), PNB_ROW(pnb_dogbox_launch, 2)},
 #else
-      {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr},
-      {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr},
+      {PNB_ROW(pnb_trf_launch, 0), PNB_NOROW, PNB_NOROW},
+      {PNB_ROW(pnb_dogbox_launch, 0), PNB_NOROW, PNB_NOROW},
 #endif
   };
-  if (model_id < 0 || model_id > 6 || t1_mode < 0 || t1_mode > 2) return nullptr;
-  return table[t1_mode][model_id];
+  if (model_id < 0 || model_id > 6 || t1_mode < 0 || t1_mode > 2 || method < 0 || method > 1) return nullptr;
+  return table[method][t1_mode][model_id];
 }
 
 int model_n_params(int model_id, int t1_mode) {
@@ -100,7 +100,9 @@ int check_problem(const pnb_trf_problem *p) {
   if (!p) return fail(PNB_E_BADARG, "null problem");
   if (p->model_id < 0 || p->model_id > 6 || p->t1_mode < 0 || p->t1_mode > 2)
     return fail(PNB_E_UNSUPPORTED, "unknown model_id / t1_mode");
-  if (!trf_launcher(p->model_id, p->t1_mode))
+  if (p->method != PNB_METHOD_TRF && p->method != PNB_METHOD_DOGBOX)
+    return fail(PNB_E_UNSUPPORTED, "method must be PNB_METHOD_TRF or PNB_METHOD_DOGBOX");
+  if (!trf_launcher(p->model_id, p->t1_mode, p->method))
     return fail(PNB_E_UNSUPPORTED, "this build has no kernel for the requested model / T1 mode");
   if (p->n_params != model_n_params(p->model_id, p->t1_mode))
     return fail(PNB_E_BADARG, "n_params does not match the model");
@@ -120,6 +122,7 @@ pnb::TrfOptions make_options(const pnb_trf_problem *p) {
   pnb::TrfOptions o;
   o.ftol = p->ftol; o.xtol = p->xtol; o.gtol = p->gtol;
   o.max_nfev = p->max_nfev; o.jac_mode = p->jac_mode; o.x_scale_jac = p->x_scale_jac;
+  o.method = p->method;
   o.frozen = p->frozen_mask & ((1u << p->n_params) - 1u);
   for (int i = 0; i < 8; i++) o.x_scale[i] = (p->x_scale[i] > 0.0) ? p->x_scale[i] : 1.0;
   o.tr = p->repetition_time; o.tm = p->mixing_time;
@@ -185,7 +188,7 @@ extern "C" int pnb_trf_fit_device(const pnb_trf_problem *p, void *cuda_stream) {
   a.params = p->params; a.cov = p->cov; a.status = p->status; a.nfev = p->nfev;
   a.njev = p->njev; a.cost = p->cost; a.r2 = p->r_squared;
   if (int rc = next_counter(&a.counter)) return rc;
-  cudaError_t e = trf_launcher(p->model_id, p->t1_mode)(&a, stream);
+  cudaError_t e = trf_launcher(p->model_id, p->t1_mode, p->method)(&a, stream);
   if (e != cudaSuccess) return cuda_fail(e, "trf kernel launch");
   g_launches.fetch_add(1);
   return 0;
@@ -294,7 +297,7 @@ extern "C" int pnb_trf_fit_host(const pnb_trf_problem *p, int device, int64_t ch
   PNB_CUDA(cudaStreamSynchronize(s0));
 
   const pnb::TrfOptions opt = make_options(p);
-  LaunchFn launch = trf_launcher(p->model_id, p->t1_mode);
+  LaunchFn launch = trf_launcher(p->model_id, p->t1_mode, p->method);
   const size_t NV = (size_t)p->n_vox;
   // pageable caller memory is staged through page-locked blocks with multi-threaded host copies
   const bool staged = pnbi::is_pageable(p->ydata) || pnbi::is_pageable(p->params);

@@ -42,6 +42,7 @@ struct TrfOptions {
   int max_nfev;
   int jac_mode;      // 0 analytic Jacobian, 1 SciPy '2-point' finite differences
   int x_scale_jac;   // x_scale == 'jac'
+  int method;        // 0 'trf', 1 'dogbox' (pnb_dogbox_core.cuh)
   unsigned frozen;   // bit j set: parameter j is fixed at its p0 value
   double x_scale[8];
   double tr, tm;     // repetition / mixing time of the T1 variants
@@ -553,9 +554,11 @@ PNB_HD bool trf_begin(TrfLane<M> &S, const TrfOptions &O, const double (&p0)[M::
   if (!y_finite) { S.status = kStNonFiniteY; return false; }
   if (bad_bounds) { S.status = kStBadBounds; return false; }
   if (outside) { S.status = kStInfeasible; return false; }
+  if (O.method == 0) {  // least_squares(): x0 = make_strictly_feasible(x0, lb, ub) for 'trf' only
 #pragma unroll
-  for (int i = 0; i < N; i++)
-    if (!((O.frozen >> i) & 1u)) S.x[i] = strictly_feasible(S.x[i], lb[i * lbs], ub[i * lbs], 1e-10);
+    for (int i = 0; i < N; i++)
+      if (!((O.frozen >> i) & 1u)) S.x[i] = strictly_feasible(S.x[i], lb[i * lbs], ub[i * lbs], 1e-10);
+  }
   return true;
 }
 

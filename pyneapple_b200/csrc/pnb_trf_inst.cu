@@ -1,5 +1,5 @@
-// One translation unit per (model, T1 mode): compiled with
-//   -DPNB_MODEL_ID=<0..6> -DPNB_T1MODE=<0..2>
+// One translation unit per (model, T1 mode, method): compiled with
+//   -DPNB_MODEL_ID=<0..6> -DPNB_T1MODE=<0..2> [-DPNB_METHOD=1 for dogbox]
 // so the seven-plus register-heavy kernels build in parallel.
 #include "pnb_trf_kernel.cuh"
 
@@ -10,10 +10,17 @@
 #define PNB_TRF_BLOCK 128
 #endif
 
+#ifndef PNB_METHOD
+#define PNB_METHOD 0
+#endif
+#if PNB_METHOD == 1
+#define PNB_CAT_(a, b, c) pnb_dogbox_launch_##a##_##b
+#else
 #define PNB_CAT_(a, b, c) pnb_trf_launch_##a##_##b
+#endif
 #define PNB_CAT(a, b) PNB_CAT_(a, b, 0)
 
 extern "C" cudaError_t PNB_CAT(PNB_MODEL_ID, PNB_T1MODE)(const pnb::TrfDeviceArgs *a,
                                                           cudaStream_t stream) {
-  return pnb::trf_launch<pnb::Model<PNB_MODEL_ID, PNB_T1MODE>, PNB_TRF_BLOCK>(*a, stream);
+  return pnb::trf_launch<pnb::Model<PNB_MODEL_ID, PNB_T1MODE>, PNB_TRF_BLOCK, PNB_METHOD>(*a, stream);
 }

@@ -25,7 +25,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
-#include "pnb_trf_core.cuh"
+#include "pnb_dogbox_core.cuh"
 
 namespace pnb {
 
@@ -63,7 +63,7 @@ constexpr int kTrfClaim = 64;  // voxel indices claimed per warp-level atomicAdd
 #define PNB_TRF_MINBLOCKS 1
 #endif
 
-template <class M, int BLOCK>
+template <class M, int BLOCK, int METHOD = 0>
 __global__ void __launch_bounds__(BLOCK, PNB_TRF_MINBLOCKS) trf_kernel(const TrfDeviceArgs a) {
   constexpr int N = M::NP;
   constexpr unsigned FULL = 0xffffffffu;
@@ -114,6 +114,7 @@ __global__ void __launch_bounds__(BLOCK, PNB_TRF_MINBLOCKS) trf_kernel(const Trf
   claim_range(qb, nb);
 
   TrfLane<M> S;
+  DogboxLane<M> DB;  // METHOD == 1 only
   long long cur = -1, nxt = -1;
   int buf = 0, nxt_buf = 0;  // which half of the double buffers holds `cur` / receives `nxt`
   bool first_eval = false;
@@ -196,13 +197,17 @@ __global__ void __launch_bounds__(BLOCK, PNB_TRF_MINBLOCKS) trf_kernel(const Trf
       // ---- prepare a trial step -------------------------------------------------
       bool go = true;
       if (S.need_prologue) {
-        go = trf_prologue<M>(S, O, my_lb, my_ub, BLOCK);
+        go = (METHOD == 1) ? dbx_prologue<M>(S, DB, O) : trf_prologue<M>(S, O, my_lb, my_ub, BLOCK);
         S.need_prologue = false;
       }
       if (go) {
-        double p_h[N];
-        trf_solve_tr<M>(S, p_h);
-        trf_select_step<M>(S, p_h, my_lb, my_ub, BLOCK, O.frozen);
+        if (METHOD == 1) {
+          dbx_trial<M>(S, DB, O, my_lb, my_ub, BLOCK);
+        } else {
+          double p_h[N];
+          trf_solve_tr<M>(S, p_h);
+          trf_select_step<M>(S, p_h, my_lb, my_ub, BLOCK, O.frozen);
+        }
         do_eval = true;
       } else {
         finished = true;
@@ -215,9 +220,12 @@ __global__ void __launch_bounds__(BLOCK, PNB_TRF_MINBLOCKS) trf_kernel(const Trf
       trf_evaluate<M>(S.x_new, O, m, yb, my_lb, my_ub, BLOCK, c, g, A);
       if (first_eval) {
         first_eval = false;
-        if (!trf_after_first_eval<M>(S, O, c, g, A, my_lb, my_ub, BLOCK)) finished = true;
+        const bool ok0 = (METHOD == 1) ? dbx_after_first_eval<M>(S, DB, O, c, g, A, my_lb, my_ub, BLOCK)
+                                       : trf_after_first_eval<M>(S, O, c, g, A, my_lb, my_ub, BLOCK);
+        if (!ok0) finished = true;
       } else {
-        S.need_prologue = trf_after_trial<M>(S, O, c, g, A);
+        S.need_prologue = (METHOD == 1) ? dbx_after_trial<M>(S, DB, O, c, g, A, my_lb, my_ub, BLOCK)
+                                        : trf_after_trial<M>(S, O, c, g, A);
       }
     }
     __syncwarp();
@@ -273,9 +281,9 @@ template <class M, int BLOCK> size_t trf_smem_bytes(int n_b) {
 }
 
 // Launch configuration: persistent grid, as many CTAs as are resident.
-template <class M, int BLOCK> cudaError_t trf_launch(const TrfDeviceArgs &a, cudaStream_t stream) {
+template <class M, int BLOCK, int METHOD = 0> cudaError_t trf_launch(const TrfDeviceArgs &a, cudaStream_t stream) {
   const size_t smem = trf_smem_bytes<M, BLOCK>(a.n_b);
-  auto kern = trf_kernel<M, BLOCK>;
+  auto kern = trf_kernel<M, BLOCK, METHOD>;
   static int blocks_per_sm_cache = -1;
   static size_t smem_cache = 0;
   static int sm_count = 0;

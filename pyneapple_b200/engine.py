@@ -33,6 +33,7 @@ STATUS_MESSAGES = {
 
 JAC_ANALYTIC = 0
 JAC_TWO_POINT = 1
+METHODS = {"trf": 0, "dogbox": 1}  # PNB_METHOD_*: scipy.optimize.least_squares(method=...)
 
 
 def _is_torch_cuda(x) -> bool:
@@ -75,6 +76,7 @@ def trf_fit(
     device: int = 0,
     chunk_vox: int = 0,
     out: dict | None = None,
+    method: str = "trf",
 ):
     """Fit all voxels.  ``p0``/``lb``/``ub``: ``(n_all,)`` or ``(n_all, n_vox)`` over
     ``desc.all_names`` (frozen rows of ``p0`` carry the fixed values).
@@ -97,6 +99,9 @@ def trf_fit(
     prob.ftol, prob.xtol, prob.gtol = float(ftol), float(xtol), float(gtol)
     prob.jac_mode = int(jac_mode)
     prob.x_scale_jac = int(bool(x_scale_jac))
+    if method not in METHODS:
+        raise NotImplementedError(f"method={method!r}: SciPy's 'trf' and 'dogbox' have a B200 implementation")
+    prob.method = METHODS[method]
     xs = np.ones(8)
     if x_scale is not None:
         xs[:n_all] = np.broadcast_to(np.asarray(x_scale, float), (n_all,))

@@ -97,15 +97,21 @@ class CurveFitSolver(BaseSolver):
         self.cost_ = None
         self.r_squared_ = None
 
+    def _ls_method(self) -> str:
+        """least_squares method the engine runs (subclasses with their own outer method use 'trf')."""
+        return self.method if self.method in engine.METHODS else "trf"
+
     # ------------------------------------------------------------------
     def fit(self, xdata, ydata, p0=None, bounds=None, pixel_fixed_params=None, **fit_kwargs):
         """Fit all voxels (curvefit.py:91-159).  Unknown keyword arguments are
         swallowed like the reference does (``fixed_param_maps=None`` arrives
         here from ``run_pipeline`` through ``IDEALFitter.fit``)."""
         self._reset_state()
-        if self.method != "trf":
+        if self.method not in engine.METHODS:
+            # 'lm' (MINPACK) cannot be used through this solver in the reference either: curve_fit
+            # rejects it for bounded problems and the solver always passes bounds
             raise NotImplementedError(
-                f"method={self.method!r}: only SciPy's 'trf' has a B200 implementation"
+                f"method={self.method!r}: SciPy's 'trf' and 'dogbox' have a B200 implementation"
             )
         xdata = np.asarray(xdata)
         on_device = engine._is_torch_cuda(ydata)
@@ -189,6 +195,7 @@ class CurveFitSolver(BaseSolver):
             jac_mode=jac_mode, x_scale=xs_full, x_scale_jac=x_scale_jac,
             want_cov=self.want_cov, device=self.device, chunk_vox=self.chunk_vox,
             out=self._pinned_out(len(all_names), len(all_names) - len(fixed_names), n_pixels, ydata),
+            method=self._ls_method(),
         )
         self._free_rows = [all_names.index(n) for n in free_names]
         return res, free_names
@@ -250,6 +257,7 @@ class CurveFitSolver(BaseSolver):
             ftol=self.tol, xtol=self.solver_kwargs.get("xtol", 1e-8),
             gtol=self.solver_kwargs.get("gtol", 1e-8), jac_mode=jac_mode,
             want_cov=self.want_cov if want_cov is None else want_cov, device=self.device,
+            method=self._ls_method(),
         )
         res["free_names"] = free_names
         res["free_rows"] = [all_names.index(n) for n in free_names]

@@ -29,6 +29,18 @@ TRF_CASES = {
     "trf_biexp_s0_maxiter5": ("biexp", "s0"),
     "trf_biexp_s0_badbounds": ("biexp", "s0"),
 }
+# method = "dogbox" goldens (oracle/make_golden.py: case_dogbox)
+DBX_CASES = {
+    "dbx_biexp_s0_c2": ("biexp", "s0"),
+    "dbx_biexp_s0_onbound": ("biexp", "s0"),
+    "dbx_biexp_s0_maxiter1": ("biexp", "s0"),
+    "dbx_biexp_s0_maxiter2": ("biexp", "s0"),
+    "dbx_biexp_s0_maxiter3": ("biexp", "s0"),
+    "dbx_biexp_s0_maxiter6": ("biexp", "s0"),
+    "dbx_biexp_s0_pixfixed_D1": ("biexp", "s0"),
+    "dbx_mono_c1": ("monoexp", "s0"),
+    "dbx_triexp_reduced": ("triexp", "reduced"),
+}
 MODEL_FIXED = {"trf_biexp_s0_modelfixed_D2": {"D2": 0.03}}
 
 

@@ -16,7 +16,7 @@ _LIB = None
 def build(force=False):
     srcs = [os.path.join(_HERE, "trf_hostsim.cpp")] + [
         os.path.join(_HERE, "..", "..", "pyneapple_b200", "csrc", f)
-        for f in ("pnb_trf_core.cuh", "pnb_models.cuh", "pnb_hd.cuh")
+        for f in ("pnb_trf_core.cuh", "pnb_dogbox_core.cuh", "pnb_models.cuh", "pnb_hd.cuh")
     ]
     newest = max(os.path.getmtime(s) for s in srcs)
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < newest:
@@ -39,7 +39,7 @@ def _p(a, t=C.c_double):
 
 
 def trf_fit(model_id, b, y, p0, lb, ub, frozen=None, t1_mode=0, tr=0.0, tm=0.0, ftol=1e-8,
-            xtol=1e-8, gtol=1e-8, max_nfev=250, jac_mode=0, x_scale_jac=False, x_scale=None):
+            xtol=1e-8, gtol=1e-8, max_nfev=250, jac_mode=0, x_scale_jac=False, x_scale=None, method=0):
     b = np.ascontiguousarray(b, np.float64)
     y = np.ascontiguousarray(np.atleast_2d(y), np.float64)
     n_vox, nb = y.shape
@@ -64,7 +64,7 @@ def trf_fit(model_id, b, y, p0, lb, ub, frozen=None, t1_mode=0, tr=0.0, tm=0.0, 
         C.c_long(n_vox), _p(y), _p(p0), _p(lb), _p(ub), _p(fr, C.c_int), C.c_double(ftol),
         C.c_double(xtol), C.c_double(gtol), C.c_int(max_nfev), C.c_int(jac_mode),
         C.c_int(int(x_scale_jac)), _p(xs), _p(params), _p(cov), _p(status, C.c_int),
-        _p(nfev, C.c_int), _p(cost),
+        _p(nfev, C.c_int), _p(cost), C.c_int(method),
     )
     if rc != 0:
         raise RuntimeError(f"hostsim: unsupported model {model_id}/{t1_mode}")

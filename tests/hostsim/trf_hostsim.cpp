@@ -6,7 +6,7 @@
 #include <cstring>
 #include <cmath>
 using std::exp; using std::sqrt; using std::fabs; using std::copysign; using std::nextafter;
-#include "../../pyneapple_b200/csrc/pnb_trf_core.cuh"
+#include "../../pyneapple_b200/csrc/pnb_dogbox_core.cuh"
 
 using namespace pnb;
 
@@ -21,13 +21,35 @@ static void run_one(const TrfOptions &O, int m, const double *b, const double *y
   bool yfin = true;
   for (int r = 0; r < m; r++) yfin = yfin && finite_d(y[r]);
   auto yb = [&](int r, double &yv, double &bv) { yv = y[r]; bv = b[r]; };
-  bool running = trf_begin<M>(S, O, p0v, lb, ub, 1, yfin);
   double c, g[N], A[N][N];
-  if (running) {
-    trf_evaluate<M>(S.x, O, m, yb, lb, ub, 1, c, g, A);
-    running = trf_after_first_eval<M>(S, O, c, g, A, lb, ub, 1);
+  bool running = false;
+  S.status = kStRunning;
+  if (O.method == 0) {
+    running = trf_begin<M>(S, O, p0v, lb, ub, 1, yfin);
+    if (running) {
+      trf_evaluate<M>(S.x, O, m, yb, lb, ub, 1, c, g, A);
+      running = trf_after_first_eval<M>(S, O, c, g, A, lb, ub, 1);
+    }
   }
-  while (running) {
+  DogboxLane<M> DB;
+  if (O.method == 1 && S.status == kStRunning) {
+    // the same calls, in the same order, as trf_kernel<M, BLOCK, 1>
+    running = trf_begin<M>(S, O, p0v, lb, ub, 1, yfin);
+    if (running) {
+      trf_evaluate<M>(S.x, O, m, yb, lb, ub, 1, c, g, A);
+      running = dbx_after_first_eval<M>(S, DB, O, c, g, A, lb, ub, 1);
+    }
+    while (running) {
+      if (S.need_prologue) {
+        if (!dbx_prologue<M>(S, DB, O)) break;
+        S.need_prologue = false;
+      }
+      dbx_trial<M>(S, DB, O, lb, ub, 1);
+      trf_evaluate<M>(S.x_new, O, m, yb, lb, ub, 1, c, g, A);
+      S.need_prologue = dbx_after_trial<M>(S, DB, O, c, g, A, lb, ub, 1);
+    }
+  }
+  while (running && O.method == 0) {
     if (S.need_prologue) {
       if (!trf_prologue<M>(S, O, lb, ub, 1)) break;
       S.need_prologue = false;
@@ -66,10 +88,10 @@ extern "C" int pnbh_trf_fit(int model_id, int t1_mode, double tr, double tm, int
                             long n_vox, const double *y, const double *p0, const double *lb,
                             const double *ub, const int *frozen, double ftol, double xtol, double gtol,
                             int max_nfev, int jac_mode, int x_scale_jac, const double *x_scale,
-                            double *params, double *cov, int *status, int *nfev, double *cost) {
+                            double *params, double *cov, int *status, int *nfev, double *cost, int method) {
   TrfOptions O;
   O.ftol = ftol; O.xtol = xtol; O.gtol = gtol; O.max_nfev = max_nfev; O.jac_mode = jac_mode;
-  O.x_scale_jac = x_scale_jac; O.frozen = 0; O.tr = tr; O.tm = tm;
+  O.x_scale_jac = x_scale_jac; O.frozen = 0; O.tr = tr; O.tm = tm; O.method = method;
   for (int i = 0; i < 8; i++) { O.x_scale[i] = x_scale ? x_scale[i] : 1.0; if (frozen && i < 7 && frozen[i]) O.frozen |= 1u << i; }
 #define CASE(ID, T) if (model_id == ID && t1_mode == T) { run_all<Model<ID, T>>(O, nb, b, n_vox, y, p0, lb, ub, params, cov, status, nfev, cost); return 0; }
   CASE(0, 0) CASE(1, 0) CASE(2, 0) CASE(3, 0) CASE(4, 0) CASE(5, 0) CASE(6, 0)

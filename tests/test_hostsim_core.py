@@ -9,7 +9,7 @@ from __future__ import annotations
 import numpy as np
 import pytest
 
-from _util import TRF_CASES, full_problem, rel_err
+from _util import DBX_CASES, TRF_CASES, full_problem, rel_err
 from hostsim import hostsim
 from oracle import c_oracle
 
@@ -96,3 +96,23 @@ def test_model_exp_is_within_one_ulp_of_libm():
     assert ulp.max() <= 1.0, ulp.max()
     assert np.array_equal(got[~fin], ref[~fin])
     assert np.isnan(hostsim.exp(np.array([np.nan]))[0])
+
+
+@pytest.mark.parametrize("name", sorted(DBX_CASES))
+def test_dogbox_core_matches_reference(name):
+    """pnb_dogbox_core.cuh (method = "dogbox") against the reference's outputs."""
+    kind, m = DBX_CASES[name]
+    P = full_problem(name)
+    jm = 1 if P["uses_fd"] else 0
+    r = hostsim.trf_fit(c_oracle.MODEL_IDS[(kind, m)], P["b"], P["y"], P["P0"], P["LB"], P["UB"],
+                        frozen=P["frozen"], ftol=P["tol"], max_nfev=P["max_iter"], jac_mode=jm, method=1)
+    free = [i for i in range(len(P["all_names"])) if not P["frozen"][i]]
+    par = r["params"][:, free]
+    assert ((r["status"] > 0) == P["ref_success"]).all()
+    fail = ~P["ref_success"]
+    assert np.array_equal(par[fail], P["ref_params"][fail])
+    ok = P["ref_success"]
+    if ok.any():
+        err = rel_err(par[ok], P["ref_params"][ok]).max(axis=1)
+        assert (err > 1e-4).sum() == 0, (err > 1e-4).sum()
+        assert np.median(err) < 1e-7

@@ -5,7 +5,7 @@ from __future__ import annotations
 import numpy as np
 import pytest
 
-from _util import MODEL_FIXED, TRF_CASES, full_problem, load, rel_err
+from _util import DBX_CASES, MODEL_FIXED, TRF_CASES, full_problem, load, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -44,9 +44,50 @@ def _residual_norm(model, b, y, params_by_name, fixed):
 @pytest.mark.parametrize("name", sorted(TRF_CASES))
 @pytest.mark.parametrize("jac", ["reference", "analytic"])
 def test_golden_parity(name, jac):
-    kind, mode = TRF_CASES[name]
+    _golden_parity(name, TRF_CASES, jac=jac)
+
+
+@pytest.mark.parametrize("name", sorted(DBX_CASES))
+def test_dogbox_golden_parity(name):
+    """method = "dogbox" (scipy/optimize/_lsq/dogbox.py) against the reference run with that method."""
+    _golden_parity(name, DBX_CASES, jac="reference", method="dogbox")
+
+
+def test_dogbox_large_sample_against_the_scipy_port():
+    """4 096 voxels of config C2 with method = "dogbox" vs the oracle port (same SciPy calls)."""
+    from oracle import ref_port
+    from pyneapple_b200 import synth
+
+    cfg = synth.CONFIGS["C2"]
+    b, y, _ = synth.sample_voxels(cfg, 4096, z=33)
+    names = ["f1", "D1", "D2", "S0"]
+    solver = CurveFitSolver(model=models.BiExpModel(fit_s0=True), p0=cfg.p0, bounds=cfg.bounds, max_iter=250,
+                            tol=1e-8, method="dogbox")
+    solver.fit(b, y)
+    got = np.stack([solver.params_[n] for n in names], axis=0)
+    n = y.shape[0]
+    P0, LB, UB = (np.tile(np.array(v)[:, None], (1, n)) for v in (
+        [cfg.p0[k] for k in names], [cfg.bounds[k][0] for k in names], [cfg.bounds[k][1] for k in names]))
+    ref = ref_port.curvefit_fit(ref_port.Model("biexp", "s0"), b, y, P0, LB, UB, max_iter=250, tol=1e-8,
+                                method="dogbox", n_jobs=-1)
+    assert ((solver.status_ > 0) == ref["success"]).all()
+    ok = ref["success"]
+    err = rel_err(got[:, ok], ref["params"][:, ok]).max(axis=0)
+    assert (err <= 1e-4).all(), err.max()
+    assert np.median(err) < 1e-7
+
+
+def test_unsupported_method_is_rejected():
+    solver = CurveFitSolver(model=models.MonoExpModel(), p0={"S0": 1000.0, "D": 1e-3},
+                            bounds={"S0": (1.0, 5000.0), "D": (1e-5, 0.1)}, method="lm")
+    with pytest.raises(NotImplementedError):
+        solver.fit(np.array([0.0, 100.0, 500.0]), np.array([[1000.0, 900.0, 600.0]]))
+
+
+def _golden_parity(name, cases, jac, **solver_kw):
+    kind, mode = cases[name]
     P = full_problem(name)
-    solver, model = _make_solver(name, kind, mode, P, jac=jac)
+    solver, model = _make_solver(name, kind, mode, P, jac=jac, **solver_kw)
     g = load(name)
     kwargs = {}
     if P["per_voxel"]:
