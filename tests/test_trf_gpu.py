@@ -78,7 +78,7 @@ def test_dogbox_large_sample_against_the_scipy_port():
 
 
 def test_unsupported_method_is_rejected():
-    solver = CurveFitSolver(model=models.MonoExpModel(), p0={"S0": 1000.0, "D": 1e-3},
+    solver = CurveFitSolver(model=models.MonoExpModel(), max_iter=250, tol=1e-8, p0={"S0": 1000.0, "D": 1e-3},
                             bounds={"S0": (1.0, 5000.0), "D": (1e-5, 0.1)}, method="lm")
     with pytest.raises(NotImplementedError):
         solver.fit(np.array([0.0, 100.0, 500.0]), np.array([[1000.0, 900.0, 600.0]]))
