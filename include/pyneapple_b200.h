@@ -212,6 +212,28 @@ int pnb_spectrum_peaks_device(const pnb_spectrum_problem *prob, void *cuda_strea
 int pnb_spectrum_peaks_host(const pnb_spectrum_problem *prob, int device, int64_t chunk_vox);
 int pnb_sizeof_spectrum_problem(void);
 
+/*
+ * Mean signal of every segmentation label: replaces the per-label
+ * np.mean(image[segmentation == seg], axis=0) loop of
+ * SegmentationWiseFitter._extract_segmentation_mean_signals (fitters/segmentationwise.py:112-137).
+ * `label` holds the dense index of each voxel's label (0 .. n_labels-1, the position in
+ * np.unique(segmentation)); voxels with an index outside that range are skipped.  An empty label
+ * gets NaN, like np.mean of an empty selection.  Deterministic (no floating-point atomics); the
+ * order of the additions differs from NumPy's, so the means agree to a few ulp.
+ */
+typedef struct pnb_segmeans_problem {
+  int32_t n_b;
+  int32_t n_labels;
+  int64_t n_vox;             /* all voxels of the volume, C order                 */
+  const double *image;       /* (n_vox, n_b)                                      */
+  const int32_t *label;      /* (n_vox)                                           */
+  double *means;             /* (n_labels, n_b)                                   */
+  int64_t *counts;           /* (n_labels) voxels per label, or NULL              */
+} pnb_segmeans_problem;
+
+int pnb_segment_means_device(const pnb_segmeans_problem *prob, void *cuda_stream);
+int pnb_segment_means_host(const pnb_segmeans_problem *prob, int device);
+
 /* housekeeping */
 int pnb_abi_version(void);
 /* sizeof(struct pnb_trf_problem) as compiled, for binding self-checks */

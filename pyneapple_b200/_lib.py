@@ -112,6 +112,20 @@ class SpectrumProblem(C.Structure):
     ]
 
 
+class SegmeansProblem(C.Structure):
+    """Mirror of ``struct pnb_segmeans_problem``."""
+
+    _fields_ = [
+        ("n_b", C.c_int32),
+        ("n_labels", C.c_int32),
+        ("n_vox", C.c_int64),
+        ("image", C.c_void_p),
+        ("label", C.c_void_p),
+        ("means", C.c_void_p),
+        ("counts", C.c_void_p),
+    ]
+
+
 class ResizeProblem(C.Structure):
     """Mirror of ``struct pnb_resize_problem``."""
 
@@ -172,6 +186,10 @@ def load():
     lib.pnb_spectrum_peaks_device.restype = C.c_int
     lib.pnb_spectrum_peaks_host.argtypes = [C.POINTER(SpectrumProblem), C.c_int, C.c_int64]
     lib.pnb_spectrum_peaks_host.restype = C.c_int
+    lib.pnb_segment_means_device.argtypes = [C.POINTER(SegmeansProblem), C.c_void_p]
+    lib.pnb_segment_means_device.restype = C.c_int
+    lib.pnb_segment_means_host.argtypes = [C.POINTER(SegmeansProblem), C.c_int]
+    lib.pnb_segment_means_host.restype = C.c_int
     lib.pnb_nnls_last_redo_count.argtypes = [C.c_int]
     lib.pnb_nnls_last_redo_count.restype = C.c_int64
     lib.pnb_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_int64]

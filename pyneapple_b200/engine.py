@@ -290,3 +290,50 @@ def nnls_fit(basis, reg_matrix, signal, max_iter: int, *, device: int = 0, chunk
     prob.r_squared = r2.ctypes.data
     _lib.check(lib.pnb_nnls_fit_host(C.byref(prob), int(device), int(chunk_vox)), "pnb_nnls_fit_host")
     return dict(coefficients=coef, residual=res, status=status, iterations=iters, r2=r2)
+
+
+def segment_means(image, segmentation, *, device: int = 0):
+    """Mean signal of every label of ``segmentation`` (``fitters/segmentationwise.py:112-137``).
+
+    ``image``: ``(..., n_b)`` numpy array or CUDA tensor, ``segmentation``: its spatial shape.
+    Returns ``(labels, means (n_labels, n_b), counts, inverse)``: ``labels = np.unique(segmentation)``
+    (the background label included, like the reference), ``inverse`` the dense label index of
+    every voxel (C order).  One pass over the volume on the GPU (``pnb_segment_means_*``).
+    """
+    _lib.require_device()
+    lib = _lib.load()
+    n_b = int(image.shape[-1])
+    prob = _lib.SegmeansProblem()
+    prob.n_b = n_b
+    if _is_torch_cuda(image):
+        import torch
+
+        dev = image.device
+        seg = torch.as_tensor(segmentation, device=dev)
+        labels_t, inverse = torch.unique(seg, return_inverse=True)
+        img = image.reshape(-1, n_b).contiguous().to(torch.float64)
+        lab = inverse.reshape(-1).to(torch.int32).contiguous()
+        L = int(labels_t.numel())
+        means = torch.empty((L, n_b), dtype=torch.float64, device=dev)
+        counts = torch.empty((L,), dtype=torch.int64, device=dev)
+        prob.n_labels, prob.n_vox = L, int(lab.numel())
+        prob.image, prob.label = img.data_ptr(), lab.data_ptr()
+        prob.means, prob.counts = means.data_ptr(), counts.data_ptr()
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(lib.pnb_segment_means_device(C.byref(prob), C.c_void_p(stream)), "pnb_segment_means_device")
+        return labels_t.cpu().numpy(), means, counts, inverse.reshape(-1)
+    segmentation = np.asarray(segmentation)
+    labels, inverse = np.unique(segmentation, return_inverse=True)
+    img = np.ascontiguousarray(np.asarray(image, dtype=np.float64).reshape(-1, n_b))
+    lab = np.ascontiguousarray(inverse.reshape(-1), dtype=np.int32)
+    if lab.shape[0] != img.shape[0]:
+        raise ValueError(f"segmentation has {lab.shape[0]} voxels, the image {img.shape[0]}")
+    L = int(labels.shape[0])
+    means = np.empty((L, n_b))
+    counts = np.empty(L, np.int64)
+    prob.n_labels, prob.n_vox = L, int(lab.shape[0])
+    prob.image, prob.label = img.ctypes.data, lab.ctypes.data
+    prob.means, prob.counts = means.ctypes.data, counts.ctypes.data
+    _lib.check(lib.pnb_segment_means_host(C.byref(prob), int(device)), "pnb_segment_means_host")
+    return labels, means, counts, inverse.reshape(-1)

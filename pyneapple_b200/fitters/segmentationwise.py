@@ -1,6 +1,7 @@
 """One fit per segmentation label on the label's mean signal
-(mirror of reference fitters/segmentationwise.py:19-179; a handful of fits, the
-GPU solver is used for API uniformity, not for speed)."""
+(mirror of reference fitters/segmentationwise.py:19-179).  The per-label means — one
+pass over the whole volume — are reduced on the device (``pnb_segment_means_*``); the
+handful of fits go through the GPU solver for API uniformity, not for speed."""
 
 from __future__ import annotations
 
@@ -8,6 +9,7 @@ import time
 
 import numpy as np
 
+from .. import engine
 from .. import validation as V
 from ..models import describe_model, family_forward
 from .base import BaseFitter, PixelIndices
@@ -29,8 +31,9 @@ class SegmentationWiseFitter(BaseFitter):
         if fixed_param_maps is not None:
             V.validate_fixed_param_maps(fixed_param_maps, image.shape[:-1],
                                         self.solver.model._all_param_names)
+            dev = getattr(self.solver, "device", 0)
             pixel_fixed_params = {
-                name: np.array([np.mean(vol[segmentation == seg]) for seg in self.segment_labels])
+                name: engine.segment_means(np.asarray(vol, dtype=np.float64)[..., None], segmentation, device=dev)[1][:, 0]
                 for name, vol in fixed_param_maps.items()
             }
         self.solver.fit(xdata, segs_to_fit, pixel_fixed_params=pixel_fixed_params, **fit_kwargs)
@@ -41,9 +44,8 @@ class SegmentationWiseFitter(BaseFitter):
 
     def _extract_segmentation_mean_signals(self, image, segmentation):
         # np.unique includes the background label 0, like the reference (segmentationwise.py:116)
-        labels, inverse = np.unique(segmentation, return_inverse=True)
+        labels, means, _, inverse = engine.segment_means(image, segmentation, device=getattr(self.solver, "device", 0))
         inverse = inverse.reshape(segmentation.shape)
-        means = np.array([np.mean(image[segmentation == seg], axis=0) for seg in labels])
         order = np.argsort(inverse.ravel(), kind="stable")  # voxels grouped by label, C order within
         coords = np.stack(np.unravel_index(order, segmentation.shape), axis=1)
         self.segment_labels = labels
