@@ -52,8 +52,9 @@ template <int MT, int WK> struct NnlsV3Cfg {
   static constexpr int BWK = 2 * WK + 1;       // band width the kernel is compiled for
   static constexpr int LB = (WK == 0) ? 0 : ((BWK + 1) & ~1);  // padded band row
   static constexpr int WP = (WK + 1) & ~1;     // zero padding of the coefficient vector, each side
-  static constexpr int XW = NQ + 2 * WP;       // coefficient window of one lane
-  static constexpr int NX = NR + 2 * WP;
+  static constexpr int XW = NQ + 2 * WK;       // coefficient window of one lane: bins 8l-WK .. 8l+7+WK
+  static constexpr int XR = 34;                // row stride of the coefficient scratch: column 0 / 33 stay zero
+  static constexpr int NX = NQ * XR;           // x[j] lives at (j % 8) * XR + j / 8 + 1 (lane-major, conflict-free)
   static constexpr int KC = 96;                // slots
   static constexpr int KB = PNB_V3_KB;         // rows of H in the warp's own shared memory
   static constexpr int K1 = PNB_V3_K1;         // rows KB .. K1-1: tier-1 extension, K1 .. KC-1: tier 2
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
   double *pool1 = gdiag + NR + 2;                      // n_e1 areas of T1 doubles (rows KB .. K1-1)
   double *pool2 = pool1 + (size_t)n_e1 * C::T1;        // n_e2 areas of T2 doubles (rows K1 .. KC-1)
   double *wbase = pool2 + (size_t)n_e2 * C::T2 + (size_t)wid * C::PER_WARP;
-  double *xs_raw = wbase;                  // NX, x[j] at xs_raw[j + WP]
+  double *xs_raw = wbase;                  // NX, x[j] at xs_raw[xpos(j)]
   double *gsm = xs_raw + C::NX;            // KC
   double *usm = gsm + KC;                  // KC
   double *zs = usm + KC;                   // KC
@@ -93,7 +94,7 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
   int *ro = reinterpret_cast<int *>(rs + MT);  // KC: offset of the slot's dictionary row in Bt
   int *Pb = ro + KC;                           // KC: bin of the slot
   double *Hb = rs + MT + KC;               // packed rows 0 .. KB-1
-  double *xs = xs_raw + WP;
+  auto xpos = [](int j) -> int { return (j & 7) * C::XR + (j >> 3) + 1; };
 
   for (int i = threadIdx.x; i < NR * LD; i += nthreads) {
     const int row = i / LD, b = i - row * LD;
@@ -115,6 +116,30 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
     double acc = (j < n) ? a.rtr[(size_t)j * (2 * W + 1) + W] : 0.0;
     for (int b = 0; b < MT; b++) acc += Bt[row * LD + b] * Bt[row * LD + b];
     gdiag[j] = acc;
+  }
+  // interior rows of mu^2 R^T R are identical for every regularisation order of the reference
+  // (model_functions/nnls.py:46-85): their 2 WK + 1 weights live in registers, only the first and
+  // last W bins read their own row (12 % of all shared-memory wavefronts went into those rows)
+  double wt[C::BWK];
+  unsigned bmask = 0xffu;
+  if (LB > 0) {
+    const int jmid = n / 2, rmid = (jmid & 7) * 32 + (jmid >> 3);
+    bool same = true;
+    for (int j = W + threadIdx.x; j < n - W; j += nthreads) {
+      const int row = (j & 7) * 32 + (j >> 3);
+      for (int t = 0; t < C::BWK; t++) same = same && (rtrs[row * LB + t] == rtrs[rmid * LB + t]);
+    }
+    const bool toep = __syncthreads_and(same) && n > 2 * W + 1;
+#pragma unroll
+    for (int t = 0; t < C::BWK; t++) wt[t] = rtrs[rmid * LB + t];
+    if (toep) {
+      bmask = 0;
+#pragma unroll
+      for (int q = 0; q < NQ; q++) {
+        const int j = NQ * lane + q;
+        if (j < W || j >= n - W) bmask |= 1u << q;
+      }
+    }
   }
   for (int i = lane; i < C::NX; i += 32) xs_raw[i] = 0.0;
   for (int i = lane; i < KC; i += 32) zs[i] = 0.0;
@@ -165,9 +190,12 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
       double acc = 0.0;
       if (LB > 0) {
         const double *rp = rtrs + row * LB;
-        const double *xp = xs + (j - WK);
 #pragma unroll
-        for (int t = 0; t < C::BWK; t++) acc += rp[t] * xp[t];
+        for (int t = 0; t < C::BWK; t++) {
+          int jj = j - WK + t;  // taps outside [0, NR) carry a zero weight: any valid address will do
+          jj = jj < 0 ? 0 : (jj >= NR ? NR - 1 : jj);
+          acc += rp[t] * xs_raw[xpos(jj)];
+        }
       }
       return acc;
     };
@@ -212,9 +240,14 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
       if (do_dual) {
         double xw[C::XW > 0 ? C::XW : 1];
         if (LB > 0) {
-          const double2 *xp = reinterpret_cast<const double2 *>(xs_raw + NQ * lane);
+          // x[8 lane - WK .. 8 lane + 7 + WK]: own bins from the lane's column, the halo from the neighbours'
 #pragma unroll
-          for (int t = 0; t < C::XW / 2; t++) { const double2 v = xp[t]; xw[2 * t] = v.x; xw[2 * t + 1] = v.y; }
+          for (int t = 0; t < C::XW; t++) {
+            const int qq = t - WK;  // bin offset relative to 8 lane
+            const int q8 = qq < 0 ? qq + NQ : (qq >= NQ ? qq - NQ : qq);
+            const int dl = qq < 0 ? -1 : (qq >= NQ ? 1 : 0);
+            xw[t] = xs_raw[q8 * C::XR + lane + 1 + dl];
+          }
         }
         const unsigned skip = inP | rej;
 #pragma unroll
@@ -222,13 +255,22 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
           const int row = q * 32 + lane;
           double acc = col_dot(row, rr);
           if (LB > 0) {
-            const double2 *rp = reinterpret_cast<const double2 *>(rtrs + row * LB);
             double b0 = 0.0, b1 = 0.0;
+            if ((bmask >> q) & 1u) {
+              // first / last W bins (or a regulariser that is not Toeplitz): the row from shared memory
+              const double2 *rp = reinterpret_cast<const double2 *>(rtrs + row * LB);
 #pragma unroll
-            for (int t = 0; t < LB / 2; t++) {
-              const double2 v = rp[t];
-              b0 += v.x * xw[q + WP - WK + 2 * t];
-              if (2 * t + 1 < C::BWK) b1 += v.y * xw[q + WP - WK + 2 * t + 1];
+              for (int t = 0; t < LB / 2; t++) {
+                const double2 v = rp[t];
+                b0 += v.x * xw[q + 2 * t];
+                if (2 * t + 1 < C::BWK) b1 += v.y * xw[q + 2 * t + 1];
+              }
+            } else {
+#pragma unroll
+              for (int t = 0; t < C::BWK; t += 2) {
+                b0 += wt[t] * xw[q + t];
+                if (t + 1 < C::BWK) b1 += wt[t + 1] * xw[q + t + 1];
+              }
             }
             acc -= b0 + b1;
           }
@@ -359,7 +401,7 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
         // active-set decisions were being made; wrong results only appeared above 3e-4
         if ((pass == 0 && rel > 5e-5) || !pos) { mode = kNnlsRedo; break; }
 #pragma unroll 1
-        for (int i = lane; i < k; i += 32) { const double z = zs[i] + usm[i]; zs[i] = z; xs[Pb[i]] = z; }
+        for (int i = lane; i < k; i += 32) { const double z = zs[i] + usm[i]; zs[i] = z; xs_raw[xpos(Pb[i])] = z; }
         __syncwarp();
         pass += 1;
         if (rel < 1e-13 || pass == 4) {
@@ -436,7 +478,7 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
             const double dq = Hrow(q)[q], zq = zs[q];
 #pragma unroll 1
             for (int i = lane; i < k; i += 32) usm[i] = (i >= q) ? Hrow(i)[q] : Hrow(q)[i];
-            if (lane == 0) xs[idx] = 0.0;
+            if (lane == 0) xs_raw[xpos(idx)] = 0.0;
             const double dinv = 1.0 / dq;
             scale = -dinv;
             zfac = zq * dinv;
@@ -528,7 +570,7 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
             int bad = KC;
 #pragma unroll 1
             for (int i = lane; i < k; i += 32)
-              if (xs[Pb[i]] <= 0.0 && i < bad) bad = i;
+              if (xs_raw[xpos(Pb[i])] <= 0.0 && i < bad) bad = i;
             bad = __reduce_min_sync(FULL, bad);
             if (bad < KC) { q = bad; continue; }
           }
@@ -545,7 +587,7 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
           for (int i = lane; i < k; i += 32) {
             const double z = zs[i];
             if (z <= 0.0) {
-              const double xv = xs[Pb[i]];
+              const double xv = xs_raw[xpos(Pb[i])];
               const double t = -xv / (z - xv);
               if (alpha > t) { alpha = t; jj = i; }
             }
@@ -558,8 +600,8 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
           }
 #pragma unroll 1
           for (int i = lane; i < k; i += 32) {
-            const int p = Pb[i];
-            xs[p] += alpha * (zs[i] - xs[p]);
+            const int p = xpos(Pb[i]);
+            xs_raw[p] += alpha * (zs[i] - xs_raw[p]);
           }
           __syncwarp();
           q = jj;
@@ -567,7 +609,7 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
       }
       if (mode != 1) break;
 #pragma unroll 1
-      for (int i = lane; i < k; i += 32) xs[Pb[i]] = zs[i];
+      for (int i = lane; i < k; i += 32) xs_raw[xpos(Pb[i])] = zs[i];
       __syncwarp();
     }
 
@@ -580,7 +622,7 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
         for (int b = 0; b < MT; b++) ss += rs[b] * rs[b];
 #pragma unroll 2
         for (int jx = lane; jx < n; jx += 32) {
-          const double xj = xs[jx];
+          const double xj = xs_raw[xpos(jx)];
           out[jx] = xj;
           if (xj != 0.0) part += xj * band_at((jx & 7) * 32 + (jx >> 3), jx);
         }
@@ -607,7 +649,7 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
     // leave the scratch clean for the next voxel: x = 0, z = 0, rows < k of H = 0
     __syncwarp();
 #pragma unroll 1
-    for (int i = lane; i < k; i += 32) { xs[Pb[i]] = 0.0; zs[i] = 0.0; }
+    for (int i = lane; i < k; i += 32) { xs_raw[xpos(Pb[i])] = 0.0; zs[i] = 0.0; }
     {
       const int kb = k < KB ? k : KB;
       const int nb = (kb * (kb + 1)) / 2;
