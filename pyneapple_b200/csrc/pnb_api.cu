@@ -3,6 +3,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -49,7 +50,9 @@ bool is_pageable(const void *ptr) {
 
 void parallel_memcpy(void *dst, const void *src, size_t bytes) {
   static const unsigned hw = std::thread::hardware_concurrency();
-  unsigned nt = hw > 8 ? 8 : (hw ? hw : 1);
+  // PNB_COPY_THREADS overrides the default of min(16, cores) host threads per staging copy
+  static const unsigned want = [] { const char *e = std::getenv("PNB_COPY_THREADS"); return e ? (unsigned)std::atoi(e) : 0u; }();
+  unsigned nt = want ? want : (hw > 16 ? 16 : (hw ? hw : 1));
   if (bytes < (4u << 20) || nt < 2) { std::memcpy(dst, src, bytes); return; }
   const size_t part = ((bytes / nt) + 4095) & ~(size_t)4095;
   std::vector<std::thread> th;

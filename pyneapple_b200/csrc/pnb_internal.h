@@ -11,7 +11,7 @@ void count_launch();
 // true for ordinary (pageable) host memory: cudaMemcpyAsync on it is staged by the driver at a
 // fraction of PCIe speed and blocks the host, so the host pipelines stage it themselves
 bool is_pageable(const void *ptr);
-// memcpy split over a few host threads (one thread does ~10 GB/s, PCIe 5 x16 moves ~55 GB/s)
+// memcpy split over up to 16 host threads (one thread does ~10 GB/s, PCIe 5 x16 moves ~55 GB/s)
 void parallel_memcpy(void *dst, const void *src, size_t bytes);
 }  // namespace pnbi
 
