@@ -127,6 +127,14 @@ def nnls_algorithmic_flops(m, n_bins, w, iters, k_final):
     return float(np.sum(2 * m * n_bins + n_outer * per_outer + iters * per_inner))
 
 
+def _traffic(name):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/), or None."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", name))).get("dram_bytes_per_launch")
+    except (OSError, ValueError):
+        return None
+
+
 def bench_nnls(args, world, rank, local_rank, dev):
     """250-bin NNLS half of the metric: config C3 (d_range [0.0008, 0.5], reg_order 2, mu 0.02)."""
     import torch
@@ -202,9 +210,12 @@ def bench_nnls(args, world, rank, local_rank, dev):
         "roofline": {"bound": "fp64", "kernel": "nnls_v3_kernel<16,2> (+ nnls_kernel<2> for the voxels it hands over)", "achieved": flops / (kernel_ms * 1e-3) / 1e12,
                      "peak": fp64_peak, "unit": "TFLOP/s", "frac": flops / (kernel_ms * 1e-3) / 1e12 / fp64_peak,
                      "flops_per_launch": flops, "flop_model": "SURVEY.md §8(d) K4, from device iteration counters",
-                     "kernel_ms": kernel_ms, "traffic": None,
+                     "kernel_ms": kernel_ms, "traffic": _traffic("nnls_traffic.json"),
                      "hbm": {"achieved": alg_bytes / (kernel_ms * 1e-3) / 1e9, "unit": "GB/s",
-                             "algorithmic_bytes_per_launch": alg_bytes}},
+                             "algorithmic_bytes_per_launch": alg_bytes},
+                     "shared_memory": "the fast kernel moves 0.80 shared-memory wavefronts per clock and SM (1.0 = "
+                                      "the pipe's limit; profiles/r1_final_summary.md): half of them are the "
+                                      "dictionary columns of the dual pass"},
     }
     if not args.no_cpu_baseline:
         from oracle import ref_port
@@ -446,13 +457,7 @@ def main():
     alg_bytes = n_vox * (8 * n_b + 8 * 4 + 8 * 16 + 4 + 4 + 4 + 8 + 8)
     achieved_tf = flops / (kernel_ms * 1e-3) / 1e12
     achieved_gbs = alg_bytes / (kernel_ms * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "trf_traffic.json")
-    if os.path.exists(tpath):
-        try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
-        except ValueError:
-            traffic = None
+    traffic = _traffic("trf_traffic.json")
     roofline = {
         "bound": "fp64", "kernel": "trf_kernel<Model<BiS0>,128>", "achieved": achieved_tf, "peak": fp64_peak,
         "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak,
