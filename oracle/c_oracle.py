@@ -41,7 +41,7 @@ def _p(a, t=C.c_double):
 
 
 def trf_fit(model_id, b, y, p0, lb, ub, frozen=None, t1_mode=0, tr=0.0, tm=0.0, ftol=1e-8,
-            xtol=1e-8, gtol=1e-8, max_nfev=250, jac_mode=1, x_scale_jac=False, x_scale=None):
+            xtol=1e-8, gtol=1e-8, max_nfev=250, jac_mode=1, x_scale_jac=False, x_scale=None, method="trf"):
     """p0/lb/ub: (n_vox, n_all) row-major over the FULL parameter list."""
     b = np.ascontiguousarray(b, np.float64)
     y = np.ascontiguousarray(np.atleast_2d(y), np.float64)
@@ -58,8 +58,8 @@ def trf_fit(model_id, b, y, p0, lb, ub, frozen=None, t1_mode=0, tr=0.0, tm=0.0, 
     nfev = np.empty(n_vox, np.int32)
     cost = np.empty(n_vox)
     xs = None if x_scale is None else np.ascontiguousarray(x_scale, np.float64)
-    rc = lib().pnbo_trf_fit(
-        C.c_int(model_id), C.c_int(t1_mode), C.c_double(tr), C.c_double(tm), C.c_int(nb), _p(b),
+    rc = lib().pnbo_lsq_fit(
+        C.c_int({"trf": 0, "dogbox": 1}[method]), C.c_int(model_id), C.c_int(t1_mode), C.c_double(tr), C.c_double(tm), C.c_int(nb), _p(b),
         C.c_long(n_vox), _p(y), _p(p0), _p(lb), _p(ub), _p(fr, C.c_int), C.c_double(ftol),
         C.c_double(xtol), C.c_double(gtol), C.c_int(max_nfev), C.c_int(jac_mode),
         C.c_int(int(x_scale_jac)), None if xs is None else _p(xs), _p(params), _p(cov),

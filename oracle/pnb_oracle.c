@@ -20,6 +20,9 @@
  *                     scipy/optimize/_numdiff.py       2-point differences
  *                        (_compute_absolute_step, _adjust_scheme_to_bounds)
  *                     called from solvers/curvefit.py:295-306
+ *   pnbo_lsq_fit(method = 1)
+ *                  <- scipy/optimize/_lsq/dogbox.py     dogbox, dogleg_step,
+ *                        find_intersection (method = "dogbox" of the same call)
  *   pnbo_nnls      <- Lawson & Hanson, "Solving Least Squares Problems",
  *                     ch. 23 algorithm NNLS (what scipy.optimize.nnls wraps),
  *                     called from solvers/nnls_solver.py:195-197
@@ -595,6 +598,185 @@ static int trf_one(prob_t *P, const trf_opts *O, const double *x0, double *x, do
   return status;
 }
 
+/* ------------------------------------------------------------------ */
+/* method='dogbox': scipy/optimize/_lsq/dogbox.py (dogbox, dogleg_step, */
+/* find_intersection), tr_solver='exact', loss='linear' — reached by     */
+/* solvers/curvefit.py:295-306 when the TOML sets method = "dogbox".     */
+/* J is kept explicitly here; lstsq(J_free, -f, rcond=-1) through the    */
+/* one-sided Jacobi SVD (singular values <= eps * s_max are dropped).    */
+/* ------------------------------------------------------------------ */
+static double step_size_to_bound_hits(int n, const double *x, const double *s, const double *lb,
+                                      const double *ub, int *hits) {
+  double steps[MAXN], mn = INFINITY;
+  for (int i = 0; i < n; i++) {
+    steps[i] = INFINITY;
+    if (s[i] != 0) steps[i] = fmax((lb[i] - x[i]) / s[i], (ub[i] - x[i]) / s[i]);
+    if (steps[i] < mn) mn = steps[i];
+  }
+  for (int i = 0; i < n; i++) hits[i] = (steps[i] == mn) ? ((s[i] > 0) - (s[i] < 0)) : 0;
+  return mn;
+}
+
+static int dogbox_one(prob_t *P, const trf_opts *O, const double *x0, double *x, double *cov,
+                      int *nfev_out, int *njev_out, double *cost_out, double *opt_out) {
+  int n = P->n, m = P->nb;
+  const double *lb = P->lb, *ub = P->ub;
+  *nfev_out = 0; *njev_out = 0; *cost_out = NAN; *opt_out = NAN;
+  for (int i = 0; i < m; i++) if (!isfinite(P->y[i])) return -3;
+  for (int i = 0; i < n; i++) if (!(lb[i] < ub[i])) return -1;
+  if (!in_bounds(n, x0, lb, ub)) return -2;
+  memcpy(x, x0, sizeof(double) * n); /* no make_strictly_feasible for dogbox (least_squares.py) */
+
+  double f[MAXM], f_new[MAXM], J[MAXM * MAXN], g[MAXN];
+  prob_fun(P, x, f);
+  for (int i = 0; i < m; i++) if (!isfinite(f[i])) return -4;
+  prob_jac(P, x, f, J);
+  int nfev = 1, njev = 1;
+  double cost = 0.5 * vdot(m, f, f);
+  for (int k = 0; k < n; k++) { double t = 0; for (int i = 0; i < m; i++) t += J[i * n + k] * f[i]; g[k] = t; }
+  double scale[MAXN], scale_inv[MAXN];
+  if (O->x_scale_jac) {
+    for (int k = 0; k < n; k++) {
+      double t = 0; for (int i = 0; i < m; i++) t += J[i * n + k] * J[i * n + k];
+      scale_inv[k] = sqrt(t); if (scale_inv[k] == 0) scale_inv[k] = 1; scale[k] = 1 / scale_inv[k];
+    }
+  } else for (int k = 0; k < n; k++) { scale[k] = O->x_scale[k]; scale_inv[k] = 1 / scale[k]; }
+  double Delta = 0;
+  for (int k = 0; k < n; k++) Delta = fmax(Delta, fabs(x0[k] * scale_inv[k]));
+  if (Delta == 0) Delta = 1.0;
+  int on_bound[MAXN];
+  for (int k = 0; k < n; k++) { on_bound[k] = 0; if (x0[k] == lb[k]) on_bound[k] = -1; if (x0[k] == ub[k]) on_bound[k] = 1; }
+  int status = -99;
+  double g_norm = 0;
+
+  for (;;) {
+    int fr[MAXN], nf = 0; /* free_set: indices of the free variables */
+    g_norm = 0;
+    for (int k = 0; k < n; k++) {
+      int active = on_bound[k] * g[k] < 0;
+      if (!active) { fr[nf++] = k; g_norm = fmax(g_norm, fabs(g[k])); }
+    }
+    if (g_norm < O->gtol) status = 1;
+    if (status != -99 || nfev == O->max_nfev) break;
+    double Jf[MAXM * MAXN], gf[MAXN], xf[MAXN], lf[MAXN], uf_[MAXN], sf[MAXN];
+    for (int a = 0; a < nf; a++) {
+      gf[a] = g[fr[a]]; xf[a] = x[fr[a]]; lf[a] = lb[fr[a]]; uf_[a] = ub[fr[a]]; sf[a] = scale[fr[a]];
+      for (int i = 0; i < m; i++) Jf[i * nf + a] = J[i * n + fr[a]];
+    }
+    /* newton_step = lstsq(J_free, -f, rcond=-1)[0] */
+    double newton[MAXN];
+    {
+      double A[MAXM * MAXN], s[MAXN], V[MAXN * MAXN];
+      memcpy(A, Jf, sizeof(double) * m * nf);
+      jacobi_svd(m, nf, A, s, V);
+      double coef[MAXN];
+      for (int k = 0; k < nf; k++) {
+        double t = 0;
+        for (int i = 0; i < m; i++) t += A[i * nf + k] * (-f[i]); /* (U s)^T b */
+        coef[k] = (nf > 0 && s[k] > EPS * s[0]) ? t / (s[k] * s[k]) : 0.0;
+      }
+      for (int a = 0; a < nf; a++) { double t = 0; for (int k = 0; k < nf; k++) t += V[a * nf + k] * coef[k]; newton[a] = t; }
+    }
+    /* a, b = build_quadratic_1d(J_free, g_free, -g_free) */
+    double qa = 0, qb = 0;
+    for (int i = 0; i < m; i++) { double t = 0; for (int a = 0; a < nf; a++) t += Jf[i * nf + a] * (-gf[a]); qa += t * t; }
+    qa *= 0.5;
+    for (int a = 0; a < nf; a++) qb += gf[a] * (-gf[a]);
+
+    double actual_reduction = -1, cost_new = cost, x_new[MAXN], step[MAXN];
+    int on_free[MAXN];
+    while (actual_reduction <= 0 && nfev < O->max_nfev) {
+      /* dogleg_step */
+      double lbt[MAXN], ubt[MAXN], sfree[MAXN];
+      int orig_l[MAXN], orig_u[MAXN], tr_l[MAXN], tr_u[MAXN], tr_hit = 0, inside = 1;
+      for (int a = 0; a < nf; a++) {
+        double trb = Delta * sf[a], lc = lf[a] - xf[a], uc = uf_[a] - xf[a];
+        lbt[a] = fmax(lc, -trb); ubt[a] = fmin(uc, trb);
+        orig_l[a] = lbt[a] == lc; orig_u[a] = ubt[a] == uc; tr_l[a] = lbt[a] == -trb; tr_u[a] = ubt[a] == trb;
+        on_free[a] = 0;
+        if (!(newton[a] >= lbt[a] && newton[a] <= ubt[a])) inside = 0;
+      }
+      if (inside) {
+        memcpy(sfree, newton, sizeof(double) * nf);
+      } else {
+        double zero[MAXN] = {0}, ng[MAXN], cauchy[MAXN], diff[MAXN], yv;
+        int hits[MAXN];
+        for (int a = 0; a < nf; a++) ng[a] = -gf[a];
+        double to_bounds = step_size_to_bound_hits(nf, zero, ng, lbt, ubt, hits);
+        double t = minimize_quadratic_1d(qa, qb, 0.0, to_bounds, 0.0, &yv);
+        for (int a = 0; a < nf; a++) { cauchy[a] = -t * gf[a]; diff[a] = newton[a] - cauchy[a]; }
+        double step_size = step_size_to_bound_hits(nf, cauchy, diff, lbt, ubt, hits);
+        for (int a = 0; a < nf; a++) {
+          if (hits[a] < 0 && orig_l[a]) on_free[a] = -1;
+          if (hits[a] > 0 && orig_u[a]) on_free[a] = 1;
+          if ((hits[a] < 0 && tr_l[a]) || (hits[a] > 0 && tr_u[a])) tr_hit = 1;
+          sfree[a] = cauchy[a] + step_size * diff[a];
+        }
+      }
+      for (int k = 0; k < n; k++) step[k] = 0;
+      for (int a = 0; a < nf; a++) step[fr[a]] = sfree[a];
+      /* predicted_reduction = -evaluate_quadratic(J_free, g_free, step_free) */
+      double q = 0, l = 0;
+      for (int i = 0; i < m; i++) { double t = 0; for (int a = 0; a < nf; a++) t += Jf[i * nf + a] * sfree[a]; q += t * t; }
+      for (int a = 0; a < nf; a++) l += sfree[a] * gf[a];
+      double predicted = -(0.5 * q + l);
+      for (int k = 0; k < n; k++) x_new[k] = fmin(fmax(x[k] + step[k], lb[k]), ub[k]);
+      prob_fun(P, x_new, f_new);
+      nfev++;
+      double step_h_norm = 0;
+      for (int k = 0; k < n; k++) step_h_norm = fmax(step_h_norm, fabs(step[k] * scale_inv[k]));
+      int finite = 1;
+      for (int i = 0; i < m; i++) if (!isfinite(f_new[i])) finite = 0;
+      if (!finite) { Delta = 0.25 * step_h_norm; continue; }
+      cost_new = 0.5 * vdot(m, f_new, f_new);
+      actual_reduction = cost - cost_new;
+      double ratio;
+      if (predicted > 0) ratio = actual_reduction / predicted;
+      else if (predicted == 0 && actual_reduction == 0) ratio = 1;
+      else ratio = 0;
+      if (ratio < 0.25) Delta = 0.25 * step_h_norm;
+      else if (ratio > 0.75 && tr_hit) Delta *= 2.0;
+      double step_norm = vnorm(n, step), x_norm = vnorm(n, x);
+      int ft = (actual_reduction < O->ftol * cost) && ratio > 0.25;
+      int xt = step_norm < O->xtol * (O->xtol + x_norm);
+      if (ft && xt) status = 4; else if (ft) status = 2; else if (xt) status = 3;
+      if (status != -99) break;
+    }
+    if (actual_reduction > 0) {
+      for (int a = 0; a < nf; a++) on_bound[fr[a]] = on_free[a];
+      memcpy(x, x_new, sizeof(double) * n);
+      for (int k = 0; k < n; k++) { if (on_bound[k] == -1) x[k] = lb[k]; if (on_bound[k] == 1) x[k] = ub[k]; }
+      memcpy(f, f_new, sizeof(double) * m);
+      cost = cost_new;
+      prob_jac(P, x, f, J);
+      njev++;
+      for (int k = 0; k < n; k++) { double t = 0; for (int i = 0; i < m; i++) t += J[i * n + k] * f[i]; g[k] = t; }
+      if (O->x_scale_jac)
+        for (int k = 0; k < n; k++) {
+          double t = 0; for (int i = 0; i < m; i++) t += J[i * n + k] * J[i * n + k];
+          scale_inv[k] = fmax(sqrt(t), scale_inv[k]); scale[k] = 1 / scale_inv[k];
+        }
+    }
+  }
+  if (status == -99) status = 0;
+  *nfev_out = nfev; *njev_out = njev; *cost_out = cost; *opt_out = g_norm;
+  {
+    double Jc[MAXM * MAXN], s[MAXN], V[MAXN * MAXN];
+    memcpy(Jc, J, sizeof(double) * m * n);
+    jacobi_svd(m, n, Jc, s, V);
+    double thr = EPS * (m > n ? m : n) * s[0];
+    for (int i = 0; i < n; i++)
+      for (int j = 0; j < n; j++) {
+        double t = 0;
+        for (int k = 0; k < n; k++) if (s[k] > thr) t += V[i * n + k] * V[j * n + k] / (s[k] * s[k]);
+        cov[i * n + j] = t;
+      }
+    if (m > n) { double s_sq = 2 * cost / (m - n); for (int i = 0; i < n * n; i++) cov[i] *= s_sq; }
+    else for (int i = 0; i < n * n; i++) cov[i] = INFINITY;
+  }
+  return status;
+}
+
 /*
  * Batch entry point.  Layouts: y (n_vox, nb) row-major; p0/lb/ub (n_vox, n_all)
  * row-major over the model's FULL parameter list (entries of frozen parameters
@@ -603,7 +785,7 @@ static int trf_one(prob_t *P, const trf_opts *O, const double *x0, double *x, do
  * (n_vox, n_free, n_free), status, nfev, cost.  On failure (status <= 0)
  * params = p0 and cov = NaN, as solvers/curvefit.py:308-317 does.
  */
-int pnbo_trf_fit(int model_id, int t1_mode, double tr, double tm, int nb, const double *b,
+int pnbo_lsq_fit(int method, int model_id, int t1_mode, double tr, double tm, int nb, const double *b,
                  long n_vox, const double *y, const double *p0, const double *lb, const double *ub,
                  const int *frozen, double ftol, double xtol, double gtol, int max_nfev,
                  int jac_mode, int x_scale_jac, const double *x_scale, double *params, double *cov,
@@ -628,7 +810,8 @@ int pnbo_trf_fit(int model_id, int t1_mode, double tr, double tm, int nb, const 
     }
     P.lb = l; P.ub = u;
     int nf, nj; double cs, op;
-    int st = trf_one(&P, &O, x0, x, c, &nf, &nj, &cs, &op);
+    int st = method == 1 ? dogbox_one(&P, &O, x0, x, c, &nf, &nj, &cs, &op)
+                         : trf_one(&P, &O, x0, x, c, &nf, &nj, &cs, &op);
     status[vx] = st; nfev[vx] = nf; cost[vx] = cs;
     for (int k = 0; k < na; k++) params[vx * na + k] = p0[vx * na + k];
     if (st > 0) {
@@ -638,6 +821,16 @@ int pnbo_trf_fit(int model_id, int t1_mode, double tr, double tm, int nb, const 
       for (int k = 0; k < n * n; k++) cov[vx * n * n + k] = NAN;
   }
   return 0;
+}
+
+/* method = 'trf' (the historical entry point) */
+int pnbo_trf_fit(int model_id, int t1_mode, double tr, double tm, int nb, const double *b,
+                 long n_vox, const double *y, const double *p0, const double *lb, const double *ub,
+                 const int *frozen, double ftol, double xtol, double gtol, int max_nfev,
+                 int jac_mode, int x_scale_jac, const double *x_scale, double *params, double *cov,
+                 int *status, int *nfev, double *cost) {
+  return pnbo_lsq_fit(0, model_id, t1_mode, tr, tm, nb, b, n_vox, y, p0, lb, ub, frozen, ftol, xtol, gtol,
+                      max_nfev, jac_mode, x_scale_jac, x_scale, params, cov, status, nfev, cost);
 }
 
 /* ------------------------------------------------------------------ */
