@@ -86,6 +86,44 @@ def test_c3_nnls_full_volume_kuhn_tucker():
     assert (np.abs(w / scale)[x[sub] > 0] <= 1e-10).all()
     r_host = np.sqrt(((y[sub] - x[sub] @ B.T) ** 2).sum(axis=1) + ((x[sub] @ R.T) ** 2).sum(axis=1))
     assert np.abs(r_host - res[sub]).max() < 1e-8
+    # the (very few) voxels reported as failed fail in SciPy too: same iteration-cap rule
+    from oracle import ref_port
+
+    bad = np.where(~ok)[0][:8]
+    if bad.size:
+        assert not ref_port.nnls_fit(b, y[bad], (0.0008, 0.5), 250, 2, 0.02, 250)["success"].any()
+    # spectrum post-processing of the whole volume (8f N4): fractions sum to one, positions are bins
+    from pyneapple_b200 import spectrum
+
+    cut = [(0.0008, 0.003), (0.003, 0.05), (0.05, 0.5)]
+    pk = spectrum.find_spectrum_peaks_batch(x, model.bins, 0.1, True, cutoffs=cut, max_peaks=8)
+    has = pk["n_peaks"] > 0
+    assert has.mean() > 0.999 and pk["n_peaks"].max() <= 8
+    assert np.abs(np.nansum(pk["f_values"][has], axis=1) - 1).max() < 1e-12
+    assert np.isin(pk["d_values"][has][:, 0], model.bins).all()
+    assert np.abs(np.nansum(pk["f_cut"][has], axis=1) - 1).max() < 1e-12
+    sub = np.arange(0, y.shape[0], 40009)
+    ref = ref_port.spectrum_peaks(x[sub], model.bins, 0.1, True, cut, 8)
+    assert np.array_equal(ref["n_peaks"], pk["n_peaks"][sub])
+    np.testing.assert_allclose(pk["f_values"][sub], ref["f_values"], rtol=1e-12, equal_nan=True)
+
+
+def test_c2_dogbox_full_volume_agrees_with_trf():
+    """method = "dogbox" on the whole C2 volume: a different path to the same minimiser."""
+    cfg = synth.CONFIGS["C2"]
+    b, img, _ = synth.make_volume(cfg)
+    y = img.reshape(-1, 16)
+    names = ["f1", "D1", "D2", "S0"]
+    kw = dict(p0=cfg.p0, bounds=cfg.bounds, want_cov=False, **cfg.solver_kwargs)
+    t = CurveFitSolver(models.BiExpModel(fit_s0=True), **kw).fit(b, y)
+    d = CurveFitSolver(models.BiExpModel(fit_s0=True), method="dogbox", **kw).fit(b, y)
+    assert (d.status_ > 0).all() and d.nfev_.max() <= 60
+    _bounds_ok(d, cfg, names)
+    # both stop on ftol = 1e-8: the costs agree to that order, the parameters to its square root
+    assert np.abs(d.cost_ / t.cost_ - 1).max() < 1e-6
+    for n in names:
+        assert np.median(np.abs(d.params_[n] / t.params_[n] - 1)) < 1e-6, n
+        assert np.quantile(np.abs(d.params_[n] / t.params_[n] - 1), 0.999) < 1e-3, n
 
 
 def test_c4_ideal_full_volume():
