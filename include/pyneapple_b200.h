@@ -245,6 +245,14 @@ int64_t pnb_launch_count(void);
 /* pinned host memory for callers that want full-speed transfers */
 int pnb_host_alloc(void **ptr, int64_t bytes);
 int pnb_host_free(void *ptr);
+/* Synchronous copies between device memory and host memory of any kind.  Pageable host memory —
+ * the numpy arrays the reference's fitters hold (fitters/base.py:280-330) — is staged in 32 MB
+ * pieces through two page-locked blocks with multi-threaded host copies (~5x cudaMemcpy on such
+ * memory); page-locked memory is copied directly.  `after_stream`: the stream whose work produces
+ * dev_src (synchronised first); `then_stream`: unused ordering hint, the call returns when the data
+ * is on the device. */
+int pnb_download(void *host_dst, const void *dev_src, int64_t bytes, void *after_stream);
+int pnb_upload(void *dev_dst, const void *host_src, int64_t bytes, void *then_stream);
 /* FP64 FMA micro-benchmark: achieved TFLOP/s of dependent-chain-free DFMA (roofline denominator) */
 int pnb_measure_fp64_peak(int device, double *tflops);
 

@@ -194,6 +194,10 @@ def load():
     lib.pnb_nnls_last_redo_count.restype = C.c_int64
     lib.pnb_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_int64]
     lib.pnb_host_free.argtypes = [C.c_void_p]
+    lib.pnb_download.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.pnb_download.restype = C.c_int
+    lib.pnb_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.pnb_upload.restype = C.c_int
     lib.pnb_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     _lib = lib
     return lib

@@ -337,3 +337,42 @@ def segment_means(image, segmentation, *, device: int = 0):
     prob.means, prob.counts = means.ctypes.data, counts.ctypes.data
     _lib.check(lib.pnb_segment_means_host(C.byref(prob), int(device)), "pnb_segment_means_host")
     return labels, means, counts, inverse.reshape(-1)
+
+
+_TORCH_NP = None
+
+
+def to_host(tensor) -> np.ndarray:
+    """CUDA tensor -> fresh numpy array through ``pnb_download`` (staged, multi-threaded: about five
+    times ``tensor.cpu()`` for the pageable memory numpy allocates)."""
+    import torch
+
+    global _TORCH_NP
+    if _TORCH_NP is None:
+        _TORCH_NP = {torch.float64: np.float64, torch.float32: np.float32, torch.int32: np.int32,
+                     torch.int64: np.int64, torch.bool: np.bool_, torch.uint8: np.uint8}
+    if not _is_torch_cuda(tensor):
+        return np.asarray(tensor)
+    if tensor.dtype not in _TORCH_NP or tensor.numel() * tensor.element_size() < (1 << 20):
+        return tensor.cpu().numpy()
+    t = tensor.contiguous()
+    out = np.empty(tuple(t.shape), dtype=_TORCH_NP[t.dtype])
+    with torch.cuda.device(t.device):
+        stream = torch.cuda.current_stream(t.device).cuda_stream
+        _lib.check(_lib.load().pnb_download(out.ctypes.data, t.data_ptr(), out.nbytes, C.c_void_p(stream)), "pnb_download")
+    return out
+
+
+def to_device(array, device):
+    """numpy array -> CUDA tensor through ``pnb_upload`` (staged like :func:`to_host`)."""
+    import torch
+
+    a = np.ascontiguousarray(array)
+    if a.nbytes < (1 << 20) or a.dtype.type not in (np.float64, np.float32, np.int32, np.int64, np.uint8, np.bool_):
+        return torch.as_tensor(a).to(device)
+    dev = torch.device(device)
+    t = torch.empty(a.shape, dtype=torch.from_numpy(a[:0].reshape(-1)).dtype, device=dev)
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(_lib.load().pnb_upload(t.data_ptr(), a.ctypes.data, a.nbytes, C.c_void_p(stream)), "pnb_upload")
+    return t

@@ -17,6 +17,7 @@ import time
 
 import numpy as np
 
+from .. import engine
 from .. import validation as V
 from ..resize import METHODS, interpolate_array
 from .base import BaseFitter, PixelIndices
@@ -120,7 +121,7 @@ class IDEALFitter(BaseFitter):
         lo_vals = torch.tensor([solver.bounds[n][0] for n in names], **f64)
         hi_vals = torch.tensor([solver.bounds[n][1] for n in names], **f64)
         tol_vals = torch.tensor([self.step_tol[n] for n in names], **f64)
-        img_d = torch.as_tensor(np.ascontiguousarray(image, dtype=np.float64)).to(dev)
+        img_d = engine.to_device(np.ascontiguousarray(image, dtype=np.float64), dev)
         seg = segmentation[..., None] if segmentation.ndim == 3 else segmentation
         seg_d = torch.as_tensor(np.ascontiguousarray(seg)).to(dev)
         if not seg_d.dtype.is_floating_point:
@@ -160,8 +161,8 @@ class IDEALFitter(BaseFitter):
             step_maps.append(param_map)
             self.step_pixel_counts.append(int(coords.shape[0]))
         solver.store_device_result(res)
-        self.step_params = [m.cpu().numpy() for m in step_maps]
-        self.pixel_indices = PixelIndices(coords.cpu().numpy())
+        self.step_params = [engine.to_host(m) for m in step_maps]
+        self.pixel_indices = PixelIndices(engine.to_host(coords))
         self.fitted_params_ = {}
         for param, values in solver.params_.items():
             self.fitted_params_[param] = values

@@ -124,7 +124,7 @@ class CurveFitSolver(BaseSolver):
         p0_m, lb_m, ub_m = self._validate_p0_and_bounds(p0, bounds, n_pixels)
         res, free_names = self._solve(xdata, ydata, p0_m, lb_m, ub_m, pixel_fixed_params, n_pixels)
         if on_device:
-            res = {k: (v.cpu().numpy() if v is not None else None) for k, v in res.items()}
+            res = {k: (engine.to_host(v) if v is not None else None) for k, v in res.items()}
         self._store(res, free_names, n_pixels)
         return self
 
@@ -267,7 +267,7 @@ class CurveFitSolver(BaseSolver):
         """Copy a :meth:`fit_device` result to the host and publish it like ``fit`` does."""
         self._reset_state()
         free_names, self._free_rows = res["free_names"], res["free_rows"]
-        host = {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in res.items()
+        host = {k: (engine.to_host(v) if hasattr(v, "cpu") else v) for k, v in res.items()
                 if k not in ("free_names", "free_rows")}
         self._store(host, free_names, host["params"].shape[1])
         return self

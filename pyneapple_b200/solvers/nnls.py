@@ -90,7 +90,7 @@ class NNLSSolver(BaseSolver):
         res = engine.nnls_fit(basis, reg, signal, self.max_iter, device=self.device,
                               chunk_vox=self.chunk_vox, out=out, algorithm=self.algorithm)
         if on_device:
-            res = {k: v.cpu().numpy() for k, v in res.items()}
+            res = {k: engine.to_host(v) for k, v in res.items()}
         status = res["status"]
         self.status_, self.iterations_ = status, res["iterations"]
         self.r_squared_ = res.get("r2")

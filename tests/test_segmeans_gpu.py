@@ -46,3 +46,22 @@ def test_device_tensors_and_the_fitter():
     assert means_d.is_cuda and np.array_equal(lab_d, labels)
     np.testing.assert_allclose(means_d.cpu().numpy(), ref, rtol=1e-13)
     assert int(counts_d.sum()) == seg.size
+
+
+def test_staged_transfers_round_trip():
+    """pnb_upload / pnb_download (pageable host memory through page-locked bounce blocks)."""
+    import torch
+
+    from pyneapple_b200 import engine
+
+    rng = np.random.default_rng(0)
+    for shape, dtype in (((3, 1_000_003), np.float64), ((70 << 20,), np.uint8), ((513, 257, 9), np.float32),
+                         ((12_345_678,), np.int32), ((10,), np.float64)):
+        a = (rng.random(shape) * 200).astype(dtype)
+        t = engine.to_device(a, "cuda:0")
+        assert t.is_cuda and tuple(t.shape) == a.shape
+        assert np.array_equal(t.cpu().numpy(), a)
+        back = engine.to_host(t * 1)
+        assert back.dtype == a.dtype and np.array_equal(back, a)
+    nc = torch.arange(6_000_000, dtype=torch.float64, device="cuda").reshape(2000, 3000).T  # non-contiguous
+    assert np.array_equal(engine.to_host(nc), nc.cpu().numpy())
