@@ -220,7 +220,11 @@ extern "C" int pnb_nnls_fit_host(const pnb_nnls_problem *p, int device, int64_t 
   std::lock_guard<std::mutex> lk(g_mu);
   NnlsCtx &C = g_ctx[device & 15];
   const int m = p->n_b, n = p->n_bins, BW = 2 * p->rtr_halfband + 1;
-  if (chunk_vox <= 0) chunk_vox = 1 << 18;  // long enough that the tail of a launch (its slowest voxels) stays small
+  const bool staged = pnbi::is_pageable(p->signal) || pnbi::is_pageable(p->coefficients);
+  // default chunk: long enough that the tail of a launch (its slowest voxels) stays small; with
+  // pageable caller memory the call is bound by the host copies anyway and a quarter of that keeps
+  // the page-locked staging blocks (3 x chunk x 8 (n_b + n_bins + 3) bytes, ~1 s per GB to lock) small
+  if (chunk_vox <= 0) chunk_vox = staged ? (1 << 16) : (1 << 18);
   if (chunk_vox > p->n_vox) chunk_vox = p->n_vox;
   const size_t Cn = (size_t)chunk_vox;
   if (!C.streams[0])
@@ -250,7 +254,6 @@ extern "C" int pnb_nnls_fit_host(const pnb_nnls_problem *p, int device, int64_t 
   PNBI_CUDA(cudaMemcpy(C.B, p->basis, (size_t)m * n * sizeof(double), cudaMemcpyHostToDevice));
   PNBI_CUDA(cudaMemcpy(C.rtr, p->rtr_band, (size_t)n * BW * sizeof(double), cudaMemcpyHostToDevice));
   const size_t NV = (size_t)p->n_vox;
-  const bool staged = pnbi::is_pageable(p->signal) || pnbi::is_pageable(p->coefficients);
   const size_t D = sizeof(double), I = sizeof(int);
   const size_t o_y = 0, o_coef = o_y + Cn * m * D, o_rn = o_coef + Cn * n * D, o_r2 = o_rn + Cn * D;
   const size_t o_st = o_r2 + Cn * D, o_it = o_st + Cn * I, pin_bytes = o_it + Cn * I;

@@ -123,7 +123,7 @@ class IDEALFitter(BaseFitter):
         tol_vals = torch.tensor([self.step_tol[n] for n in names], **f64)
         img_d = engine.to_device(np.ascontiguousarray(image, dtype=np.float64), dev)
         seg = segmentation[..., None] if segmentation.ndim == 3 else segmentation
-        seg_d = torch.as_tensor(np.ascontiguousarray(seg)).to(dev)
+        seg_d = engine.to_device(np.ascontiguousarray(seg), dev)
         if not seg_d.dtype.is_floating_point:
             seg_d = seg_d.to(torch.float32)  # ideal.py:310-311
         thr = torch.tensor(self.segmentation_threshold, dtype=seg_d.dtype, device=dev)

@@ -16,6 +16,7 @@ from dataclasses import replace
 
 import numpy as np
 
+from .. import engine
 from .. import validation as V
 from .base import BaseFitter
 from .pixelwise import PixelWiseFitter
@@ -94,7 +95,7 @@ class SegmentedFitter(BaseFitter):
             raise TypeError("SegmentedFitter needs B200 CurveFitSolver instances for both steps")
         pixel_to_fit = self._extract_pixel_data(image, segmentation)
         dev = torch.device("cuda", self.step2_solver.device)
-        y_dev = torch.as_tensor(np.ascontiguousarray(pixel_to_fit)).to(dev)
+        y_dev = engine.to_device(np.ascontiguousarray(pixel_to_fit), dev)
         # ---- step 1 on the b-value subset --------------------------------------
         sub_idx = torch.as_tensor(np.nonzero(bmask)[0], device=dev)
         y1 = y_dev if bmask.all() else y_dev.index_select(1, sub_idx).contiguous()

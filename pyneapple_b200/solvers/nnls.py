@@ -154,7 +154,7 @@ class NNLSSolver(BaseSolver):
         # and the uploads (128 B per voxel) are small next to the fit itself
         for s0 in range(0, n_vox, chunk_vox):
             s1 = min(n_vox, s0 + chunk_vox)
-            y = torch.as_tensor(signal[s0:s1]).to(dev)
+            y = engine.to_device(signal[s0:s1], dev)
             fit = engine.nnls_fit(basis, reg, y, self.max_iter, device=self.device, algorithm=self.algorithm)
             pk = spectrum.find_spectrum_peaks_batch(fit.pop("coefficients"), self.model.bins, height, regularized,
                                                     cutoffs=cutoffs, max_peaks=max_peaks)

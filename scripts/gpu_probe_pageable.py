@@ -10,6 +10,7 @@ for rep in range(3):
     t = time.perf_counter(); s.fit(b, y); dt = time.perf_counter() - t
 print(f"threads {os.environ.get('PNB_COPY_THREADS', 'default')}: C2 pageable solver.fit {dt*1e3:.1f} ms -> {y.shape[0]/dt/1e6:.1f} Mvox/s")
 n = NNLSSolver(models.NNLSModel((0.0008, 0.5), 250), reg_order=2, mu=0.02, max_iter=250)
-for rep in range(2):
+for rep in range(3):
     t = time.perf_counter(); n.fit(b, y); dt = time.perf_counter() - t
+    print(f'  C3 call {rep}: {dt*1e3:.0f} ms')
 print(f"threads {os.environ.get('PNB_COPY_THREADS', 'default')}: C3 pageable solver.fit {dt*1e3:.1f} ms -> {y.shape[0]/dt/1e6:.2f} Mvox/s")
