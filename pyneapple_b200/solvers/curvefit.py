@@ -300,7 +300,9 @@ class CurveFitSolver(BaseSolver):
         self.njev_ = res["njev"]
         self.r_squared_ = res.get("r2")
         if pcov is None:
-            pcov = np.full((n_pixels, len(free_names), len(free_names)), np.nan)
+            # covariance not requested (want_cov=False): a read-only NaN view of the right shape instead of
+            # filling n_pixels x n x n doubles (0.84 GB / 113 ms for a 4.19 M-voxel tri-exponential slab)
+            pcov = np.broadcast_to(np.nan, (n_pixels, len(free_names), len(free_names)))
         self.pixel_results_ = PixelResults(
             params=rows, covariance=pcov, status=status,
             messages=lambda i, s=status: engine.STATUS_MESSAGES[int(s[i])] if s[i] <= 0 else None,
