@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -48,22 +49,79 @@ bool is_pageable(const void *ptr) {
   return attr.type == cudaMemoryTypeUnregistered;
 }
 
+namespace {
+// Persistent copy workers: a staged host pipeline issues ~100 copies of 2-35 MB per call, and
+// creating 15 threads for each of them cost more than the copies of the small ones.
+class CopyPool {
+ public:
+  explicit CopyPool(unsigned n) : n_(n) {
+    for (unsigned t = 0; t < n_; t++) workers_.emplace_back([this, t] { run(t); });
+  }
+  ~CopyPool() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      stop_ = true;
+      gen_++;
+    }
+    cv_.notify_all();
+    for (auto &w : workers_) w.join();
+  }
+  unsigned size() const { return n_; }
+  // copies [part * (t + 1), ...) pieces on the workers while the caller copies piece 0
+  void copy(char *dst, const char *src, size_t bytes, size_t part, unsigned pieces) {
+    std::unique_lock<std::mutex> lk(mu_);
+    dst_ = dst; src_ = src; bytes_ = bytes; part_ = part; pieces_ = pieces;
+    pending_ = pieces - 1;
+    gen_++;
+    lk.unlock();
+    cv_.notify_all();
+    std::memcpy(dst, src, part < bytes ? part : bytes);
+    lk.lock();
+    done_.wait(lk, [this] { return pending_ == 0; });
+  }
+
+ private:
+  void run(unsigned t) {
+    unsigned long long seen = 0;
+    for (;;) {
+      std::unique_lock<std::mutex> lk(mu_);
+      cv_.wait(lk, [&] { return gen_ != seen; });
+      seen = gen_;
+      if (stop_) return;
+      const unsigned piece = t + 1;
+      if (piece >= pieces_) continue;
+      char *d = dst_; const char *s = src_;
+      const size_t off = part_ * piece, total = bytes_, part = part_;
+      lk.unlock();
+      if (off < total) std::memcpy(d + off, s + off, off + part > total ? total - off : part);
+      lk.lock();
+      if (--pending_ == 0) done_.notify_one();
+    }
+  }
+  unsigned n_;
+  std::vector<std::thread> workers_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_;
+  unsigned long long gen_ = 0;
+  bool stop_ = false;
+  char *dst_ = nullptr; const char *src_ = nullptr;
+  size_t bytes_ = 0, part_ = 0;
+  unsigned pieces_ = 0, pending_ = 0;
+};
+std::mutex g_copy_mu;  // one parallel copy at a time (the pool has one job slot)
+}  // namespace
+
 void parallel_memcpy(void *dst, const void *src, size_t bytes) {
   static const unsigned hw = std::thread::hardware_concurrency();
   // PNB_COPY_THREADS overrides the default of min(16, cores) host threads per staging copy
   static const unsigned want = [] { const char *e = std::getenv("PNB_COPY_THREADS"); return e ? (unsigned)std::atoi(e) : 0u; }();
-  unsigned nt = want ? want : (hw > 16 ? 16 : (hw ? hw : 1));
+  static const unsigned nt = want ? want : (hw > 16 ? 16 : (hw ? hw : 1));
   if (bytes < (4u << 20) || nt < 2) { std::memcpy(dst, src, bytes); return; }
+  static CopyPool *pool = new CopyPool(nt - 1);  // lives for the process (workers sleep on a condition variable)
   const size_t part = ((bytes / nt) + 4095) & ~(size_t)4095;
-  std::vector<std::thread> th;
-  for (unsigned t = 1; t < nt; t++) {
-    const size_t off = part * t;
-    if (off >= bytes) break;
-    const size_t len = (off + part > bytes) ? bytes - off : part;
-    th.emplace_back([=] { std::memcpy((char *)dst + off, (const char *)src + off, len); });
-  }
-  std::memcpy(dst, src, part < bytes ? part : bytes);
-  for (auto &t : th) t.join();
+  const unsigned pieces = (unsigned)((bytes + part - 1) / part);
+  std::lock_guard<std::mutex> lk(g_copy_mu);
+  pool->copy((char *)dst, (const char *)src, bytes, part, pieces);
 }
 }  // namespace pnbi
 
