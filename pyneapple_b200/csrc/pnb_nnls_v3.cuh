@@ -10,7 +10,9 @@
 //
 //   * lane l owns the 8 CONSECUTIVE bins 8l .. 8l+7.  Their duals live in
 //     registers; the banded regulariser reads one window x[8l-W .. 8l+7+W] of the
-//     coefficient vector instead of 2W+1 values per bin; the whole dual pass is
+//     coefficient vector instead of 2W+1 values per bin (the vector is stored
+//     lane-major so these loads are bank-conflict free) and takes the interior
+//     (Toeplitz) weights of mu^2 R^T R from registers; the whole dual pass is
 //     one fully unrolled block (8 x (MT/2 + 3) LDS.128, 8 x (MT + 2W+1) DFMA) that
 //     also tracks the lane's best candidate, and the warp-wide arg-max is two
 //     redux.sync on the halves of the (positive) double instead of a 5-step
@@ -23,10 +25,11 @@
 //     1e-18 of being absorbed.
 //   * rows >= k of H and z are kept at zero, which turns the bordering update into
 //     the same rank-one update as every other row (u = [v; -1]).
-//   * shared memory per warp holds rows 0 .. KB-1 of the packed inverse (KB = 40
-//     covers 89 % of the voxels of config C3); a warp whose active set outgrows
-//     that borrows one of E extension areas (rows KB .. 63) from a CTA-wide pool
-//     and returns it when the voxel is done.  12 warps per SM instead of 8.
+//   * shared memory per warp holds rows 0 .. KB-1 of the packed inverse (KB = 36
+//     covers 81 % of the voxels of config C3); a warp whose active set outgrows
+//     that borrows extension areas (rows KB .. K1-1, then K1 .. 95) from a CTA-wide
+//     pool and returns them when the voxel is done.  12 warps per SM instead of 8,
+//     96 slots instead of 64.
 //
 // Status / hand-over protocol, iteration counter, certification thresholds:
 // identical to pnb_nnls_fast.cuh (see there).
@@ -51,7 +54,6 @@ template <int MT, int WK> struct NnlsV3Cfg {
   static constexpr int LD = MT + 2;            // row stride of the dictionary (doubles)
   static constexpr int BWK = 2 * WK + 1;       // band width the kernel is compiled for
   static constexpr int LB = (WK == 0) ? 0 : ((BWK + 1) & ~1);  // padded band row
-  static constexpr int WP = (WK + 1) & ~1;     // zero padding of the coefficient vector, each side
   static constexpr int XW = NQ + 2 * WK;       // coefficient window of one lane: bins 8l-WK .. 8l+7+WK
   static constexpr int XR = 34;                // row stride of the coefficient scratch: column 0 / 33 stay zero
   static constexpr int NX = NQ * XR;           // x[j] lives at (j % 8) * XR + j / 8 + 1 (lane-major, conflict-free)
@@ -71,7 +73,7 @@ template <int MT, int WK> struct NnlsV3Cfg {
 template <int MT, int WK>
 __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const NnlsDeviceArgs a, const int n_e1, const int n_e2) {
   using C = NnlsV3Cfg<MT, WK>;
-  constexpr int NQ = C::NQ, NR = C::NR, LD = C::LD, LB = C::LB, WP = C::WP, KC = C::KC, KB = C::KB, K1 = C::K1;
+  constexpr int NQ = C::NQ, NR = C::NR, LD = C::LD, LB = C::LB, KC = C::KC, KB = C::KB, K1 = C::K1;
   extern __shared__ __align__(16) double smem_v3[];
   double *smem = smem_v3;
   const int m = a.m, n = a.n, W = a.W;
