@@ -399,17 +399,18 @@ def main():
     total_ms = float(t.item())
     value = n_vox * world * args.steps / (total_ms * 1e-3)
 
-    # per-launch kernel duration for the roofline (kernel only, no gather)
+    # per-launch kernel duration for the roofline (kernel only, no gather): CUDA events around
+    # five back-to-back launches on the launching stream
     kev0, kev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kt = []
+    r = engine.trf_fit(desc, b, y_dev, p0, lb, ub, 0, max_nfev=250, ftol=1e-8, jac_mode=jac_mode, device=local_rank)
+    torch.cuda.synchronize()
+    kev0.record()
     for _ in range(5):
-        kev0.record()
         r = engine.trf_fit(desc, b, y_dev, p0, lb, ub, 0, max_nfev=250, ftol=1e-8, jac_mode=jac_mode,
                            device=local_rank)
-        kev1.record()
-        torch.cuda.synchronize()
-        kt.append(kev0.elapsed_time(kev1))
-    kernel_ms = float(np.mean(kt[1:]))
+    kev1.record()
+    torch.cuda.synchronize()
+    kernel_ms = kev0.elapsed_time(kev1) / 5
     nfev_sum = int(r["nfev"].sum().item())
     njev_sum = int(r["njev"].sum().item())
     success = float((r["status"] > 0).double().mean().item())
