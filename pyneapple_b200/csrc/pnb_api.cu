@@ -38,6 +38,22 @@ using LaunchFn = cudaError_t (*)(const pnb::TrfDeviceArgs *, cudaStream_t);
 
 }  // namespace
 
+namespace pnb {
+cudaError_t trf_cov_launch(int n_free, long long n_vox, int m, const int *status, double *cov, cudaStream_t stream) {
+#define PNB_COV_CASE(nf)                                                                           \
+  case nf: {                                                                                       \
+    constexpr int TV = pnb::CovTile<nf>::TV;                                                       \
+    cov_kernel<nf><<<(unsigned)((n_vox + TV - 1) / TV), TV, 0, stream>>>(n_vox, m, status, cov);   \
+  } break;
+  switch (n_free) {
+    PNB_COV_CASE(2) PNB_COV_CASE(3) PNB_COV_CASE(4) PNB_COV_CASE(5) PNB_COV_CASE(6) PNB_COV_CASE(7)
+    default: return cudaErrorInvalidValue;
+  }
+  g_launches.fetch_add(1);
+  return cudaGetLastError();
+}
+}  // namespace pnb
+
 namespace pnbi {
 int fail(int code, const std::string &msg) { return ::fail(code, msg); }
 int cuda_fail(cudaError_t e, const char *what) { return ::cuda_fail(e, what); }
@@ -66,7 +82,6 @@ class CopyPool {
     cv_.notify_all();
     for (auto &w : workers_) w.join();
   }
-  unsigned size() const { return n_; }
   // copies [part * (t + 1), ...) pieces on the workers while the caller copies piece 0
   void copy(char *dst, const char *src, size_t bytes, size_t part, unsigned pieces) {
     std::unique_lock<std::mutex> lk(mu_);

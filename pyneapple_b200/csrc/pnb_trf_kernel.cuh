@@ -264,17 +264,115 @@ __global__ void __launch_bounds__(BLOCK, PNB_TRF_MINBLOCKS) trf_kernel(const Trf
       }
       if (a.cov) {
         double *cv = a.cov + vox * (long long)(n_free * n_free);
-        if (ok) {
-          trf_covariance<M>(S, O, m, cv);
-        } else {
+        if (!ok) {
           const double qnan = nan("");
           for (int i = 0; i < n_free * n_free; i++) cv[i] = qnan;
+        } else if (n_free < 2) {
+          trf_covariance<M>(S, O, m, cv);
+        } else {
+          // The few lanes that finish in a pass would run the LDL^T / pseudo-inverse at ~4 of 32
+          // lanes (15 % of the kernel for 3 % of the arithmetic).  They only park J^T J over the
+          // free parameters (packed lower triangle) and the cost in the voxel's covariance slot;
+          // cov_kernel (below) turns every slot into pinv(J^T J) * 2 cost / (m - n) with all
+          // lanes busy.  n (n + 1) / 2 + 1 <= n^2 for n >= 2.
+          int q = 0;
+#pragma unroll
+          for (int i = 0; i < N; i++) {
+            if ((O.frozen >> i) & 1u) continue;
+#pragma unroll
+            for (int j = 0; j <= i; j++) {
+              if ((O.frozen >> j) & 1u) continue;
+              cv[q++] = S.A[i][j];
+            }
+          }
+          cv[q] = S.cost;
         }
       }
       cur = -1;
     }
   }
 }
+
+// curve_fit's covariance from the parked normal matrix: pinv(J^T J) * 2 cost / (m - n), inf when
+// m <= n (same rules as trf_covariance).  One thread per voxel, every lane busy.
+template <int NF> struct CovTile { static constexpr int TV = NF <= 4 ? 256 : 64; };  // voxels per CTA (<= 48 KB tile)
+
+template <int NF>
+__global__ void __launch_bounds__(CovTile<NF>::TV) cov_kernel(long long n_vox, int m, const int *__restrict__ status,
+                                                              double *__restrict__ cov) {
+  constexpr int TV = CovTile<NF>::TV;
+  // a tile of TV voxel slots goes through shared memory so that global memory is read and written
+  // with consecutive lanes on consecutive doubles (each thread's slot is NF^2 doubles long)
+  constexpr int SL = NF * NF, LDS = SL | 1;  // odd row stride: conflict-free per-thread rows
+  __shared__ double tile[TV * LDS];
+  const long long v0 = (long long)blockIdx.x * TV;
+  const int nv = (int)((n_vox - v0) < TV ? (n_vox - v0) : TV);
+  double *base = cov + v0 * SL;
+  for (int i = threadIdx.x; i < nv * SL; i += TV) tile[(i / SL) * LDS + (i % SL)] = base[i];
+  __syncthreads();
+  const bool live = (int)threadIdx.x < nv && status[v0 + threadIdx.x] > 0;
+  if (live) {
+    double *cv = tile + threadIdx.x * LDS;
+    double A[NF][NF], C[NF][NF], L[NF][NF], dinv[NF];
+    int q = 0;
+#pragma unroll
+    for (int i = 0; i < NF; i++)
+#pragma unroll
+      for (int j = 0; j <= i; j++) A[i][j] = cv[q++];
+    const double cost = cv[q];
+    if (m <= NF) {
+#pragma unroll
+      for (int i = 0; i < NF; i++)
+#pragma unroll
+        for (int j = 0; j < NF; j++) C[i][j] = kInf;
+    } else {
+      const double s_sq = 2.0 * cost / (double)(m - NF);
+      if (ldlt<NF>(A, 0.0, L, dinv)) {
+#pragma unroll
+        for (int c = 0; c < NF; c++) {
+          double e[NF], x[NF];
+#pragma unroll
+          for (int i = 0; i < NF; i++) e[i] = (i == c) ? 1.0 : 0.0;
+          ldlt_solve<NF>(L, dinv, e, x);
+#pragma unroll
+          for (int i = 0; i < NF; i++) C[i][c] = x[i] * s_sq;
+        }
+      } else {
+        // rank deficient: Moore-Penrose inverse, singular values s <= eps * max(m, n) * s_max dropped
+        double Asym[NF][NF], V[NF][NF], w[NF];
+#pragma unroll
+        for (int i = 0; i < NF; i++)
+#pragma unroll
+          for (int j = 0; j < NF; j++) Asym[i][j] = (j <= i) ? A[i][j] : A[j][i];
+        jacobi_eig<NF>(Asym, V, w);
+        double wmax = 0.0;
+#pragma unroll
+        for (int i = 0; i < NF; i++) wmax = dmax(wmax, w[i]);
+        const double thr = kEps * (double)(m > NF ? m : NF);
+        const double wthr = thr * thr * wmax, noise = 4.0 * NF * kEps * wmax;
+#pragma unroll
+        for (int i = 0; i < NF; i++)
+#pragma unroll
+          for (int j = 0; j < NF; j++) {
+            double t = 0.0;
+#pragma unroll
+            for (int kk = 0; kk < NF; kk++)
+              if (w[kk] > wthr && w[kk] > noise) t += V[i][kk] * V[j][kk] / w[kk];
+            C[i][j] = t * s_sq;
+          }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NF; i++)
+#pragma unroll
+      for (int j = 0; j < NF; j++) cv[i * NF + j] = C[i][j];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nv * SL; i += TV) base[i] = tile[(i / SL) * LDS + (i % SL)];
+}
+
+// defined once in pnb_api.cu (six small instantiations)
+cudaError_t trf_cov_launch(int n_free, long long n_vox, int m, const int *status, double *cov, cudaStream_t stream);
 
 template <class M, int BLOCK> size_t trf_smem_bytes(int n_b) {
   return sizeof(double) * (((n_b + 1) & ~1) + (size_t)2 * n_b * BLOCK + 6 * M::NP * BLOCK);
@@ -314,7 +412,12 @@ template <class M, int BLOCK, int METHOD = 0> cudaError_t trf_launch(const TrfDe
   err = cudaMemsetAsync(a.counter, 0, sizeof(unsigned long long), stream);
   if (err != cudaSuccess) return err;
   kern<<<(unsigned)grid, BLOCK, smem, stream>>>(a);
-  return cudaGetLastError();
+  err = cudaGetLastError();
+  if (err != cudaSuccess || !a.cov) return err;
+  int n_free = 0;
+  for (int i = 0; i < M::NP; i++) n_free += ((a.opt.frozen >> i) & 1u) ? 0 : 1;
+  if (n_free < 2) return err;
+  return trf_cov_launch(n_free, a.n_vox, a.n_b, a.status, a.cov, stream);
 }
 
 }  // namespace pnb
