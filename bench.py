@@ -313,11 +313,34 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    _emit(line)
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Route file descriptor 1 to stderr for the duration of the run: stdout must carry exactly one
+    JSON line, and libraries (NCCL with NCCL_DEBUG=VERSION, for one) print there."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -345,9 +368,6 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's own log (NCCL_DEBUG=VERSION / INFO on some
-        # boxes) goes to stderr instead
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     base = synth.CONFIGS["C2"]
@@ -501,7 +521,7 @@ def main():
     }
     line.update(extra)
     line["nnls"] = nnls
-    print(json.dumps(line))
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
