@@ -122,6 +122,33 @@ def test_other_measurement_counts(n_b):
     assert np.abs(s.diagnostics_["residual"] - ref["rnorm"]).max() <= 1e-8
 
 
+@pytest.mark.parametrize("n_bins", [9, 33, 64, 127, 249, 256, 257, 300])
+@pytest.mark.parametrize("order", [1, 2, 3])
+def test_other_dictionary_sizes(n_bins, order):
+    """The fast kernel owns 8 consecutive bins per lane and handles the first / last W bins (and the
+    bins beyond n_bins) separately: every size around its limits (256 bins, then the previous
+    generation takes over) against the C restatement of Lawson-Hanson."""
+    from oracle import c_oracle, ref_port
+
+    rng = np.random.default_rng(1000 * order + n_bins)
+    b = np.array([0, 25, 50, 75, 100, 150, 200, 300, 400, 500, 600, 700, 800, 900, 1000, 1200], float)
+    n = 96
+    f = rng.uniform(0.05, 0.4, n)[:, None]
+    y = 1000 * (f * np.exp(-b * rng.uniform(0.01, 0.1, n)[:, None]) +
+                (1 - f) * np.exp(-b * rng.uniform(5e-4, 2.5e-3, n)[:, None])) + rng.normal(0, 10, (n, 16))
+    y[0] = 0.0
+    y[1, 3] = np.inf
+    model = models.NNLSModel(d_range=(0.0007, 0.4), n_bins=n_bins)
+    s = NNLSSolver(model=model, reg_order=order, mu=0.03, max_iter=3 * n_bins).fit(b, y)
+    A = np.concatenate([ref_port.nnls_basis(b, model.bins), ref_port.regularization_matrix(n_bins, order, 0.03)])
+    fin = np.isfinite(y).all(axis=1)
+    ref = c_oracle.nnls(A, np.concatenate([y[fin], np.zeros((fin.sum(), n_bins))], axis=1), 3 * n_bins)
+    assert ((s.status_[fin] == 1) == (ref["status"] == 1)).all()
+    assert (s.status_[~fin] != 1).all() and (s.params_["coefficients"][~fin] == 0).all()
+    assert np.abs(s.params_["coefficients"][fin] - ref["x"]).max() <= 1e-6
+    assert np.abs(s.diagnostics_["residual"][fin] - ref["rnorm"]).max() <= 1e-8
+
+
 def test_chunked_host_pipeline_equals_single_launch():
     """Many small chunks on alternating streams (each with its own scratch / hand-over list)."""
     from pyneapple_b200 import synth
