@@ -116,3 +116,34 @@ def test_dogbox_core_matches_reference(name):
         err = rel_err(par[ok], P["ref_params"][ok]).max(axis=1)
         assert (err > 1e-4).sum() == 0, (err > 1e-4).sum()
         assert np.median(err) < 1e-7
+
+
+def test_dogbox_t1_variants_and_x_scale_jac_against_c_oracle():
+    """method = "dogbox" with the T1 / STEAM models and with x_scale='jac': device core vs the plain-C
+    restatement of scipy's dogbox (both pinned to the reference goldens for the plain models)."""
+    rng = np.random.default_rng(5)
+    b = np.array([0, 50, 100, 200, 400, 600, 800, 1000, 1200, 1500], float)
+    n = 48
+    s0, d, t1 = rng.uniform(800, 1200, n), rng.uniform(8e-4, 2e-3, n), rng.uniform(900, 1500, n)
+    for t1_mode, tm in ((1, 0.0), (2, 30.0)):
+        tr = 2500.0
+        y = s0[:, None] * np.exp(-b * d[:, None]) * (1 - np.exp(-tr / t1[:, None]))
+        if t1_mode == 2:
+            y = y * np.exp(-tm / t1[:, None])
+        y = y + rng.normal(0, 3, y.shape)
+        P0 = np.tile([1000.0, 1e-3, 1200.0], (n, 1))
+        LB = np.tile([1.0, 1e-5, 100.0], (n, 1))
+        UB = np.tile([5000.0, 0.1, 5000.0], (n, 1))
+        a = hostsim.trf_fit(0, b, y, P0, LB, UB, t1_mode=t1_mode, tr=tr, tm=tm, jac_mode=0, method=1)
+        c = c_oracle.trf_fit(0, b, y, P0, LB, UB, t1_mode=t1_mode, tr=tr, tm=tm, jac_mode=0, method="dogbox")
+        assert ((a["status"] > 0) == (c["status"] > 0)).all()
+        ok = c["status"] > 0
+        assert rel_err(a["params"][ok, 1], c["params"][ok, 1]).max() < 1e-6
+        assert rel_err(a["cost"][ok], c["cost"][ok]).max() < 1e-8
+    P = full_problem("dbx_biexp_s0_c2")
+    m = 32
+    a = hostsim.trf_fit(3, P["b"], P["y"][:m], P["P0"][:m], P["LB"][:m], P["UB"][:m], jac_mode=1, x_scale_jac=True, method=1)
+    c = c_oracle.trf_fit(3, P["b"], P["y"][:m], P["P0"][:m], P["LB"][:m], P["UB"][:m], jac_mode=1, x_scale_jac=True,
+                         method="dogbox")
+    assert ((a["status"] > 0) == (c["status"] > 0)).all()
+    assert rel_err(a["params"], c["params"]).max() < 1e-5
