@@ -386,11 +386,15 @@ def main():
     # ------------------------------------------------------------ device-resident steps
     y_dev = torch.as_tensor(y_host).to(dev)
 
+    gathered = [None]
+
     def device_step():
         r = engine.trf_fit(desc, b, y_dev, p0, lb, ub, 0, max_nfev=250, ftol=1e-8, jac_mode=jac_mode,
                            device=local_rank)
         if world > 1:
-            parallel.gather_to_rank0(r["params"], [n_vox] * world, dim=1)
+            # the blocks arrive stacked (world, n_params, n_vox): every rank's block is the parameter
+            # map of its z-slab
+            gathered[0] = parallel.gather_to_rank0(r["params"], [n_vox] * world, dim=1, concat=False, out=gathered[0])
         return r
 
     for _ in range(args.warmup):

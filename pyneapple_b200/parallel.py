@@ -46,11 +46,15 @@ def slab_bounds(mask_per_slice: np.ndarray, world: int) -> list[tuple[int, int]]
     return [(cuts[r], cuts[r + 1]) for r in range(world)]
 
 
-def gather_to_rank0(local, sizes: list[int], dim: int = -1, dst: int = 0):
+def gather_to_rank0(local, sizes: list[int], dim: int = -1, dst: int = 0, concat: bool = True, out=None):
     """Gather per-rank tensors that differ in length along ``dim`` to ``dst``.
 
     Returns the concatenated tensor on ``dst`` and ``None`` elsewhere.  One
     ``torch.distributed.gather`` (ranks pad to the largest shard).
+    ``concat=False`` returns the blocks stacked along a new leading axis, ``(world, *padded shape)``
+    — what the collective delivers, without the extra pass over the data that joining them along
+    ``dim`` costs (the caller scatters every rank's block into its z-slab of the volume anyway);
+    ``out`` is an optional preallocated buffer of that stacked shape on ``dst``.
     """
     import torch
     import torch.distributed as dist
@@ -66,8 +70,14 @@ def gather_to_rank0(local, sizes: list[int], dim: int = -1, dst: int = 0):
         pad_shape[dim] = big - local.shape[dim]
         local = torch.cat([local, local.new_zeros(pad_shape)], dim=dim)
     local = local.contiguous()
-    bufs = [torch.empty_like(local) for _ in range(world)] if rank == dst else None
+    bufs = None
+    if rank == dst:
+        if out is None or tuple(out.shape) != (world,) + tuple(local.shape) or out.dtype != local.dtype:
+            out = torch.empty((world,) + tuple(local.shape), dtype=local.dtype, device=local.device)
+        bufs = list(out.unbind(0))
     dist.gather(local, bufs, dst=dst)
     if rank != dst:
         return None
+    if not concat:
+        return out
     return torch.cat([b.narrow(dim, 0, s) for b, s in zip(bufs, sizes)], dim=dim)

@@ -41,11 +41,18 @@ def _worker(rank, world, port, q):
     s, e = bounds[rank]
     full = torch.arange(4 * n, dtype=torch.float64).reshape(4, n)
     local = full[:, s:e].clone()
-    out = parallel.gather_to_rank0(local, [b[1] - b[0] for b in bounds], dim=1)
+    sizes = [b[1] - b[0] for b in bounds]
+    out = parallel.gather_to_rank0(local, sizes, dim=1)
+    # stacked form: what the collective delivers (ranks padded to the largest shard), buffer reused
+    buf = torch.empty((world, 4, max(sizes)), dtype=torch.float64) if rank == 0 else None
+    blocks = parallel.gather_to_rank0(local, sizes, dim=1, concat=False, out=buf)
     if rank == 0:
-        q.put(bool(torch.equal(out, full)))
+        ok = bool(torch.equal(out, full)) and blocks.data_ptr() == buf.data_ptr()
+        for r, (bs, be) in enumerate(bounds):
+            ok = ok and bool(torch.equal(blocks[r][:, : be - bs], full[:, bs:be]))
+        q.put(ok)
     else:
-        assert out is None
+        assert out is None and blocks is None
     dist.destroy_process_group()
 
 
