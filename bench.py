@@ -387,6 +387,16 @@ def main():
     y_dev = torch.as_tensor(y_host).to(dev)
 
     gathered = [None]
+    peer = None
+    if world > 1 and os.environ.get("PNB_GATHER", "peer") == "peer":
+        try:
+            peer = parallel.PeerGather((4, n_vox), torch.float64, dev)
+        except Exception as exc:  # no CUDA IPC in this environment: NCCL gather instead
+            print(f"rank {rank}: peer-memory gather unavailable ({exc}); using the NCCL gather", file=sys.stderr)
+        ok = torch.tensor([1 if peer is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            peer = None
 
     def device_step():
         r = engine.trf_fit(desc, b, y_dev, p0, lb, ub, 0, max_nfev=250, ftol=1e-8, jac_mode=jac_mode,
@@ -394,7 +404,11 @@ def main():
         if world > 1:
             # the blocks arrive stacked (world, n_params, n_vox): every rank's block is the parameter
             # map of its z-slab
-            gathered[0] = parallel.gather_to_rank0(r["params"], [n_vox] * world, dim=1, concat=False, out=gathered[0])
+            if peer is not None:
+                peer.push(r["params"])  # copy engines over NVLink peer memory; completed by the sync below
+            else:
+                gathered[0] = parallel.gather_to_rank0(r["params"], [n_vox] * world, dim=1, concat=False,
+                                                       out=gathered[0])
         return r
 
     for _ in range(args.warmup):
@@ -417,6 +431,16 @@ def main():
         dist.barrier()
     total_ms = ev[0].elapsed_time(ev[-1])
     kernel_launches = _lib.launch_count() - launches0
+    if peer is not None:
+        # the blocks really are on rank 0: compare a checksum of every rank's parameters
+        mine = r["params"].sum().reshape(1)
+        sums = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(sums, mine)
+        if rank == 0:
+            got = peer.out.sum(dim=(1, 2))
+            want = torch.cat(sums)
+            if not torch.allclose(got, want, rtol=1e-12, atol=0):
+                raise SystemExit(f"peer-memory gather delivered wrong data: {got.tolist()} vs {want.tolist()}")
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -514,7 +538,8 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "voxels_per_gpu": n_vox, "jacobian": args.jac,
                    "l2": "inputs (537 MB per GPU) exceed the 126 MB L2, no flush needed",
-                   "multi_gpu": "z-slabs, one volume per rank, NCCL gather of parameter maps to rank 0 in the timed region",
+                   "multi_gpu": "z-slabs, one volume per rank, parameter maps gathered to rank 0 in the timed region ("
+                                + ("peer-memory copies over NVLink" if peer is not None else "NCCL gather") + ")",
                    "success_rate": success, "mean_nfev": nfev_sum / n_vox},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

@@ -253,6 +253,10 @@ int pnb_host_free(void *ptr);
  * is on the device. */
 int pnb_download(void *host_dst, const void *dev_src, int64_t bytes, void *after_stream);
 int pnb_upload(void *dev_dst, const void *host_src, int64_t bytes, void *then_stream);
+/* Asynchronous device-to-device copy on a stream of the current device; dst may be peer memory
+ * (another GPU of the node, e.g. rank 0's gather buffer mapped through CUDA IPC): the copy engines
+ * move the block over NVLink — the one data-path exchange of the multi-GPU mode. */
+int pnb_copy_d2d(void *dst, const void *src, int64_t bytes, void *cuda_stream);
 /* FP64 FMA micro-benchmark: achieved TFLOP/s of dependent-chain-free DFMA (roofline denominator) */
 int pnb_measure_fp64_peak(int device, double *tflops);
 

@@ -198,6 +198,8 @@ def load():
     lib.pnb_download.restype = C.c_int
     lib.pnb_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     lib.pnb_upload.restype = C.c_int
+    lib.pnb_copy_d2d.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.pnb_copy_d2d.restype = C.c_int
     lib.pnb_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     _lib = lib
     return lib

@@ -522,6 +522,16 @@ int bounce_for(int dev, Bounce **out) {
 }
 }  // namespace
 
+// Device-to-device copy enqueued on `cuda_stream` of the CURRENT device (a peer copy when dst lives
+// on another GPU, e.g. memory mapped through CUDA IPC): the source GPU's copy engine pushes the
+// bytes over NVLink, nothing runs in the destination GPU's context.
+extern "C" int pnb_copy_d2d(void *dst, const void *src, int64_t bytes, void *cuda_stream) {
+  if (bytes <= 0) return 0;
+  if (!dst || !src) return fail(PNB_E_BADARG, "null pointer");
+  PNB_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, (cudaStream_t)cuda_stream));
+  return 0;
+}
+
 extern "C" int pnb_download(void *host_dst, const void *dev_src, int64_t bytes, void *after_stream) {
   if (bytes <= 0) return 0;
   if (!host_dst || !dev_src) return fail(PNB_E_BADARG, "null pointer");

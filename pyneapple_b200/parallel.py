@@ -81,3 +81,68 @@ def gather_to_rank0(local, sizes: list[int], dim: int = -1, dst: int = 0, concat
     if not concat:
         return out
     return torch.cat([b.narrow(dim, 0, s) for b, s in zip(bufs, sizes)], dim=dim)
+
+
+class PeerGather:
+    """Gather equally shaped per-rank blocks into one buffer on rank ``dst`` through peer memory.
+
+    Rank ``dst`` allocates ``(world, *shape)`` and publishes it with a CUDA IPC handle; every other
+    rank maps it and writes its block with a device-to-device ``cudaMemcpyAsync`` over NVLink.  The
+    copy engines do the transfer — no SM is needed, so it overlaps whatever kernel the rank launches
+    next (the NCCL gather is a kernel and cannot share an SM with the register-bound TRF kernel).
+    ``push`` only enqueues; ``wait`` makes the gathered data visible on ``dst`` (stream
+    synchronisation + barrier).  Needs the ``nccl`` backend's world to live on one node.
+    """
+
+    def __init__(self, shape, dtype, device, dst: int = 0):
+        import torch
+        import torch.distributed as dist
+
+        self.world, self.rank, self.dst = dist.get_world_size(), dist.get_rank(), dst
+        self.shape = tuple(shape)
+        self.out = None
+        self._side = None
+        payload = [None]
+        if self.rank == dst:
+            try:
+                self.out = torch.empty((self.world,) + self.shape, dtype=dtype, device=device)
+                payload = [self.out.untyped_storage()._share_cuda_()]
+            except Exception:  # the other ranks are waiting in the broadcast: tell them
+                payload = [None]
+        dist.broadcast_object_list(payload, src=dst)
+        if payload[0] is None:
+            raise RuntimeError("CUDA IPC export of the gather buffer failed on the destination rank")
+        if self.rank == dst:
+            self._remote = self.out
+        else:
+            storage = torch.UntypedStorage._new_shared_cuda(*payload[0])
+            self._remote = torch.empty(0, dtype=dtype, device=storage.device).set_(
+                storage, 0, (self.world,) + self.shape)
+
+    def push(self, local):
+        """Enqueue the copy of this rank's block on a side stream of ``local``'s device, ordered after
+        the work already queued on its current stream (so the next kernel does not wait for it)."""
+        import ctypes as C
+
+        import torch
+
+        from . import _lib
+
+        dev = local.device
+        if self._side is None:
+            self._side = torch.cuda.Stream(dev)
+        local = local.contiguous()
+        dst = self._remote[self.rank]
+        with torch.cuda.device(dev):
+            self._side.wait_stream(torch.cuda.current_stream(dev))
+            _lib.check(_lib.load().pnb_copy_d2d(dst.data_ptr(), local.data_ptr(), local.numel() * local.element_size(),
+                                                C.c_void_p(self._side.cuda_stream)), "pnb_copy_d2d")
+            local.record_stream(self._side)
+
+    def wait(self):
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.synchronize()
+        dist.barrier()
+        return self.out
