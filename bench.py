@@ -145,9 +145,10 @@ def bench_nnls(args, world, rank, local_rank, dev):
     from pyneapple_b200.solvers.nnls import regularization_matrix
 
     base = synth.CONFIGS["C3"]
-    cfg = synth.Config(**{**base.__dict__, "shape": (base.shape[0], base.shape[1], args.slices * world)})
-    z0 = rank * args.slices
-    b, img, _ = synth.make_volume(cfg, z0, z0 + args.slices)
+    # weak scaling: every rank fits its own volume of the configuration (same parameter fields, its
+    # own noise), i.e. slab `rank` of a stack of C3 volumes
+    cfg = synth.Config(**{**base.__dict__, "shape": (base.shape[0], base.shape[1], args.slices)})
+    b, img, _ = synth.make_volume(cfg, 0, args.slices, replica=rank)
     y_host = img.reshape(-1, b.shape[0])
     del img
     n_vox, n_b = y_host.shape
@@ -371,9 +372,11 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     base = synth.CONFIGS["C2"]
-    cfg = synth.Config(**{**base.__dict__, "shape": (base.shape[0], base.shape[1], args.slices * world)})
-    z0 = rank * args.slices
-    b, img, _ = synth.make_volume(cfg, z0, z0 + args.slices)
+    # weak scaling: every rank fits its own C2 volume (same parameter fields, its own noise), i.e.
+    # z-slab `rank` of a stack of `world` C2 volumes.  Cutting one world-times deeper volume instead
+    # would give every rank a different part of the parameter ranges and a different amount of work.
+    cfg = synth.Config(**{**base.__dict__, "shape": (base.shape[0], base.shape[1], args.slices)})
+    b, img, _ = synth.make_volume(cfg, 0, args.slices, replica=rank)
     n_b = b.shape[0]
     y_host = img.reshape(-1, n_b)
     del img
@@ -538,7 +541,8 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "voxels_per_gpu": n_vox, "jacobian": args.jac,
                    "l2": "inputs (537 MB per GPU) exceed the 126 MB L2, no flush needed",
-                   "multi_gpu": "z-slabs, one volume per rank, parameter maps gathered to rank 0 in the timed region ("
+                   "multi_gpu": "z-slabs of a stack of C2 volumes, one volume (same parameter fields, own noise) per rank, parameter maps gathered to "
+                                "rank 0 in the timed region ("
                                 + ("peer-memory copies over NVLink" if peer is not None else "NCCL gather") + ")",
                    "success_rate": success, "mean_nfev": nfev_sum / n_vox},
         "clocks": clocks,

@@ -112,8 +112,11 @@ def _smooth_field(rng, xs, ys, zs, lo, hi):
     return lo + (hi - lo) * u
 
 
-def truth_fields(cfg: Config, z0: int = 0, z1: int | None = None) -> dict:
-    """Ground-truth parameter maps ``name -> (X, Y, z1-z0)`` for a z-slab."""
+def truth_fields(cfg: Config, z0: int = 0, z1: int | None = None, replica: int = 0) -> dict:
+    """Ground-truth parameter maps ``name -> (X, Y, z1-z0)`` for a z-slab.
+
+    ``replica > 0``: another realisation of the same volume — the same smooth parameter fields, its
+    own jitter (and, in :func:`make_volume`, noise) streams; replica 0 is the configuration itself."""
     X, Y, Z = cfg.shape
     z1 = Z if z1 is None else z1
     xs = np.linspace(0.0, 1.0, X)
@@ -126,14 +129,14 @@ def truth_fields(cfg: Config, z0: int = 0, z1: int | None = None) -> dict:
         out[name] = base
     # per-slice jitter streams so that slabs are reproducible independently
     for zi in range(z0, z1):
-        jr = np.random.default_rng([cfg.seed, 1, zi])
+        jr = np.random.default_rng([cfg.seed, 1, zi] + ([replica] if replica else []))
         for name, (lo, hi) in cfg.truth.items():
             jit = 1.0 + 0.05 * jr.uniform(-1.0, 1.0, size=(X, Y))
             out[name][:, :, zi - z0] = np.clip(out[name][:, :, zi - z0] * jit, lo, hi)
     if cfg.name == "C5":
         # 5 % sub-population with f1 + f2 -> 1 so the inequality is active
         for zi in range(z0, z1):
-            jr = np.random.default_rng([cfg.seed, 2, zi])
+            jr = np.random.default_rng([cfg.seed, 2, zi] + ([replica] if replica else []))
             hit = jr.uniform(size=(X, Y)) < 0.05
             s = out["f1"][:, :, zi - z0] + out["f2"][:, :, zi - z0]
             scale = np.where(hit, 1.0 / s, 1.0)
@@ -142,13 +145,14 @@ def truth_fields(cfg: Config, z0: int = 0, z1: int | None = None) -> dict:
     return out
 
 
-def make_volume(cfg: Config | str, z0: int = 0, z1: int | None = None, noise: bool = True):
-    """Return ``(bvalues, image[X, Y, z1-z0, n_b], truth)`` for a z-slab of a config."""
+def make_volume(cfg: Config | str, z0: int = 0, z1: int | None = None, noise: bool = True, replica: int = 0):
+    """Return ``(bvalues, image[X, Y, z1-z0, n_b], truth)`` for a z-slab of a config (``replica``:
+    see :func:`truth_fields`)."""
     if isinstance(cfg, str):
         cfg = CONFIGS[cfg]
     X, Y, Z = cfg.shape
     z1 = Z if z1 is None else z1
-    t = truth_fields(cfg, z0, z1)
+    t = truth_fields(cfg, z0, z1, replica)
     b = cfg.bvalues
     if cfg.model == "monoexp":
         img = t["S0"][..., None] * np.exp(-b * t["D"][..., None])
@@ -169,7 +173,7 @@ def make_volume(cfg: Config | str, z0: int = 0, z1: int | None = None, noise: bo
         raise ValueError(cfg.model)
     if noise:
         for zi in range(z0, z1):
-            nr = np.random.default_rng([cfg.seed, 3, zi])
+            nr = np.random.default_rng([cfg.seed, 3, zi] + ([replica] if replica else []))
             img[:, :, zi - z0, :] += nr.normal(0.0, cfg.noise_sigma, size=(X, Y, b.shape[0]))
     return b.copy(), np.ascontiguousarray(img), t
 
