@@ -64,9 +64,9 @@ class ClockSampler:
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index=0):
+    def __init__(self, gpu_index=0, n_gpus=1):
         self.rows = []
-        self.gpu = gpu_index
+        self.gpu = ",".join(str(gpu_index + i) for i in range(max(1, n_gpus)))  # every GPU of the job
         self.proc = None
 
     def start(self):
@@ -93,24 +93,30 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, reasons, per_gpu = [], [], set(), {}
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             if len(r) < 9:
                 continue
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
+                per_gpu.setdefault(r[0], []).append(float(r[1]))
             except ValueError:
                 continue
             for nm, v in zip(names, r[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
-        return {
-            "sm_mhz": float(np.median(sm)) if sm else None,
+        med = {g: float(np.median(v)) for g, v in per_gpu.items()}
+        out = {
+            # median under load of the SLOWEST GPU of the job (the timing is the max over ranks)
+            "sm_mhz": min(med.values()) if med else None,
             "sm_max_mhz": float(max(mx)) if mx else None,
             "reasons": sorted(reasons),
             "samples": len(sm),
         }
+        if len(med) > 1:
+            out["sm_mhz_per_gpu"] = med
+        return out
 
 
 def nnls_algorithmic_flops(m, n_bins, w, iters, k_final):
@@ -162,6 +168,9 @@ def bench_nnls(args, world, rank, local_rank, dev):
     if world > 1:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nsampler = ClockSampler(0, world)
+    if rank == 0:
+        nsampler.start()
     l0 = _lib.launch_count()
     e0.record()
     for _ in range(steps):
@@ -169,6 +178,7 @@ def bench_nnls(args, world, rank, local_rank, dev):
     e1.record()
     torch.cuda.synchronize()
     launches = _lib.launch_count() - l0
+    nclocks = nsampler.stop() if rank == 0 else None
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -203,6 +213,7 @@ def bench_nnls(args, world, rank, local_rank, dev):
         "workload": "C3: pixelwise NNLS n_bins=250, d_range [0.0008, 0.5], reg_order=2, mu=0.02, max_iter=250, "
                     "256x256x64 voxels x 16 b-values",
         "value": value, "unit": UNIT, "steps": steps, "ms_per_step": ms / steps, "gpu_launches": int(launches),
+        "clocks": nclocks,
         "voxels_per_gpu": n_vox, "success_rate": ok_rate, "mean_iterations": float(iters.mean()),
         "mean_active_set": float(k_final.mean()), "max_active_set": int(k_final.max()),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(y_host.nbytes),
@@ -419,7 +430,7 @@ def main():
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(0, world)
     if rank == 0:
         sampler.start()
     launches0 = _lib.launch_count()
