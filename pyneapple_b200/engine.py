@@ -212,16 +212,35 @@ def rtr_band(reg_matrix: np.ndarray):
     Returns ``(band (n, 2W+1), W)`` with ``band[j, d + W] = (R^T R)[j, j + d]``.
     """
     R = np.asarray(reg_matrix, dtype=np.float64)
-    n = R.shape[1]
-    rtr = R.T @ R
-    nz = np.nonzero(rtr)
-    W = int(np.max(np.abs(nz[0] - nz[1]))) if nz[0].size else 0
+    m_r, n = R.shape
+    nzr = np.nonzero(R)
+    if nzr[0].size == 0:
+        return np.zeros((n, 1)), 0
+    lo, hi = int((nzr[0] - nzr[1]).min()), int((nzr[0] - nzr[1]).max())  # rows k - column j of the stencil
+    W = hi - lo
     if W > 8:
         raise NotImplementedError(f"regularisation matrix with R^T R half-bandwidth {W} > 8")
+    # (R^T R)[j, j+d] = sum_k R[k, j] R[k, j+d], added over the stencil rows k = j + r in the same
+    # order r = lo .. hi for every column.  A BLAS product would add the same terms in an order that
+    # depends on where j falls in its blocking, so the interior rows of the band could differ in the
+    # last bit — the kernel keeps them in registers only when they are identical.
     band = np.zeros((n, 2 * W + 1))
+    cols = np.arange(n)
     for d in range(-W, W + 1):
-        j = np.arange(max(0, -d), min(n, n - d))
-        band[j, d + W] = rtr[j, j + d]
+        j = cols[max(0, -d): min(n, n - d)]
+        acc = np.zeros(j.shape[0])
+        for r in range(lo, hi + 1):
+            k = j + r
+            ok = (k >= 0) & (k < m_r)
+            term = np.zeros(j.shape[0])
+            term[ok] = R[k[ok], j[ok]] * R[k[ok], j[ok] + d]
+            acc = acc + term
+        band[j, d + W] = acc
+    # trim offsets that are zero everywhere (e.g. a diagonal R)
+    while W > 0 and not band[:, 0].any() and not band[:, -1].any():
+        band = band[:, 1:-1]
+        W -= 1
+    band = np.ascontiguousarray(band)
     return band, W
 
 

@@ -174,8 +174,13 @@ def test_constrained_and_nnls_constructor_contract():
     for j in range(9):
         for d in range(-4, 5):
             if 0 <= j + d < 9:
-                assert band[j, d + 4] == full[j, j + d]
+                # same terms as the BLAS product, added in a position-independent order
+                assert band[j, d + 4] == pytest.approx(full[j, j + d], rel=4e-16, abs=0)
     assert engine.rtr_band(np.zeros((5, 5)))[1] == 0
+    # the interior rows of the band are bit-identical (the kernel keeps them in registers only then)
+    for order, W in ((1, 1), (2, 2), (3, 4)):
+        band, w = engine.rtr_band(regularization_matrix(250, order, 0.0337))
+        assert w == W and all(np.array_equal(band[W + 1], band[i]) for i in range(W + 1, 250 - W - 1))
 
 
 def test_lazy_containers():
