@@ -36,7 +36,7 @@ pnb::SpectrumArgs args_of(const pnb_spectrum_problem *p) {
 }
 
 int launch(const pnb::SpectrumArgs &a, cudaStream_t stream) {
-  const size_t smem = pnb::spectrum_smem_bytes(a.x ? a.n : 0);
+  const size_t smem = pnb::spectrum_smem_bytes(a.n);  // the kernel lays its per-warp arrays out behind n doubles
   if (smem > 200 * 1024) return pnbi::fail(PNB_E_UNSUPPORTED, "n_bins too large for shared memory");
   if (smem > 48 * 1024)
     PNBI_CUDA(cudaFuncSetAttribute(pnb::spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
