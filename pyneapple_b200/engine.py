@@ -19,7 +19,9 @@ import numpy as np
 from . import _lib
 from .models import ModelDesc
 
+ST_LM_BOUNDED = -5  # not a kernel status: method='lm' on a bounded problem (see CurveFitSolver.fit)
 STATUS_MESSAGES = {
+    -5: "Method 'lm' only works for unconstrained problems. Use 'trf' or 'dogbox' instead.",
     -4: "Residuals are not finite in the initial point.",
     -3: "array must not contain infs or NaNs",
     -2: "Initial guess is outside of provided bounds",

@@ -107,9 +107,7 @@ class CurveFitSolver(BaseSolver):
         swallowed like the reference does (``fixed_param_maps=None`` arrives
         here from ``run_pipeline`` through ``IDEALFitter.fit``)."""
         self._reset_state()
-        if self.method not in engine.METHODS:
-            # 'lm' (MINPACK) cannot be used through this solver in the reference either: curve_fit
-            # rejects it for bounded problems and the solver always passes bounds
+        if self.method not in engine.METHODS and self.method != "lm":
             raise NotImplementedError(
                 f"method={self.method!r}: SciPy's 'trf' and 'dogbox' have a B200 implementation"
             )
@@ -122,14 +120,27 @@ class CurveFitSolver(BaseSolver):
         if ydata.ndim == 1:
             ydata = ydata[None, :]
         p0_m, lb_m, ub_m = self._validate_p0_and_bounds(p0, bounds, n_pixels)
-        res, free_names = self._solve(xdata, ydata, p0_m, lb_m, ub_m, pixel_fixed_params, n_pixels)
+        lm = self.method == "lm"
+        if lm and not (np.isfinite(np.asarray(lb_m)).any() or np.isfinite(np.asarray(ub_m)).any()):
+            raise NotImplementedError("method='lm' on an unbounded problem (MINPACK) has no B200 implementation")
+        res, free_names = self._solve(xdata, ydata, p0_m, lb_m, ub_m, pixel_fixed_params, n_pixels,
+                                      max_nfev=1 if lm else None, method="dogbox" if lm else None)
         if on_device:
             res = {k: (engine.to_host(v) if v is not None else None) for k, v in res.items()}
+        if lm:
+            # curve_fit rejects 'lm' for a bounded problem before it looks at the data, for every voxel
+            # (scipy/optimize/_minpack_py.py: "Method 'lm' only works for unconstrained problems."): the
+            # reference's solver turns that into success=False, params = p0, NaN covariance
+            # (solvers/curvefit.py:308-317).  The single evaluation above (dogbox leaves x0 = p0 untouched)
+            # only supplies R^2 at p0.
+            res["status"][...] = engine.ST_LM_BOUNDED
+            if res.get("cov") is not None:
+                res["cov"][...] = np.nan
         self._store(res, free_names, n_pixels)
         return self
 
     # ------------------------------------------------------------------
-    def _solve(self, xdata, ydata, p0_m, lb_m, ub_m, pixel_fixed_params, n_pixels):
+    def _solve(self, xdata, ydata, p0_m, lb_m, ub_m, pixel_fixed_params, n_pixels, max_nfev=None, method=None):
         """Assemble full-parameter arrays and call the engine.
 
         ``p0_m`` / ``lb_m`` / ``ub_m`` are ``(n_model,)`` or ``(n_model,
@@ -190,12 +201,12 @@ class CurveFitSolver(BaseSolver):
                 xs_full[all_names.index(n)] = xs[i]
         res = engine.trf_fit(
             desc, xdata, ydata, P0, LB, UB, frozen,
-            max_nfev=self.max_iter, ftol=self.tol,
+            max_nfev=self.max_iter if max_nfev is None else max_nfev, ftol=self.tol,
             xtol=self.solver_kwargs.get("xtol", 1e-8), gtol=self.solver_kwargs.get("gtol", 1e-8),
             jac_mode=jac_mode, x_scale=xs_full, x_scale_jac=x_scale_jac,
             want_cov=self.want_cov, device=self.device, chunk_vox=self.chunk_vox,
             out=self._pinned_out(len(all_names), len(all_names) - len(fixed_names), n_pixels, ydata),
-            method=self._ls_method(),
+            method=method or self._ls_method(),
         )
         self._free_rows = [all_names.index(n) for n in free_names]
         return res, free_names

@@ -77,11 +77,22 @@ def test_dogbox_large_sample_against_the_scipy_port():
     assert np.median(err) < 1e-7
 
 
-def test_unsupported_method_is_rejected():
-    solver = CurveFitSolver(model=models.MonoExpModel(), max_iter=250, tol=1e-8, p0={"S0": 1000.0, "D": 1e-3},
-                            bounds={"S0": (1.0, 5000.0), "D": (1e-5, 0.1)}, method="lm")
+def test_method_lm_behaves_like_the_reference():
+    """curve_fit rejects 'lm' for bounded problems; the reference's solver reports that per voxel
+    (checked against the reference: success False, params = p0, NaN covariance, SciPy's message)."""
+    kw = dict(model=models.MonoExpModel(), max_iter=250, tol=1e-8, p0={"S0": 1000.0, "D": 1e-3})
+    b = np.array([0.0, 100.0, 500.0, 1000.0])
+    y = np.array([[1000.0, 900.0, 600.0, 370.0], [800.0, 700.0, 500.0, 300.0]])
+    solver = CurveFitSolver(bounds={"S0": (1.0, 5000.0), "D": (1e-5, 0.1)}, method="lm", **kw).fit(b, y)
+    for i in range(2):
+        pr = solver.pixel_results_[i]
+        assert pr.success is False or not pr.success
+        assert np.array_equal(pr.params, [1000.0, 1e-3]) and np.isnan(pr.covariance).all()
+        assert pr.message == "Method 'lm' only works for unconstrained problems. Use 'trf' or 'dogbox' instead."
     with pytest.raises(NotImplementedError):
-        solver.fit(np.array([0.0, 100.0, 500.0]), np.array([[1000.0, 900.0, 600.0]]))
+        CurveFitSolver(bounds={"S0": (-np.inf, np.inf), "D": (-np.inf, np.inf)}, method="lm", **kw).fit(b, y)
+    with pytest.raises(NotImplementedError):
+        CurveFitSolver(bounds={"S0": (1.0, 5000.0), "D": (1e-5, 0.1)}, method="cg", **kw).fit(b, y)
 
 
 def _golden_parity(name, cases, jac, **solver_kw):
