@@ -120,8 +120,12 @@ class PeerGather:
                 storage, 0, (self.world,) + self.shape)
 
     def push(self, local):
-        """Enqueue the copy of this rank's block on a side stream of ``local``'s device, ordered after
-        the work already queued on its current stream (so the next kernel does not wait for it)."""
+        """Enqueue the transfer of this rank's block: a copy into one of two persistent staging buffers
+        on the current stream, then the peer copy from there on a side stream, ordered after it (so the
+        next kernel does not wait for the transfer).  Staging keeps the caller's tensor out of the
+        picture: holding it until the peer copy is done (``record_stream``) made the caching allocator
+        run out of reusable blocks and call ``cudaMalloc`` — a device-wide synchronisation — once the
+        transfers got slower (eight ranks pushing into one GPU)."""
         import ctypes as C
 
         import torch
@@ -131,13 +135,22 @@ class PeerGather:
         dev = local.device
         if self._side is None:
             self._side = torch.cuda.Stream(dev)
-        local = local.contiguous()
+            self._stage = [torch.empty(self.shape, dtype=local.dtype, device=dev) for _ in range(2)]
+            self._done = [None, None]
+            self._turn = 0
+        t = self._turn
+        self._turn ^= 1
+        cur = torch.cuda.current_stream(dev)
+        if self._done[t] is not None:
+            cur.wait_event(self._done[t])  # the peer copy that last read this staging buffer (two pushes ago)
+        self._stage[t].copy_(local, non_blocking=True)
         dst = self._remote[self.rank]
         with torch.cuda.device(dev):
-            self._side.wait_stream(torch.cuda.current_stream(dev))
-            _lib.check(_lib.load().pnb_copy_d2d(dst.data_ptr(), local.data_ptr(), local.numel() * local.element_size(),
+            self._side.wait_stream(cur)
+            _lib.check(_lib.load().pnb_copy_d2d(dst.data_ptr(), self._stage[t].data_ptr(),
+                                                self._stage[t].numel() * self._stage[t].element_size(),
                                                 C.c_void_p(self._side.cuda_stream)), "pnb_copy_d2d")
-            local.record_stream(self._side)
+            self._done[t] = self._side.record_event()
 
     def wait(self):
         import torch
