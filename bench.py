@@ -403,7 +403,9 @@ def main():
 
     gathered = [None]
     peer = None
-    if world > 1 and os.environ.get("PNB_GATHER", "peer") == "peer":
+    # PNB_GATHER=peer: CUDA-IPC peer-memory pushes instead of the NCCL gather (slower on this pool:
+    # 36 GB/s per pusher through cudaIpc mappings against ~570 GB/s for NCCL, profiles/r1_final_multi_gpu.md)
+    if world > 1 and os.environ.get("PNB_GATHER", "nccl") == "peer":
         try:
             peer = parallel.PeerGather((4, n_vox), torch.float64, dev)
         except Exception as exc:  # no CUDA IPC in this environment: NCCL gather instead
@@ -440,6 +442,8 @@ def main():
     ev[0].record()
     for i in range(args.steps):
         r = device_step()
+        if peer is not None and i == args.steps - 1:
+            peer.flush()  # the last event must cover the transfers still in flight on the side stream
         ev[i + 1].record()
     torch.cuda.synchronize()
     if world > 1:

@@ -92,6 +92,12 @@ class PeerGather:
     next (the NCCL gather is a kernel and cannot share an SM with the register-bound TRF kernel).
     ``push`` only enqueues; ``wait`` makes the gathered data visible on ``dst`` (stream
     synchronisation + barrier).  Needs the ``nccl`` backend's world to live on one node.
+
+    Measured on this pool's B200 boxes (virtualised, ``scripts/gpu_probe_peer.py``): a push through
+    the cudaIpc mapping runs at 36 GB/s per rank — PCIe-class, although the same copy inside one
+    process reaches 700 GB/s over NVLink and peer access is enabled — so it hides behind a 13 ms
+    kernel for two to four ranks but not for eight.  ``bench.py`` therefore uses the NCCL gather
+    (``gather_to_rank0``, ~570 GB/s) unless ``PNB_GATHER=peer``.
     """
 
     def __init__(self, shape, dtype, device, dst: int = 0):
@@ -151,6 +157,14 @@ class PeerGather:
                                                 self._stage[t].numel() * self._stage[t].element_size(),
                                                 C.c_void_p(self._side.cuda_stream)), "pnb_copy_d2d")
             self._done[t] = self._side.record_event()
+
+    def flush(self):
+        """Make the current stream wait for the pushes enqueued so far (timing: an event recorded
+        afterwards covers the transfers)."""
+        import torch
+
+        if self._side is not None:
+            torch.cuda.current_stream(self._side.device).wait_stream(self._side)
 
     def wait(self):
         import torch
