@@ -55,6 +55,39 @@ def test_no_cpu_fallback():
         s.fit(b, 1000 * np.exp(-b * 1e-3))
 
 
+def test_no_cpu_fallback_for_the_new_entry_points():
+    """Spectrum post-processing, segment means, staged transfers: they raise without a device too."""
+    import numpy as np
+    from pyneapple_b200 import engine, spectrum
+
+    if _lib.load().pnb_device_count() > 0:
+        pytest.skip("a GPU is present")
+    x = np.zeros((4, 250))
+    x[:, 100] = 1.0
+    with pytest.raises(_lib.EngineError):
+        spectrum.find_spectrum_peaks_batch(x, np.geomspace(8e-4, 0.5, 250))
+    with pytest.raises(_lib.EngineError):
+        spectrum.find_spectrum_peaks(x[0], np.geomspace(8e-4, 0.5, 250))
+    with pytest.raises(_lib.EngineError):
+        spectrum.apply_cutoffs([1e-3], [1.0], [(1e-4, 1e-2)])
+    with pytest.raises(_lib.EngineError):
+        engine.segment_means(np.zeros((4, 4, 2, 8)), np.zeros((4, 4, 2), int))
+
+
+def test_bench_refuses_to_run_without_a_gpu():
+    import os
+    import subprocess
+    import sys
+
+    if _lib.load().pnb_device_count() > 0:
+        pytest.skip("a GPU is present")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0 and r.stdout.strip() == ""
+    assert "no CPU fallback" in r.stderr
+
+
 def test_spectrum_bad_arguments_are_rejected_without_a_device(lib):
     prob = _lib.SpectrumProblem()
     prob.max_peaks = 64
