@@ -144,6 +144,9 @@ typedef struct pnb_nnls_problem {
   double *r_squared;         /* (n_vox) R^2 of the un-regularised prediction, or NULL */
 } pnb_nnls_problem;
 
+/* Device-path launches on one device share one set of scratch buffers: the library orders each
+ * launch after the previous one on that device (event wait on the given stream), so launches on
+ * different streams are safe but do not overlap. */
 int pnb_nnls_fit_device(const pnb_nnls_problem *prob, void *cuda_stream);
 int pnb_nnls_fit_host(const pnb_nnls_problem *prob, int device, int64_t chunk_vox);
 int pnb_sizeof_nnls_problem(void);
@@ -249,8 +252,9 @@ int pnb_host_free(void *ptr);
  * the numpy arrays the reference's fitters hold (fitters/base.py:280-330) — is staged in 32 MB
  * pieces through two page-locked blocks with multi-threaded host copies (~5x cudaMemcpy on such
  * memory); page-locked memory is copied directly.  `after_stream`: the stream whose work produces
- * dev_src (synchronised first); `then_stream`: unused ordering hint, the call returns when the data
- * is on the device. */
+ * dev_src (synchronised first); `then_stream`: the stream that uses dev_dst — the copies are ordered
+ * after the work already queued on it (dev_dst may be recycled memory that work still reads), and
+ * the call returns when the data is on the device. */
 int pnb_download(void *host_dst, const void *dev_src, int64_t bytes, void *after_stream);
 int pnb_upload(void *dev_dst, const void *host_src, int64_t bytes, void *then_stream);
 /* Asynchronous device-to-device copy on a stream of the current device; dst may be peer memory

@@ -281,7 +281,8 @@ struct Slot {
   double *params = nullptr, *cov = nullptr, *cost = nullptr, *r2 = nullptr;
   int *status = nullptr, *nfev = nullptr, *njev = nullptr;
   unsigned long long *counter = nullptr;
-  size_t cap_y = 0, cap_p = 0, cap_cov = 0, cap_v = 0;
+  size_t cap_y = 0, cap_p0 = 0, cap_lb = 0, cap_ub = 0, cap_par = 0, cap_cov = 0;
+  size_t cap_cost = 0, cap_r2 = 0, cap_st = 0, cap_nf = 0, cap_nj = 0;
   // page-locked staging block for pageable caller memory
   char *pin = nullptr;
   size_t cap_pin = 0;
@@ -313,7 +314,8 @@ extern "C" int pnb_trf_fit_host(const pnb_trf_problem *p, int device, int64_t ch
   if (int rc = check_problem(p)) return rc;
   if (p->n_vox == 0) return 0;
   if (pnb_device_count() <= device || device < 0) return fail(PNB_E_NODEVICE, "no such CUDA device");
-  PNB_CUDA(cudaSetDevice(device));
+  pnbi::DeviceScope dev_scope(device);
+  PNB_CUDA(dev_scope.error());
   std::lock_guard<std::mutex> lk(g_pipe_mu);
   Pipeline &P = g_pipes[device & 15];
   const int np = p->n_params, nb = p->n_b;
@@ -330,36 +332,21 @@ extern "C" int pnb_trf_fit_host(const pnb_trf_problem *p, int device, int64_t ch
     PNB_CUDA(cudaMalloc(&P.vec, sizeof(double) * 3 * 8));
     P.init = true;
   }
-  if ((size_t)nb > P.cap_b) {
-    if (P.b) PNB_CUDA(cudaFree(P.b));
-    PNB_CUDA(cudaMalloc(&P.b, sizeof(double) * nb));
-    P.cap_b = nb;
-  }
+  if (int rc = grow(&P.b, &P.cap_b, (size_t)nb)) return rc;
   for (auto &s : P.slots) {
     if (int rc = grow(&s.y, &s.cap_y, C * nb)) return rc;
-    size_t need_p = C * np;
-    if (need_p > s.cap_p) {
-      for (double **q : {&s.p0, &s.lb, &s.ub, &s.params}) {
-        if (*q) PNB_CUDA(cudaFree(*q));
-        PNB_CUDA(cudaMalloc(q, need_p * sizeof(double)));
-      }
-      s.cap_p = need_p;
-    }
+    const size_t need_p = C * np;
+    if (int rc = grow(&s.p0, &s.cap_p0, need_p)) return rc;
+    if (int rc = grow(&s.lb, &s.cap_lb, need_p)) return rc;
+    if (int rc = grow(&s.ub, &s.cap_ub, need_p)) return rc;
+    if (int rc = grow(&s.params, &s.cap_par, need_p)) return rc;
     if (p->cov)
       if (int rc = grow(&s.cov, &s.cap_cov, C * nfree * nfree)) return rc;
-    if (C > s.cap_v) {
-      if (s.cost) PNB_CUDA(cudaFree(s.cost));
-      if (s.status) PNB_CUDA(cudaFree(s.status));
-      if (s.nfev) PNB_CUDA(cudaFree(s.nfev));
-      if (s.njev) PNB_CUDA(cudaFree(s.njev));
-      if (s.r2) PNB_CUDA(cudaFree(s.r2));
-      PNB_CUDA(cudaMalloc(&s.cost, C * sizeof(double)));
-      PNB_CUDA(cudaMalloc(&s.r2, C * sizeof(double)));
-      PNB_CUDA(cudaMalloc(&s.status, C * sizeof(int)));
-      PNB_CUDA(cudaMalloc(&s.nfev, C * sizeof(int)));
-      PNB_CUDA(cudaMalloc(&s.njev, C * sizeof(int)));
-      s.cap_v = C;
-    }
+    if (int rc = grow(&s.cost, &s.cap_cost, C)) return rc;
+    if (int rc = grow(&s.r2, &s.cap_r2, C)) return rc;
+    if (int rc = grow(&s.status, &s.cap_st, C)) return rc;
+    if (int rc = grow(&s.nfev, &s.cap_nf, C)) return rc;
+    if (int rc = grow(&s.njev, &s.cap_nj, C)) return rc;
   }
   // shared small inputs (synchronous, tiny)
   cudaStream_t s0 = P.slots[0].stream;
@@ -593,6 +580,19 @@ extern "C" int pnb_upload(void *dev_dst, const void *host_src, int64_t bytes, vo
   const size_t n = (size_t)bytes, P = Bounce::kPiece;
   const size_t pieces = (n + P - 1) / P;
   auto len = [&](size_t i) { return (i + 1) * P <= n ? P : n - i * P; };
+  // dev_dst may be a block the caller's allocator has just recycled: work queued on `then_stream`
+  // (a kernel of an earlier chunk, say) can still be reading it.  The side streams write it, so they
+  // must run after everything `then_stream` holds at this point (the host-side staging copies of
+  // the first two pieces still overlap that work).
+  {
+    cudaEvent_t ev;
+    PNB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    cudaError_t e = cudaEventRecord(ev, (cudaStream_t)then_stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(b->st[0], ev, 0);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(b->st[1], ev, 0);
+    cudaEventDestroy(ev);
+    if (e != cudaSuccess) return cuda_fail(e, "ordering the upload after then_stream");
+  }
   for (size_t i = 0; i < pieces; i++) {
     PNB_CUDA(cudaStreamSynchronize(b->st[i & 1]));  // the block's previous piece has left
     pnbi::parallel_memcpy(b->blk[i & 1], (const char *)host_src + i * P, len(i));
@@ -623,7 +623,8 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, 
 extern "C" int pnb_measure_fp64_peak(int device, double *tflops) {
   if (!tflops) return fail(PNB_E_BADARG, "null output");
   if (pnb_device_count() <= device || device < 0) return fail(PNB_E_NODEVICE, "no such CUDA device");
-  PNB_CUDA(cudaSetDevice(device));
+  pnbi::DeviceScope dev_scope(device);
+  PNB_CUDA(dev_scope.error());
   int sms = 0;
   PNB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   const int blocks = sms * 8, threads = 256, iters = 1 << 15;

@@ -13,6 +13,25 @@ void count_launch();
 bool is_pageable(const void *ptr);
 // memcpy split over up to 16 host threads (one thread does ~10 GB/s, PCIe 5 x16 moves ~55 GB/s)
 void parallel_memcpy(void *dst, const void *src, size_t bytes);
+// Makes `device` current for the lifetime of the object and restores the caller's device afterwards
+// (the host entry points must not change the calling thread's current device).
+class DeviceScope {
+ public:
+  explicit DeviceScope(int device) {
+    if (cudaGetDevice(&prev_) != cudaSuccess) { cudaGetLastError(); prev_ = -1; }
+    err_ = cudaSetDevice(device);
+  }
+  ~DeviceScope() {
+    if (prev_ >= 0) cudaSetDevice(prev_);
+  }
+  cudaError_t error() const { return err_; }
+  DeviceScope(const DeviceScope &) = delete;
+  DeviceScope &operator=(const DeviceScope &) = delete;
+
+ private:
+  int prev_ = -1;
+  cudaError_t err_ = cudaSuccess;
+};
 }  // namespace pnbi
 
 #define PNBI_CUDA(call)                                       \

@@ -37,7 +37,10 @@ struct NnlsCtx {
   cudaStream_t streams[kSlots] = {};
   double *y[kSlots] = {}, *coef[kSlots] = {}, *rn[kSlots] = {}, *r2[kSlots] = {};
   int *st[kSlots] = {}, *it[kSlots] = {};
-  size_t cap_vox = 0, cap_m = 0, cap_n = 0;
+  size_t cap_y[kSlots] = {}, cap_coef[kSlots] = {}, cap_rn[kSlots] = {}, cap_r2[kSlots] = {};
+  size_t cap_st[kSlots] = {}, cap_it[kSlots] = {};
+  // device-path launches share slot 0's scratch: each one waits for the previous one's event
+  cudaEvent_t dev_done = nullptr;
   double *B = nullptr, *rtr = nullptr;
   size_t cap_B = 0, cap_rtr = 0;
   // page-locked staging blocks for pageable caller memory
@@ -49,6 +52,16 @@ NnlsCtx g_ctx[16];
 // PNB_NNLS_NO_V3=1 in the environment keeps the second-generation fast kernel (A/B measurements)
 const bool g_disable_v3 = [] { const char *e = std::getenv("PNB_NNLS_NO_V3"); return e && e[0] == '1'; }();
 std::mutex g_mu;
+
+// (re)allocate a device buffer of `need` elements; pointer and capacity stay consistent on failure
+template <class T> int grow(T **ptr, size_t *cap, size_t need) {
+  if (need <= *cap) return 0;
+  if (*ptr) cudaFree(*ptr);
+  *ptr = nullptr; *cap = 0;
+  PNBI_CUDA(cudaMalloc(ptr, need * sizeof(T)));
+  *cap = need;
+  return 0;
+}
 
 int check(const pnb_nnls_problem *p) {
   if (!p) return pnbi::fail(PNB_E_BADARG, "null problem");
@@ -131,18 +144,8 @@ int launch(NnlsCtx &C, const pnb_nnls_problem *p, const double *B, const double 
   const long long want = (n_vox + kWarps - 1) / kWarps;
   const size_t per_warp = (size_t)n * (n + 1) / 2 + 5 * (size_t)n;
   const size_t need = (size_t)bps * sms * kWarps * per_warp;
-  if (need > C.scratch_cap[slot]) {
-    if (C.scratch[slot]) PNBI_CUDA(cudaFree(C.scratch[slot]));
-    C.scratch[slot] = nullptr; C.scratch_cap[slot] = 0;
-    PNBI_CUDA(cudaMalloc(&C.scratch[slot], need * sizeof(double)));
-    C.scratch_cap[slot] = need;
-  }
-  if ((size_t)n_vox > C.redo_cap[slot]) {
-    if (C.redo_list[slot]) PNBI_CUDA(cudaFree(C.redo_list[slot]));
-    C.redo_list[slot] = nullptr; C.redo_cap[slot] = 0;
-    PNBI_CUDA(cudaMalloc(&C.redo_list[slot], (size_t)n_vox * sizeof(int)));
-    C.redo_cap[slot] = (size_t)n_vox;
-  }
+  if (int rc = grow(&C.scratch[slot], &C.scratch_cap[slot], need)) return rc;
+  if (int rc = grow(&C.redo_list[slot], &C.redo_cap[slot], (size_t)n_vox)) return rc;
   if (!C.counters) PNBI_CUDA(cudaMalloc(&C.counters, 64 * sizeof(unsigned long long)));
   // three consecutive counters per call: fast work queue, redo count, robust work queue
   unsigned long long *ctr = C.counters + C.next;
@@ -208,17 +211,28 @@ extern "C" int pnb_nnls_fit_device(const pnb_nnls_problem *p, void *cuda_stream)
   int dev = 0;
   PNBI_CUDA(cudaGetDevice(&dev));
   std::lock_guard<std::mutex> lk(g_mu);
-  return launch(g_ctx[dev & 15], p, p->basis, p->rtr_band, p->signal, p->n_vox, p->coefficients,
-                p->residual, p->status, p->iterations, p->r_squared, (cudaStream_t)cuda_stream, 0);
+  NnlsCtx &C = g_ctx[dev & 15];
+  // Device-path launches use slot 0's scratch, redo list and counters whatever stream they are given:
+  // order each launch after the previous one (a no-op on the same stream), so two launches in flight
+  // on different streams of one device cannot race on them.
+  cudaStream_t stream = (cudaStream_t)cuda_stream;
+  if (!C.dev_done) PNBI_CUDA(cudaEventCreateWithFlags(&C.dev_done, cudaEventDisableTiming));
+  else PNBI_CUDA(cudaStreamWaitEvent(stream, C.dev_done, 0));
+  const int rc = launch(C, p, p->basis, p->rtr_band, p->signal, p->n_vox, p->coefficients,
+                        p->residual, p->status, p->iterations, p->r_squared, stream, 0);
+  PNBI_CUDA(cudaEventRecord(C.dev_done, stream));
+  return rc;
 }
 
 extern "C" int pnb_nnls_fit_host(const pnb_nnls_problem *p, int device, int64_t chunk_vox) {
   if (int rc = check(p)) return rc;
   if (p->n_vox == 0) return 0;
   if (pnb_device_count() <= device || device < 0) return pnbi::fail(PNB_E_NODEVICE, "no such CUDA device");
-  PNBI_CUDA(cudaSetDevice(device));
+  pnbi::DeviceScope dev_scope(device);
+  PNBI_CUDA(dev_scope.error());
   std::lock_guard<std::mutex> lk(g_mu);
   NnlsCtx &C = g_ctx[device & 15];
+  if (C.dev_done) PNBI_CUDA(cudaEventSynchronize(C.dev_done));  // a device-path launch may still use slot 0
   const int m = p->n_b, n = p->n_bins, BW = 2 * p->rtr_halfband + 1;
   const bool staged = pnbi::is_pageable(p->signal) || pnbi::is_pageable(p->coefficients);
   // default chunk: long enough that the tail of a launch (its slowest voxels) stays small; with
@@ -229,28 +243,16 @@ extern "C" int pnb_nnls_fit_host(const pnb_nnls_problem *p, int device, int64_t 
   const size_t Cn = (size_t)chunk_vox;
   if (!C.streams[0])
     for (auto &s : C.streams) PNBI_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-  if (Cn > C.cap_vox || (size_t)m > C.cap_m || (size_t)n > C.cap_n) {
-    for (int s = 0; s < kSlots; s++) {
-      if (C.y[s]) { cudaFree(C.y[s]); cudaFree(C.coef[s]); cudaFree(C.rn[s]); cudaFree(C.r2[s]); cudaFree(C.st[s]); cudaFree(C.it[s]); }
-      PNBI_CUDA(cudaMalloc(&C.y[s], Cn * m * sizeof(double)));
-      PNBI_CUDA(cudaMalloc(&C.coef[s], Cn * n * sizeof(double)));
-      PNBI_CUDA(cudaMalloc(&C.rn[s], Cn * sizeof(double)));
-      PNBI_CUDA(cudaMalloc(&C.r2[s], Cn * sizeof(double)));
-      PNBI_CUDA(cudaMalloc(&C.st[s], Cn * sizeof(int)));
-      PNBI_CUDA(cudaMalloc(&C.it[s], Cn * sizeof(int)));
-    }
-    C.cap_vox = Cn; C.cap_m = m; C.cap_n = n;
+  for (int s = 0; s < kSlots; s++) {
+    if (int rc = grow(&C.y[s], &C.cap_y[s], Cn * m)) return rc;
+    if (int rc = grow(&C.coef[s], &C.cap_coef[s], Cn * n)) return rc;
+    if (int rc = grow(&C.rn[s], &C.cap_rn[s], Cn)) return rc;
+    if (int rc = grow(&C.r2[s], &C.cap_r2[s], Cn)) return rc;
+    if (int rc = grow(&C.st[s], &C.cap_st[s], Cn)) return rc;
+    if (int rc = grow(&C.it[s], &C.cap_it[s], Cn)) return rc;
   }
-  if ((size_t)m * n > C.cap_B) {
-    if (C.B) cudaFree(C.B);
-    PNBI_CUDA(cudaMalloc(&C.B, (size_t)m * n * sizeof(double)));
-    C.cap_B = (size_t)m * n;
-  }
-  if ((size_t)n * BW > C.cap_rtr) {
-    if (C.rtr) cudaFree(C.rtr);
-    PNBI_CUDA(cudaMalloc(&C.rtr, (size_t)n * BW * sizeof(double)));
-    C.cap_rtr = (size_t)n * BW;
-  }
+  if (int rc = grow(&C.B, &C.cap_B, (size_t)m * n)) return rc;
+  if (int rc = grow(&C.rtr, &C.cap_rtr, (size_t)n * BW)) return rc;
   PNBI_CUDA(cudaMemcpy(C.B, p->basis, (size_t)m * n * sizeof(double), cudaMemcpyHostToDevice));
   PNBI_CUDA(cudaMemcpy(C.rtr, p->rtr_band, (size_t)n * BW * sizeof(double), cudaMemcpyHostToDevice));
   const size_t NV = (size_t)p->n_vox;
@@ -322,7 +324,8 @@ extern "C" int64_t pnb_nnls_last_redo_count(int device) {
   NnlsCtx &C = g_ctx[device];
   if (!C.last_redo) return 0;
   unsigned long long v = 0;
-  if (cudaSetDevice(device) != cudaSuccess) return -1;
+  pnbi::DeviceScope dev_scope(device);
+  if (dev_scope.error() != cudaSuccess) return -1;
   if (cudaMemcpy(&v, C.last_redo, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
   return (int64_t)v;
 }

@@ -44,7 +44,8 @@ extern "C" int pnb_resize2d_device(const pnb_resize_problem *p, void *cuda_strea
 extern "C" int pnb_resize2d_host(const pnb_resize_problem *p, int device) {
   if (int rc = check(p)) return rc;
   if (pnb_device_count() <= device || device < 0) return pnbi::fail(PNB_E_NODEVICE, "no such CUDA device");
-  PNBI_CUDA(cudaSetDevice(device));
+  pnbi::DeviceScope dev_scope(device);
+  PNBI_CUDA(dev_scope.error());
   const size_t esz = p->dtype == 0 ? 8 : 4;
   const size_t nsrc = (size_t)p->src_h * p->src_w * p->inner * esz;
   const size_t ndst = (size_t)p->dst_h * p->dst_w * p->inner * esz;

@@ -151,7 +151,8 @@ extern "C" int pnb_segment_means_device(const pnb_segmeans_problem *p, void *cud
 extern "C" int pnb_segment_means_host(const pnb_segmeans_problem *p, int device) {
   if (int rc = check(p)) return rc;
   if (pnb_device_count() <= device || device < 0) return pnbi::fail(PNB_E_NODEVICE, "no such CUDA device");
-  PNBI_CUDA(cudaSetDevice(device));
+  pnbi::DeviceScope dev_scope(device);
+  PNBI_CUDA(dev_scope.error());
   const size_t nv = (size_t)p->n_vox, T = (size_t)p->n_labels * p->n_b;
   double *img = nullptr, *means = nullptr;
   int *lab = nullptr;

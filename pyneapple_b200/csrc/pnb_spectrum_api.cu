@@ -67,7 +67,8 @@ extern "C" int pnb_spectrum_peaks_host(const pnb_spectrum_problem *p, int device
   if (int rc = check(p)) return rc;
   if (p->n_vox == 0) return 0;
   if (pnb_device_count() <= device || device < 0) return pnbi::fail(PNB_E_NODEVICE, "no such CUDA device");
-  PNBI_CUDA(cudaSetDevice(device));
+  pnbi::DeviceScope dev_scope(device);
+  PNBI_CUDA(dev_scope.error());
   if (chunk_vox <= 0) chunk_vox = 1 << 18;
   if (chunk_vox > p->n_vox) chunk_vox = p->n_vox;
   const size_t C = (size_t)chunk_vox, n = (size_t)p->n_bins, P = (size_t)p->max_peaks, K = (size_t)p->n_cutoffs;

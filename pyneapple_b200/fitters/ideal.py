@@ -17,7 +17,7 @@ import time
 
 import numpy as np
 
-from .. import engine
+from .. import _lib, engine
 from .. import validation as V
 from ..resize import METHODS, interpolate_array
 from .base import BaseFitter, PixelIndices
@@ -84,10 +84,21 @@ class IDEALFitter(BaseFitter):
     def fit(self, xdata, image, segmentation=None, z_range=None, **fit_kwargs):
         """``z_range=(z0, z1)`` restricts the fit to a z-slab (multi-GPU sharding: the
         in-plane resampling never couples slices)."""
-        import torch
-
         if not hasattr(self.solver, "fit_device"):
             raise TypeError("IDEALFitter needs a B200 CurveFitSolver (no CPU fallback)")
+        # fit_kwargs: the reference forwards them to solver.fit at every level (ideal.py:240-242).
+        # run_pipeline passes fixed_param_maps=None, which the solver swallows; per-voxel arrays cannot
+        # be forwarded (their length would have to match every level's voxel count — the reference
+        # raises a shape error at the first level that differs), so they are rejected up front.
+        for key, val in fit_kwargs.items():
+            if val is not None:
+                raise NotImplementedError(
+                    f"IDEALFitter.fit(..., {key}=...): per-call solver arguments are not supported by the "
+                    "device-resident IDEAL driver (per-voxel arrays cannot match every resolution level)"
+                )
+        _lib.require_device()  # EngineError, not a torch error, when there is no GPU
+        import torch
+
         xdata = np.asarray(xdata)
         V.validate_xdata(xdata)
         V.validate_data_shapes(xdata, image)
@@ -111,6 +122,13 @@ class IDEALFitter(BaseFitter):
         if self.ideal_dims == 2:
             dim_steps = np.hstack([self.dim_steps, np.full((self.dim_steps.shape[0], 1), Z)])
         else:
+            # ideal_dims = 3: the reference still resamples in-plane only (ideal.py:313-319) and then
+            # indexes slices that do not exist when a level's Z differs from the image's
+            if not np.all(self.dim_steps[:, 2] == Z):
+                raise ValueError(
+                    "ideal_dims=3 with a slice count that differs from the image's is not supported: "
+                    "the resampling is in-plane (x, y) only"
+                )
             dim_steps = self.dim_steps
         solver = self.solver
         names = solver.model.param_names
@@ -121,7 +139,10 @@ class IDEALFitter(BaseFitter):
         lo_vals = torch.tensor([solver.bounds[n][0] for n in names], **f64)
         hi_vals = torch.tensor([solver.bounds[n][1] for n in names], **f64)
         tol_vals = torch.tensor([self.step_tol[n] for n in names], **f64)
-        img_d = engine.to_device(np.ascontiguousarray(image, dtype=np.float64), dev)
+        # resample in the image's own dtype like cv2.resize does (float32 stays float32, anything that is
+        # not a float becomes float32, ideal.py:310-311); the fit upcasts to float64
+        img_dtype = image.dtype if image.dtype in (np.float32, np.float64) else np.dtype(np.float32)
+        img_d = engine.to_device(np.ascontiguousarray(image, dtype=img_dtype), dev)
         seg = segmentation[..., None] if segmentation.ndim == 3 else segmentation
         seg_d = engine.to_device(np.ascontiguousarray(seg), dev)
         if not seg_d.dtype.is_floating_point:
@@ -147,7 +168,7 @@ class IDEALFitter(BaseFitter):
             if not bool(mask.any()):
                 mask = torch.ones(shape, dtype=torch.bool, device=dev)
             coords = mask.nonzero()  # (n_pix, 3), C order over (x, y, z) like np.where
-            y = img_l[mask]  # (n_pix, n_b)
+            y = img_l[mask].to(torch.float64)  # (n_pix, n_b)
             if step_index > 0:
                 p0 = p0_map[mask].T.contiguous()
                 lb = lb_map[mask].T.contiguous()

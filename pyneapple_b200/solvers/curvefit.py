@@ -187,6 +187,22 @@ class CurveFitSolver(BaseSolver):
             jac_mode = engine.JAC_ANALYTIC if fixed_names else engine.JAC_TWO_POINT
         else:
             jac_mode = engine.JAC_ANALYTIC if self.jac == "analytic" else engine.JAC_TWO_POINT
+        xs_full, x_scale_jac = self._x_scale_args(all_names, model_names)
+        res = engine.trf_fit(
+            desc, xdata, ydata, P0, LB, UB, frozen,
+            max_nfev=self.max_iter if max_nfev is None else max_nfev, ftol=self.tol,
+            xtol=self.solver_kwargs.get("xtol", 1e-8), gtol=self.solver_kwargs.get("gtol", 1e-8),
+            jac_mode=jac_mode, x_scale=xs_full, x_scale_jac=x_scale_jac,
+            want_cov=self.want_cov, device=self.device, chunk_vox=self.chunk_vox,
+            out=self._pinned_out(len(all_names), len(all_names) - len(fixed_names), n_pixels, ydata),
+            method=method or self._ls_method(),
+        )
+        self._free_rows = [all_names.index(n) for n in free_names]
+        return res, free_names
+
+    def _x_scale_args(self, all_names, model_names):
+        """``x_scale`` of ``least_squares`` (forwarded by the reference, curvefit.py:305) as the
+        engine wants it: a vector over ``all_names`` (1.0 for fixed parameters) and the 'jac' flag."""
         x_scale = self.solver_kwargs.get("x_scale", 1.0)
         x_scale_jac = isinstance(x_scale, str)
         if x_scale_jac and x_scale != "jac":
@@ -199,17 +215,7 @@ class CurveFitSolver(BaseSolver):
             xs_full = np.ones(len(all_names))
             for i, n in enumerate(model_names):
                 xs_full[all_names.index(n)] = xs[i]
-        res = engine.trf_fit(
-            desc, xdata, ydata, P0, LB, UB, frozen,
-            max_nfev=self.max_iter if max_nfev is None else max_nfev, ftol=self.tol,
-            xtol=self.solver_kwargs.get("xtol", 1e-8), gtol=self.solver_kwargs.get("gtol", 1e-8),
-            jac_mode=jac_mode, x_scale=xs_full, x_scale_jac=x_scale_jac,
-            want_cov=self.want_cov, device=self.device, chunk_vox=self.chunk_vox,
-            out=self._pinned_out(len(all_names), len(all_names) - len(fixed_names), n_pixels, ydata),
-            method=method or self._ls_method(),
-        )
-        self._free_rows = [all_names.index(n) for n in free_names]
-        return res, free_names
+        return xs_full, x_scale_jac
 
     # ------------------------------------------------------------------
     def fit_device(self, xdata, y_dev, p0=None, bounds=None, pixel_fixed_params=None, want_cov=None):
@@ -263,10 +269,12 @@ class CurveFitSolver(BaseSolver):
             jac_mode = engine.JAC_ANALYTIC if fixed_names else engine.JAC_TWO_POINT
         else:
             jac_mode = engine.JAC_ANALYTIC if self.jac == "analytic" else engine.JAC_TWO_POINT
+        xs_full, x_scale_jac = self._x_scale_args(all_names, model_names)
         res = engine.trf_fit(
             desc, np.asarray(xdata, float), y_dev, P0, LB, UB, frozen, max_nfev=self.max_iter,
             ftol=self.tol, xtol=self.solver_kwargs.get("xtol", 1e-8),
             gtol=self.solver_kwargs.get("gtol", 1e-8), jac_mode=jac_mode,
+            x_scale=xs_full, x_scale_jac=x_scale_jac,
             want_cov=self.want_cov if want_cov is None else want_cov, device=self.device,
             method=self._ls_method(),
         )

@@ -141,3 +141,45 @@ def test_solver_fit_spectrum_peaks_equals_fit_then_postprocess():
         assert np.array_equal(fused[k], v, equal_nan=True), k
     assert np.array_equal(fused["status"], solver.status_)
     np.testing.assert_array_equal(fused["residual"], solver.diagnostics_["residual"])
+
+
+def test_fused_pipeline_with_large_chunks_orders_uploads_after_the_kernels():
+    """Chunks of 8 MB take the staged (pageable) ``pnb_upload`` path, and with four of them the
+    caching allocator hands chunk i the block of chunk i-2 while that chunk's NNLS kernel may still
+    be reading it: the upload has to be ordered after the work queued on the stream."""
+    from pyneapple_b200 import models, spectrum, synth
+    from pyneapple_b200.solvers import NNLSSolver
+
+    cfg = synth.CONFIGS["C3"]
+    b, y, _ = synth.sample_voxels(cfg, 4 * 65536 + 777)
+    assert y[:65536].nbytes >= (4 << 20)
+    model = models.NNLSModel(d_range=(0.0008, 0.5), n_bins=250)
+    solver = NNLSSolver(model=model, reg_order=2, mu=0.02, max_iter=250)
+    fused = solver.fit_spectrum_peaks(b, y, height=0.1, chunk_vox=65536)
+    solver.fit(b, y)
+    two = spectrum.find_spectrum_peaks_batch(solver.params_["coefficients"], model.bins, 0.1, True)
+    for k, v in two.items():
+        assert np.array_equal(fused[k], v, equal_nan=True), k
+    assert np.array_equal(fused["status"], solver.status_)
+    np.testing.assert_array_equal(fused["residual"], solver.diagnostics_["residual"])
+
+
+def test_to_device_loop_does_not_overwrite_memory_a_queued_kernel_still_reads():
+    import torch
+
+    from pyneapple_b200 import engine, models, synth
+    from pyneapple_b200.solvers.nnls import regularization_matrix
+
+    cfg = synth.CONFIGS["C3"]
+    b, y, _ = synth.sample_voxels(cfg, 3 * 49152)
+    model = models.NNLSModel(d_range=(0.0008, 0.5), n_bins=250)
+    basis, R = model.get_basis(b), regularization_matrix(250, 2, 0.02)
+    whole = engine.nnls_fit(basis, R, torch.as_tensor(y).cuda(), 250)["coefficients"].cpu().numpy()
+    got = []
+    for s0 in range(0, y.shape[0], 49152):
+        yd = engine.to_device(y[s0:s0 + 49152], torch.device("cuda", 0))  # 6 MB: staged upload
+        fit = engine.nnls_fit(basis, R, yd, 250)
+        got.append(fit["coefficients"])
+        del yd, fit  # the block goes back to the allocator while the kernel is still queued
+    got = torch.cat(got).cpu().numpy()
+    assert np.array_equal(got, whole)
