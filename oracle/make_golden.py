@@ -408,6 +408,100 @@ def case_dogbox():
     _run_curvefit("dbx_triexp_reduced", "triexp", {}, bb, yy, p05, b5, method="dogbox")
 
 
+def _t1_signal(model, b, truth, sigma, rng):
+    """Noisy signals of a reference model for per-voxel truth vectors (n_vox, n_all)."""
+    y = np.stack([model.forward(b, *row) for row in truth])
+    return y + rng.normal(0.0, sigma, y.shape)
+
+
+def case_t1():
+    """T1 / STEAM variants (models/monoexp.py:120-163, model_functions/multiexp.py:210-302), T1 fitted,
+    model-fixed and per-voxel fixed, for method trf and dogbox.  TR / TM / T1 in ms."""
+    rng = np.random.default_rng(21)
+    tr, tm = 2500.0, 30.0
+    b16 = synth.CONFIGS["C2"].bvalues
+    b24 = synth.CONFIGS["C5"].bvalues
+    n = 128
+
+    def extras(model):
+        return dict(t1_mode=2 if model.fit_t1_steam else 1, tr=tr, tm=tm if model.fit_t1_steam else 0.0)
+
+    def run(name, kind, mk, b, y, p0, bounds, **kw):
+        model = MODELS[kind](**mk)
+        _run_curvefit(name, kind, mk, b, y, p0, bounds, **kw)
+        # re-save with the T1 description added (np.savez has no append)
+        path = os.path.join(GOLD, name + ".npz")
+        g = dict(np.load(path))
+        g.update({k: np.asarray(v) for k, v in extras(model).items()})
+        np.savez_compressed(path, **g)
+
+    # ---- mono-exponential -------------------------------------------------------------------
+    s0, d, t1 = rng.uniform(800, 1200, n), rng.uniform(8e-4, 2e-3, n), rng.uniform(900, 1500, n)
+    p0 = {"S0": 1000.0, "D": 1e-3, "T1": 1200.0}
+    bd = {"S0": (1.0, 5000.0), "D": (1e-5, 0.1), "T1": (100.0, 5000.0)}
+    for tag, mk in (("t1", dict(fit_t1=True, repetition_time=tr)),
+                    ("steam", dict(fit_t1_steam=True, repetition_time=tr, mixing_time=tm))):
+        m = MonoExpModel(**mk)
+        y = _t1_signal(m, b16, np.stack([s0, d, t1], 1), 3.0, rng)
+        run(f"trf_mono_{tag}", "monoexp", mk, b16, y, p0, bd)                      # T1 fitted (S0 x C(T1) only)
+        run(f"trf_mono_{tag}_pixfixed", "monoexp", mk, b16, y, p0, bd, pixel_fixed={"T1": t1})
+        mkf = dict(mk, fixed_params={"T1": 1200.0})
+        p0f = {k: v for k, v in p0.items() if k != "T1"}
+        bdf = {k: v for k, v in bd.items() if k != "T1"}
+        run(f"trf_mono_{tag}_modelfixed", "monoexp", mkf, b16, y, p0f, bdf)
+        run(f"dbx_mono_{tag}_pixfixed", "monoexp", mk, b16, y, p0, bd, pixel_fixed={"T1": t1}, method="dogbox")
+    # ---- bi-exponential ----------------------------------------------------------------------
+    f1, d1, d2 = rng.uniform(0.05, 0.4, n), rng.uniform(5e-4, 2.5e-3, n), rng.uniform(0.01, 0.1, n)
+    s0 = rng.uniform(800, 1200, n)
+    # reduced mode: the amplitude is fixed at 1, so T1 is identifiable from C(T1) alone
+    mk = dict(fit_t1=True, repetition_time=tr)
+    m = BiExpModel(**mk)
+    y = _t1_signal(m, b16, np.stack([f1, d1, d2, t1], 1), 0.005, rng)
+    p0 = {"f1": 0.2, "D1": 0.001, "D2": 0.02, "T1": 1200.0}
+    bd = {"f1": (0.01, 0.99), "D1": (1e-5, 0.003), "D2": (0.003, 0.3), "T1": (100.0, 5000.0)}
+    run("trf_biexp_reduced_t1", "biexp", mk, b16, y, p0, bd)
+    run("dbx_biexp_reduced_t1", "biexp", mk, b16, y, p0, bd, method="dogbox")
+    mk = dict(fit_s0=True, fit_t1_steam=True, repetition_time=tr, mixing_time=tm)
+    m = BiExpModel(**mk)
+    y = _t1_signal(m, b16, np.stack([f1, d1, d2, s0, t1], 1), 3.0, rng)
+    p0 = dict(p0, S0=1000.0)
+    bd = dict(bd, S0=(1.0, 5000.0))
+    run("trf_biexp_s0_steam_pixfixed", "biexp", mk, b16, y, p0, bd, pixel_fixed={"T1": t1})
+    run("dbx_biexp_s0_steam_pixfixed", "biexp", mk, b16, y, p0, bd, pixel_fixed={"T1": t1}, method="dogbox")
+    mk = dict(fit_reduced=False, fit_t1=True, repetition_time=tr, fixed_params={"T1": 1300.0})
+    m = BiExpModel(fit_reduced=False, fit_t1=True, repetition_time=tr)
+    y = _t1_signal(m, b16, np.stack([f1, d1, 1 - f1, d2, np.full(n, 1300.0)], 1), 0.005, rng)
+    p0 = {"f1": 0.2, "D1": 0.001, "f2": 0.8, "D2": 0.02}
+    bd = {"f1": (0.0, 1.5), "D1": (1e-5, 0.003), "f2": (0.0, 1.5), "D2": (0.003, 0.3)}
+    run("trf_biexp_full_t1_modelfixed", "biexp", mk, b16, y, p0, bd)
+    # ---- tri-exponential ---------------------------------------------------------------------
+    n3 = 96
+    f1, f2 = rng.uniform(0.05, 0.25, n3), rng.uniform(0.1, 0.35, n3)
+    d1, d2, d3 = rng.uniform(0.05, 0.2, n3), rng.uniform(5e-3, 2e-2, n3), rng.uniform(5e-4, 2e-3, n3)
+    t13 = rng.uniform(900, 1500, n3)
+    p0 = {"f1": 0.15, "D1": 0.1, "f2": 0.25, "D2": 0.01, "D3": 0.001, "T1": 1200.0}
+    bd = {"f1": (0.0, 1.0), "D1": (0.03, 0.5), "f2": (0.0, 1.0), "D2": (0.003, 0.03), "D3": (1e-4, 0.003),
+          "T1": (100.0, 5000.0)}
+    mk = dict(fit_t1_steam=True, repetition_time=tr, mixing_time=tm)
+    m = TriExpModel(**mk)
+    y = _t1_signal(m, b24, np.stack([f1, d1, f2, d2, d3, t13], 1), 0.004, rng)
+    run("trf_triexp_reduced_steam", "triexp", mk, b24, y, p0, bd)
+    run("dbx_triexp_reduced_steam_pixfixed", "triexp", mk, b24, y, p0, bd, pixel_fixed={"T1": t13}, method="dogbox")
+    mk = dict(fit_s0=True, fit_t1=True, repetition_time=tr)
+    m = TriExpModel(**mk)
+    s03 = rng.uniform(800, 1200, n3)
+    y = _t1_signal(m, b24, np.stack([f1, d1, f2, d2, d3, s03, t13], 1), 3.0, rng)
+    run("trf_triexp_s0_t1_pixfixed", "triexp", mk, b24, y, dict(p0, S0=900.0), dict(bd, S0=(1.0, 5000.0)),
+        pixel_fixed={"T1": t13})
+    mk = dict(fit_reduced=False, fit_t1_steam=True, repetition_time=tr, mixing_time=tm, fixed_params={"T1": 1100.0})
+    m = TriExpModel(fit_reduced=False, fit_t1_steam=True, repetition_time=tr, mixing_time=tm)
+    y = _t1_signal(m, b24, np.stack([f1, d1, f2, d2, 1 - f1 - f2, d3, np.full(n3, 1100.0)], 1), 0.004, rng)
+    p0f = {"f1": 0.15, "D1": 0.1, "f2": 0.25, "D2": 0.01, "f3": 0.6, "D3": 0.001}
+    bf = {"f1": (0.0, 1.0), "D1": (0.03, 0.5), "f2": (0.0, 1.0), "D2": (0.003, 0.03), "f3": (0.0, 1.0),
+          "D3": (1e-4, 0.003)}
+    run("trf_triexp_full_steam_modelfixed", "triexp", mk, b24, y, p0f, bf)
+
+
 CASES = {k[5:]: v for k, v in globals().items() if k.startswith("case_")}
 
 if __name__ == "__main__":

@@ -41,7 +41,47 @@ DBX_CASES = {
     "dbx_mono_c1": ("monoexp", "s0"),
     "dbx_triexp_reduced": ("triexp", "reduced"),
 }
-MODEL_FIXED = {"trf_biexp_s0_modelfixed_D2": {"D2": 0.03}}
+# T1 / STEAM goldens (oracle/make_golden.py: case_t1); t1_mode / tr / tm are stored in the file
+TRF_T1_CASES = {
+    "trf_mono_t1": ("monoexp", "s0"),
+    "trf_mono_t1_pixfixed": ("monoexp", "s0"),
+    "trf_mono_t1_modelfixed": ("monoexp", "s0"),
+    "trf_mono_steam": ("monoexp", "s0"),
+    "trf_mono_steam_pixfixed": ("monoexp", "s0"),
+    "trf_mono_steam_modelfixed": ("monoexp", "s0"),
+    "trf_biexp_reduced_t1": ("biexp", "reduced"),
+    "trf_biexp_s0_steam_pixfixed": ("biexp", "s0"),
+    "trf_biexp_full_t1_modelfixed": ("biexp", "full"),
+    "trf_triexp_reduced_steam": ("triexp", "reduced"),
+    "trf_triexp_s0_t1_pixfixed": ("triexp", "s0"),
+    "trf_triexp_full_steam_modelfixed": ("triexp", "full"),
+}
+DBX_T1_CASES = {
+    "dbx_mono_t1_pixfixed": ("monoexp", "s0"),
+    "dbx_mono_steam_pixfixed": ("monoexp", "s0"),
+    "dbx_biexp_reduced_t1": ("biexp", "reduced"),
+    "dbx_biexp_s0_steam_pixfixed": ("biexp", "s0"),
+    "dbx_triexp_reduced_steam_pixfixed": ("triexp", "reduced"),
+}
+# T1 fitted next to a free amplitude: S0 and T1 enter only through S0 * C(T1), so the minimiser is a
+# curve; parity is checked on the identifiable quantities (D, S0 * C(T1)) and the residual
+T1_AMPLITUDE_ONLY = {"trf_mono_t1", "trf_mono_steam"}
+MODEL_FIXED = {"trf_biexp_s0_modelfixed_D2": {"D2": 0.03},
+               "trf_mono_t1_modelfixed": {"T1": 1200.0}, "trf_mono_steam_modelfixed": {"T1": 1200.0},
+               "trf_biexp_full_t1_modelfixed": {"T1": 1300.0}, "trf_triexp_full_steam_modelfixed": {"T1": 1100.0}}
+
+
+def t1_kwargs(name):
+    """Model keyword arguments (fit_t1 / fit_t1_steam / repetition_time / mixing_time) of a golden."""
+    g = load(name)
+    if "t1_mode" not in g.files:
+        return {}
+    kw = {"repetition_time": float(g["tr"])}
+    if int(g["t1_mode"]) == 2:
+        kw.update(fit_t1_steam=True, mixing_time=float(g["tm"]))
+    else:
+        kw["fit_t1"] = True
+    return kw
 
 
 def load(name):
@@ -90,6 +130,8 @@ def full_problem(name):
         uses_fd=not (pix_fixed or mfixed), pix_fixed=pix_fixed, mfixed=mfixed,
         p0_vec=g["p0"], lb_vec=g["lb"], ub_vec=g["ub"],
         per_voxel="p0_arr" in g.files,
+        t1_mode=int(g["t1_mode"]) if "t1_mode" in g.files else 0,
+        tr=float(g["tr"]) if "tr" in g.files else 0.0, tm=float(g["tm"]) if "tm" in g.files else 0.0,
     )
 
 

@@ -96,6 +96,7 @@ extern "C" int pnbh_trf_fit(int model_id, int t1_mode, double tr, double tm, int
 #define CASE(ID, T) if (model_id == ID && t1_mode == T) { run_all<Model<ID, T>>(O, nb, b, n_vox, y, p0, lb, ub, params, cov, status, nfev, cost); return 0; }
   CASE(0, 0) CASE(1, 0) CASE(2, 0) CASE(3, 0) CASE(4, 0) CASE(5, 0) CASE(6, 0)
   CASE(0, 1) CASE(1, 1) CASE(3, 1) CASE(0, 2) CASE(3, 2) CASE(4, 1) CASE(6, 2)
+  CASE(2, 1) CASE(4, 2) CASE(6, 1) CASE(5, 2)
   return -1;
 }
 

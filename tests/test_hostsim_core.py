@@ -9,7 +9,8 @@ from __future__ import annotations
 import numpy as np
 import pytest
 
-from _util import DBX_CASES, TRF_CASES, full_problem, rel_err
+from _util import (DBX_CASES, DBX_T1_CASES, T1_AMPLITUDE_ONLY, TRF_CASES, TRF_T1_CASES, full_problem,
+                   rel_err)
 from hostsim import hostsim
 from oracle import c_oracle
 
@@ -147,3 +148,36 @@ def test_dogbox_t1_variants_and_x_scale_jac_against_c_oracle():
                          method="dogbox")
     assert ((a["status"] > 0) == (c["status"] > 0)).all()
     assert rel_err(a["params"], c["params"]).max() < 1e-5
+
+
+def _t1_amplitude(par, t1_mode, tr, tm, i_s0, i_t1):
+    f = 1.0 - np.exp(-tr / par[:, i_t1])
+    if t1_mode == 2:
+        f = f * np.exp(-tm / par[:, i_t1])
+    return par[:, i_s0] * f
+
+
+@pytest.mark.parametrize("name", sorted(TRF_T1_CASES) + sorted(DBX_T1_CASES))
+def test_t1_goldens_core_matches_reference(name):
+    """T1 / STEAM variants against goldens produced by the reference's own models and solver
+    (models/monoexp.py:120-163, model_functions/multiexp.py:210-302)."""
+    cases = TRF_T1_CASES if name in TRF_T1_CASES else DBX_T1_CASES
+    kind, m = cases[name]
+    P = full_problem(name)
+    jm = 1 if P["uses_fd"] else 0
+    r = hostsim.trf_fit(c_oracle.MODEL_IDS[(kind, m)], P["b"], P["y"], P["P0"], P["LB"], P["UB"],
+                        frozen=P["frozen"], ftol=P["tol"], max_nfev=P["max_iter"], jac_mode=jm,
+                        t1_mode=P["t1_mode"], tr=P["tr"], tm=P["tm"], method=1 if name.startswith("dbx") else 0)
+    free = [i for i in range(len(P["all_names"])) if not P["frozen"][i]]
+    par = r["params"][:, free]
+    assert ((r["status"] > 0) == P["ref_success"]).all()
+    ok = P["ref_success"]
+    if name in T1_AMPLITUDE_ONLY:
+        ref = P["ref_params"]
+        assert rel_err(par[ok, 1], ref[ok, 1]).max() < 1e-4
+        amp = _t1_amplitude(par, P["t1_mode"], P["tr"], P["tm"], 0, 2)
+        amp_ref = _t1_amplitude(ref, P["t1_mode"], P["tr"], P["tm"], 0, 2)
+        assert rel_err(amp[ok], amp_ref[ok]).max() < 1e-4
+        return
+    err = rel_err(par[ok], P["ref_params"][ok]).max(axis=1)
+    assert (err > 1e-4).sum() == 0, (int((err > 1e-4).sum()), float(err.max()))

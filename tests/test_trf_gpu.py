@@ -5,7 +5,8 @@ from __future__ import annotations
 import numpy as np
 import pytest
 
-from _util import DBX_CASES, MODEL_FIXED, TRF_CASES, full_problem, load, rel_err
+from _util import (DBX_CASES, DBX_T1_CASES, MODEL_FIXED, T1_AMPLITUDE_ONLY, TRF_CASES, TRF_T1_CASES,
+                   full_problem, load, rel_err, t1_kwargs)
 
 pytestmark = pytest.mark.gpu
 
@@ -22,6 +23,7 @@ UNIDENTIFIABLE = {"trf_triexp_full": 2}
 
 def _make_solver(name, kind, mode, P, **kw):
     mk = {} if kind == "monoexp" else dict(MODE_KW[mode])
+    mk.update(t1_kwargs(name))
     if name in MODEL_FIXED:
         mk["fixed_params"] = MODEL_FIXED[name]
     model = MODEL_CLS[kind](**mk)
@@ -51,6 +53,19 @@ def test_golden_parity(name, jac):
 def test_dogbox_golden_parity(name):
     """method = "dogbox" (scipy/optimize/_lsq/dogbox.py) against the reference run with that method."""
     _golden_parity(name, DBX_CASES, jac="reference", method="dogbox")
+
+
+@pytest.mark.parametrize("name", sorted(TRF_T1_CASES))
+@pytest.mark.parametrize("jac", ["reference", "analytic"])
+def test_t1_steam_golden_parity(name, jac):
+    """T1 / STEAM model variants (models/monoexp.py:120-163, model_functions/multiexp.py:210-302):
+    T1 fitted, model-fixed and per-voxel fixed, against the reference's own outputs."""
+    _golden_parity(name, TRF_T1_CASES, jac=jac)
+
+
+@pytest.mark.parametrize("name", sorted(DBX_T1_CASES))
+def test_t1_steam_dogbox_golden_parity(name):
+    _golden_parity(name, DBX_T1_CASES, jac="reference", method="dogbox")
 
 
 def test_dogbox_large_sample_against_the_scipy_port():
@@ -119,6 +134,19 @@ def _golden_parity(name, cases, jac, **solver_kw):
         assert msgs == [P["messages"][int(i)] for i in np.where(fail)[0]]
     ok = P["ref_success"]
     if not ok.any():
+        return
+    if name in T1_AMPLITUDE_ONLY:
+        # S0 and T1 enter only through S0 * C(T1): compare D, that product, and the residual
+        def amp(p):
+            f = 1.0 - np.exp(-P["tr"] / p[:, 2])
+            return p[:, 0] * (f * np.exp(-P["tm"] / p[:, 2]) if P["t1_mode"] == 2 else f)
+        assert rel_err(got[ok, 1], P["ref_params"][ok, 1]).max() <= 1e-4
+        assert rel_err(amp(got[ok]), amp(P["ref_params"][ok])).max() <= 1e-4
+        ours = {n: got[ok][:, i] for i, n in enumerate(free)}
+        ref = {n: P["ref_params"][ok][:, i] for i, n in enumerate(free)}
+        r_ours = _residual_norm(model, P["b"], P["y"][ok], ours, {})
+        r_ref = _residual_norm(model, P["b"], P["y"][ok], ref, {})
+        assert (r_ours <= r_ref * (1 + 1e-7) + 1e-12).all()
         return
     # parameters within 1e-4 relative of the reference (north_star tolerance)
     err = rel_err(got[ok], P["ref_params"][ok]).max(axis=1)
