@@ -51,6 +51,10 @@ struct NnlsCtx {
 NnlsCtx g_ctx[16];
 // PNB_NNLS_NO_V3=1 in the environment keeps the second-generation fast kernel (A/B measurements)
 const bool g_disable_v3 = [] { const char *e = std::getenv("PNB_NNLS_NO_V3"); return e && e[0] == '1'; }();
+// certification threshold of the fast path (NnlsDeviceArgs::cert_ztol): a would-be coefficient above
+// it sends the voxel to the robust path.  2e-7 keeps the worst case a factor 5 inside the 1e-6
+// absolute parity tolerance; PNB_NNLS_CERT_ZTOL overrides it (measurements).
+const double g_cert_ztol = [] { const char *e = std::getenv("PNB_NNLS_CERT_ZTOL"); return e ? std::atof(e) : 2e-7; }();
 std::mutex g_mu;
 
 // (re)allocate a device buffer of `need` elements; pointer and capacity stay consistent on failure
@@ -155,6 +159,7 @@ int launch(NnlsCtx &C, const pnb_nnls_problem *p, const double *B, const double 
   a.m = m; a.n = n; a.W = W; a.maxiter = p->max_iter; a.n_vox = n_vox;
   a.B = B; a.rtr = rtr; a.y = y; a.coef = coef; a.rnorm = rn; a.status = st; a.iters = it; a.r2 = r2;
   a.scratch = C.scratch[slot];
+  a.cert_ztol = g_cert_ztol;
   a.redo_count = ctr + 1; a.redo_list = C.redo_list[slot];
   C.last_redo = use_fast ? ctr + 1 : nullptr;
   if (use_fast) {

@@ -61,6 +61,10 @@ struct NnlsDeviceArgs {
   // a work-list launch only runs when work_count lies in [work_min, work_max] (lets the host
   // enqueue two differently shaped launches and have the device pick one without a sync)
   unsigned long long work_min, work_max;
+  // fast path, certification: a bin whose dual is positive but below the rounding threshold at the
+  // polished point would enter with the coefficient dual / pivot^2; above cert_ztol the voxel is
+  // handed to the robust path (see nnls_v3_kernel, PH_CHECK)
+  double cert_ztol;
 };
 
 // column-major packed lower triangle with leading dimension ld: element (i, c), i >= c

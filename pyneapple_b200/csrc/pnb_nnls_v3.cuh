@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
   __syncthreads();
 
   const int kcap = n_e1 > 0 ? (n_e2 > 0 ? KC : K1) : KB;
-  enum { PH_INIT = 0, PH_ITER = 1, PH_POLISH = 2, PH_VERIFY = 3 };
+  enum { PH_INIT = 0, PH_ITER = 1, PH_POLISH = 2, PH_VERIFY = 3, PH_CHECK = 4 };
 
   // Every voxel is a sequence of TRIPS through one loop body whose big blocks (residual, dual,
   // H * vector, rank-one update of H) exist exactly once in the instruction stream: the first
@@ -171,7 +171,9 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
     double *H1 = nullptr, *H2 = nullptr;  // extension areas, biased so that H? + i (i + 1) / 2 is row i
     int phase = PH_INIT, pass = 0;
     bool do_dual = true;
-    double hmax = 0.0, rel = 1.0;
+    double hmax = 0.0, rel = 1.0, zscale = 0.0;
+    int jc = -1;          // PH_CHECK: the candidate whose would-be coefficient is being computed
+    double wjc = 0.0;     // ... and its dual
 
     auto Htier = [&](int i) -> double * { return i < KB ? Hb : (i < K1 ? H1 : H2); };
     auto Hrow = [&](int i) -> double * { return Htier(i) + (i * (i + 1)) / 2; };
@@ -282,22 +284,32 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
       int j = -1, jrow = 0;
       double wj = 0.0;
       if (phase != PH_POLISH) {
-        // warp-wide arg-max of the positive duals; the lowest bin wins ties
-        const unsigned hi = (unsigned)__double2hiint(best);
-        const unsigned mhi = __reduce_max_sync(FULL, hi);
-        const unsigned lo = (hi == mhi) ? (unsigned)__double2loint(best) : 0u;
-        const unsigned mlo = __reduce_max_sync(FULL, lo);
-        const unsigned win = __ballot_sync(FULL, bq >= 0 && hi == mhi && lo == mlo);
-        if (win) {
-          j = __shfl_sync(FULL, NQ * lane + bq, __ffs(win) - 1);
-          wj = __hiloint2double((int)mhi, (int)mlo);
+        if (phase == PH_CHECK) {
+          j = jc; wj = wjc;
+        } else {
+          // warp-wide arg-max of the positive duals; the lowest bin wins ties
+          const unsigned hi = (unsigned)__double2hiint(best);
+          const unsigned mhi = __reduce_max_sync(FULL, hi);
+          const unsigned lo = (hi == mhi) ? (unsigned)__double2loint(best) : 0u;
+          const unsigned mlo = __reduce_max_sync(FULL, lo);
+          const unsigned win = __ballot_sync(FULL, bq >= 0 && hi == mhi && lo == mlo);
+          if (win) {
+            j = __shfl_sync(FULL, NQ * lane + bq, __ffs(win) - 1);
+            wj = __hiloint2double((int)mhi, (int)mlo);
+          }
         }
         if (phase == PH_INIT) { hmax = wj; phase = PH_ITER; }
         if (phase == PH_VERIFY) {
           // duals of bins that sit at the optimum are zero to rounding (+-1e-13 relative) in every
           // voxel; anything clearly positive means this is not a Kuhn-Tucker point
-          if (wj > 1e-12 * hmax) mode = kNnlsRedo;
-          break;
+          if (wj > 1e-12 * hmax) { mode = kNnlsRedo; break; }
+          // A positive dual below that threshold may be rounding noise or the start of one more
+          // Lawson-Hanson step, and SciPy takes that step for ANY positive dual.  What matters is
+          // the coefficient the bin would enter with, dual / pivot^2 — large when the bin is nearly
+          // dependent on the active ones.  One more trip (no dual pass) computes the pivot.
+          if (j < 0 || k == 0 || k == kcap) break;
+          phase = PH_CHECK; do_dual = false; jc = j; wjc = wj;
+          continue;
         }
         if (j < 0) {  // Kuhn-Tucker point of the carried solution: polish it
           if (k == 0) break;
@@ -399,6 +411,7 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
           zmax = fmax(zmax, __shfl_xor_sync(FULL, zmax, o));
         }
         rel = dmax_ / zmax;
+        zscale = zmax;
         // the first correction measures how far the carried solution had drifted while the
         // active-set decisions were being made; wrong results only appeared above 3e-4
         if ((pass == 0 && rel > 5e-5) || !pos) { mode = kNnlsRedo; break; }
@@ -415,6 +428,13 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
       }
       // ---- PH_ITER: Lawson-Hanson's independence and z tests for candidate j ------------------
       p0 = warp_sum(p0);
+      if (phase == PH_CHECK) {
+        // would-be coefficient of the sub-threshold candidate at the polished point: negligible ->
+        // the voxel is certified; otherwise the robust path (SciPy's own arithmetic) decides
+        const double piv2 = gdiag[j] - (p0 > 0.0 ? p0 : 0.0);
+        if (!(piv2 > 0.0) || wj > a.cert_ztol * fmax(1.0, 1e-4 * zscale) * piv2) mode = kNnlsRedo;
+        break;
+      }
       double sinv = 0.0, zeta = 0.0;
       {
         const double unorm2 = p0 > 0.0 ? p0 : 0.0;
