@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PNB_ABI_VERSION 2
+#define PNB_ABI_VERSION 3
 
 /* model_id: parameter order is the reference's `_all_param_names`
  * (models/monoexp.py:91-105, models/biexp.py:103-126, models/triexp.py:103-128) */
@@ -102,7 +102,9 @@ typedef struct pnb_trf_problem {
   double x_scale[8];         /* per parameter, 1.0 = SciPy default             */
   /* outputs */
   double *params;            /* (n_params, n_vox); fixed rows repeat the fixed value */
-  double *cov;               /* (n_vox, n_free, n_free) or NULL                */
+  double *cov;               /* (n_vox, n_free, n_free) or NULL.  pnb_trf_fit_host also accepts
+                                DEVICE memory of the fitting GPU here: the covariances then stay
+                                on the GPU (no D2H traffic) for the caller to fetch on demand  */
   int32_t *status;           /* (n_vox)                                        */
   int32_t *nfev;             /* (n_vox) residual evaluations, SciPy's count     */
   int32_t *njev;             /* (n_vox) or NULL                                */
@@ -113,6 +115,15 @@ typedef struct pnb_trf_problem {
 
 int pnb_trf_fit_device(const pnb_trf_problem *prob, void *cuda_stream);
 int pnb_trf_fit_host(const pnb_trf_problem *prob, int device, int64_t chunk_vox);
+/* The same call spread over n_devices GPUs of the node (devices[i], or 0 .. n_devices-1 when NULL):
+ * the voxels are cut into contiguous, balanced ranges (range i = voxels [i n / N, ...), the z-slabs
+ * of SURVEY.md §8e), one host pipeline per GPU runs concurrently, and every GPU copies its results
+ * straight into its part of the caller's arrays — one process, no gather step.  Replaces the joblib
+ * pool of CurveFitSolver._fit_data (solvers/curvefit.py:201-229) at node scale.
+ * cov_per_device: NULL (covariances go to prob->cov on the host, or nowhere when that is NULL), or
+ * n_devices DEVICE buffers, buffer i on GPU i holding its range's (n_range, n_free, n_free). */
+int pnb_trf_fit_host_multi(const pnb_trf_problem *prob, const int32_t *devices, int32_t n_devices,
+                           int64_t chunk_vox, double *const *cov_per_device);
 
 /*
  * Tikhonov-regularised non-negative least squares for n_vox voxels on a shared
@@ -149,6 +160,10 @@ typedef struct pnb_nnls_problem {
  * different streams are safe but do not overlap. */
 int pnb_nnls_fit_device(const pnb_nnls_problem *prob, void *cuda_stream);
 int pnb_nnls_fit_host(const pnb_nnls_problem *prob, int device, int64_t chunk_vox);
+/* multi-GPU form, see pnb_trf_fit_host_multi (replaces the joblib pool of NNLSSolver._fit_data,
+ * solvers/nnls_solver.py:153-172) */
+int pnb_nnls_fit_host_multi(const pnb_nnls_problem *prob, const int32_t *devices, int32_t n_devices,
+                            int64_t chunk_vox);
 int pnb_sizeof_nnls_problem(void);
 /* voxels of the most recent auto-mode launch on `device` that were re-solved by the robust path
  * (synchronises the device) */

@@ -174,6 +174,11 @@ def load():
     lib.pnb_trf_fit_device.restype = C.c_int
     lib.pnb_trf_fit_host.argtypes = [C.POINTER(TrfProblem), C.c_int, C.c_int64]
     lib.pnb_trf_fit_host.restype = C.c_int
+    lib.pnb_trf_fit_host_multi.argtypes = [C.POINTER(TrfProblem), C.POINTER(C.c_int32), C.c_int32, C.c_int64,
+                                           C.POINTER(C.c_void_p)]
+    lib.pnb_trf_fit_host_multi.restype = C.c_int
+    lib.pnb_nnls_fit_host_multi.argtypes = [C.POINTER(NnlsProblem), C.POINTER(C.c_int32), C.c_int32, C.c_int64]
+    lib.pnb_nnls_fit_host_multi.restype = C.c_int
     lib.pnb_nnls_fit_device.argtypes = [C.POINTER(NnlsProblem), C.c_void_p]
     lib.pnb_nnls_fit_device.restype = C.c_int
     lib.pnb_nnls_fit_host.argtypes = [C.POINTER(NnlsProblem), C.c_int, C.c_int64]
@@ -211,6 +216,33 @@ def require_device() -> None:
         raise EngineError(
             "no CUDA device visible: pyneapple_b200 runs on B200 GPUs only and has no CPU fallback"
         )
+
+
+def resolve_devices(device) -> list[int]:
+    """``device`` as the solvers accept it -> list of CUDA ordinals: an int, a sequence of ints, or
+    ``"all"`` (every visible GPU of the node)."""
+    if isinstance(device, str):
+        if device != "all":
+            raise ValueError("device must be an int, a sequence of ints or 'all'")
+        n = load().pnb_device_count()
+        return list(range(max(1, n)))
+    if isinstance(device, (list, tuple, np.ndarray)):
+        out = [int(d) for d in device]
+        if not out:
+            raise ValueError("empty device list")
+        return out
+    return [int(device)]
+
+
+def shard_ranges(n: int, parts: int) -> list[tuple[int, int]]:
+    """The contiguous ranges pnb_*_fit_host_multi assigns to its devices."""
+    base, rem = divmod(int(n), int(parts))
+    out, start = [], 0
+    for i in range(parts):
+        stop = start + base + (1 if i < rem else 0)
+        out.append((start, stop))
+        start = stop
+    return out
 
 
 def check(rc: int, what: str) -> None:

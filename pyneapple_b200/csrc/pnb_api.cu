@@ -297,7 +297,7 @@ struct Pipeline {
   bool init = false;
 };
 Pipeline g_pipes[16];
-std::mutex g_pipe_mu;
+std::mutex g_pipe_mu[16];  // one host pipeline per device; different devices run concurrently
 
 template <class T> int grow(T **ptr, size_t *cap, size_t need) {
   if (need <= *cap) return 0;
@@ -310,19 +310,25 @@ template <class T> int grow(T **ptr, size_t *cap, size_t need) {
 
 }  // namespace
 
-extern "C" int pnb_trf_fit_host(const pnb_trf_problem *p, int device, int64_t chunk_vox) {
-  if (int rc = check_problem(p)) return rc;
-  if (p->n_vox == 0) return 0;
+namespace {
+// Voxels [v0, v1) of the problem through the host pipeline of `device`, results written into the
+// same positions of the caller's arrays.  `cov_dev`: when not null, a DEVICE buffer on `device` that
+// receives the covariances of voxels v0 .. v1-1 (row 0 = voxel v0) instead of p->cov: they stay on
+// the GPU and cost no D2H traffic.
+int trf_host_range(const pnb_trf_problem *p, int device, int64_t chunk_vox, size_t v0, size_t v1, double *cov_dev) {
+  if (v1 <= v0) return 0;
   if (pnb_device_count() <= device || device < 0) return fail(PNB_E_NODEVICE, "no such CUDA device");
   pnbi::DeviceScope dev_scope(device);
   PNB_CUDA(dev_scope.error());
-  std::lock_guard<std::mutex> lk(g_pipe_mu);
+  std::lock_guard<std::mutex> lk(g_pipe_mu[device & 15]);
   Pipeline &P = g_pipes[device & 15];
   const int np = p->n_params, nb = p->n_b;
   const int nfree = np - popcount(p->frozen_mask & ((1u << np) - 1u));
   if (chunk_vox <= 0) chunk_vox = 1 << 18;
-  if (chunk_vox > p->n_vox) chunk_vox = p->n_vox;
+  if ((size_t)chunk_vox > v1 - v0) chunk_vox = (int64_t)(v1 - v0);
   const size_t C = (size_t)chunk_vox;
+  double *const host_cov = cov_dev ? nullptr : p->cov;  // covariance that travels to the host
+  const bool any_cov = cov_dev || p->cov;
 
   if (!P.init) {
     for (auto &s : P.slots) {
@@ -340,7 +346,7 @@ extern "C" int pnb_trf_fit_host(const pnb_trf_problem *p, int device, int64_t ch
     if (int rc = grow(&s.lb, &s.cap_lb, need_p)) return rc;
     if (int rc = grow(&s.ub, &s.cap_ub, need_p)) return rc;
     if (int rc = grow(&s.params, &s.cap_par, need_p)) return rc;
-    if (p->cov)
+    if (host_cov)
       if (int rc = grow(&s.cov, &s.cap_cov, C * nfree * nfree)) return rc;
     if (int rc = grow(&s.cost, &s.cap_cost, C)) return rc;
     if (int rc = grow(&s.r2, &s.cap_r2, C)) return rc;
@@ -362,12 +368,15 @@ extern "C" int pnb_trf_fit_host(const pnb_trf_problem *p, int device, int64_t ch
   const pnb::TrfOptions opt = make_options(p);
   LaunchFn launch = trf_launcher(p->model_id, p->t1_mode, p->method);
   const size_t NV = (size_t)p->n_vox;
-  // pageable caller memory is staged through page-locked blocks with multi-threaded host copies
-  const bool staged = pnbi::is_pageable(p->ydata) || pnbi::is_pageable(p->params);
+  // pageable caller memory is staged through page-locked blocks with multi-threaded host copies;
+  // inputs and outputs independently (a caller may hold pageable images and page-locked result arrays)
+  const bool stage_in = pnbi::is_pageable(p->ydata);
+  const bool stage_out = pnbi::is_pageable(p->params);
+  const bool staged = stage_in || stage_out;
   const size_t D = sizeof(double), I = sizeof(int);
   const size_t o_y = 0, o_p0 = o_y + C * nb * D, o_lb = o_p0 + C * np * D, o_ub = o_lb + C * np * D;
   const size_t o_par = o_ub + C * np * D, o_cov = o_par + C * np * D;
-  const size_t o_cost = o_cov + C * nfree * nfree * D, o_r2 = o_cost + C * D, o_st = o_r2 + C * D;
+  const size_t o_cost = o_cov + (host_cov ? C * nfree * nfree * D : 0), o_r2 = o_cost + C * D, o_st = o_r2 + C * D;
   const size_t o_nf = o_st + C * I, o_nj = o_nf + C * I, pin_bytes = o_nj + C * I;
   if (staged) {
     for (auto &s : P.slots) {
@@ -384,10 +393,11 @@ extern "C" int pnb_trf_fit_host(const pnb_trf_problem *p, int device, int64_t ch
   auto drain = [&](Slot &s) -> int {
     if (!s.pend_n) return 0;
     PNB_CUDA(cudaStreamSynchronize(s.stream));
+    if (!stage_out) { s.pend_n = 0; return 0; }  // only the staging block of the inputs had to be free
     const size_t st = s.pend_start, n = s.pend_n;
     for (int k = 0; k < np; k++)
       pnbi::parallel_memcpy(p->params + (size_t)k * NV + st, s.pin + o_par + (size_t)k * n * D, n * D);
-    if (p->cov) pnbi::parallel_memcpy(p->cov + st * nfree * nfree, s.pin + o_cov, n * nfree * nfree * D);
+    if (host_cov) pnbi::parallel_memcpy(host_cov + st * nfree * nfree, s.pin + o_cov, n * nfree * nfree * D);
     std::memcpy(p->status + st, s.pin + o_st, n * I);
     std::memcpy(p->nfev + st, s.pin + o_nf, n * I);
     if (p->njev) std::memcpy(p->njev + st, s.pin + o_nj, n * I);
@@ -397,14 +407,15 @@ extern "C" int pnb_trf_fit_host(const pnb_trf_problem *p, int device, int64_t ch
     return 0;
   };
   int slot = 0;
-  for (size_t start = 0; start < NV; start += C, slot = (slot + 1) % Pipeline::kSlots) {
+  for (size_t start = v0; start < v1; start += C, slot = (slot + 1) % Pipeline::kSlots) {
     Slot &s = P.slots[slot];
-    const size_t n = (NV - start < C) ? NV - start : C;
+    const size_t n = (v1 - start < C) ? v1 - start : C;
     const double *src_y = p->ydata + start * nb, *src_p0 = p->p0 + start, *src_lb = p->lb + start,
                  *src_ub = p->ub + start;
     size_t pitch = NV * D;  // row pitch of the caller's (n_params, n_vox) arrays
-    if (staged) {
+    if (staged)
       if (int rc = drain(s)) return rc;  // also waits until the slot's previous chunk is done
+    if (stage_in) {
       pnbi::parallel_memcpy(s.pin + o_y, src_y, n * nb * D);
       src_y = reinterpret_cast<const double *>(s.pin + o_y);
       if (p->p0_per_voxel) {
@@ -440,28 +451,29 @@ extern "C" int pnb_trf_fit_host(const pnb_trf_problem *p, int device, int64_t ch
     a.bd_row_stride = p->bounds_per_voxel ? (long long)n : 1;
     a.bd_vox_stride = p->bounds_per_voxel ? 1 : 0;
     a.opt = opt;
-    a.params = s.params; a.cov = p->cov ? s.cov : nullptr; a.status = s.status; a.nfev = s.nfev;
+    a.params = s.params; a.status = s.status; a.nfev = s.nfev;
+    a.cov = cov_dev ? cov_dev + (start - v0) * nfree * nfree : (host_cov ? s.cov : nullptr);
     a.njev = p->njev ? s.njev : nullptr; a.cost = p->cost ? s.cost : nullptr;
     a.r2 = p->r_squared ? s.r2 : nullptr;
     a.counter = s.counter;
     cudaError_t e = launch(&a, s.stream);
     if (e != cudaSuccess) return cuda_fail(e, "trf kernel launch");
     g_launches.fetch_add(1);
-    if (staged) {
+    if (staged) { s.pend_start = start; s.pend_n = n; }
+    if (stage_out) {
       PNB_CUDA(cudaMemcpyAsync(s.pin + o_par, s.params, D * n * np, cudaMemcpyDeviceToHost, s.stream));
-      if (p->cov)
+      if (host_cov)
         PNB_CUDA(cudaMemcpyAsync(s.pin + o_cov, s.cov, D * n * nfree * nfree, cudaMemcpyDeviceToHost, s.stream));
       PNB_CUDA(cudaMemcpyAsync(s.pin + o_st, s.status, I * n, cudaMemcpyDeviceToHost, s.stream));
       PNB_CUDA(cudaMemcpyAsync(s.pin + o_nf, s.nfev, I * n, cudaMemcpyDeviceToHost, s.stream));
       if (p->njev) PNB_CUDA(cudaMemcpyAsync(s.pin + o_nj, s.njev, I * n, cudaMemcpyDeviceToHost, s.stream));
       if (p->cost) PNB_CUDA(cudaMemcpyAsync(s.pin + o_cost, s.cost, D * n, cudaMemcpyDeviceToHost, s.stream));
       if (p->r_squared) PNB_CUDA(cudaMemcpyAsync(s.pin + o_r2, s.r2, D * n, cudaMemcpyDeviceToHost, s.stream));
-      s.pend_start = start; s.pend_n = n;
       continue;
     }
     PNB_CUDA(cudaMemcpy2DAsync(p->params + start, NV * D, s.params, n * D, n * D, np, cudaMemcpyDeviceToHost, s.stream));
-    if (p->cov)
-      PNB_CUDA(cudaMemcpyAsync(p->cov + start * nfree * nfree, s.cov, D * n * nfree * nfree,
+    if (host_cov)
+      PNB_CUDA(cudaMemcpyAsync(host_cov + start * nfree * nfree, s.cov, D * n * nfree * nfree,
                                cudaMemcpyDeviceToHost, s.stream));
     PNB_CUDA(cudaMemcpyAsync(p->status + start, s.status, I * n, cudaMemcpyDeviceToHost, s.stream));
     PNB_CUDA(cudaMemcpyAsync(p->nfev + start, s.nfev, I * n, cudaMemcpyDeviceToHost, s.stream));
@@ -478,6 +490,57 @@ extern "C" int pnb_trf_fit_host(const pnb_trf_problem *p, int device, int64_t ch
       if (int rc = drain(P.slots[(slot + k) % Pipeline::kSlots])) return rc;
     }
   for (auto &s : P.slots) PNB_CUDA(cudaStreamSynchronize(s.stream));
+  (void)any_cov;
+  return 0;
+}
+
+// true when `ptr` is device memory (the covariance may be left on the GPU)
+bool is_device_ptr(const void *ptr, int *dev_out) {
+  if (!ptr) return false;
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
+  if (attr.type != cudaMemoryTypeDevice) return false;
+  if (dev_out) *dev_out = attr.device;
+  return true;
+}
+}  // namespace
+
+extern "C" int pnb_trf_fit_host(const pnb_trf_problem *p, int device, int64_t chunk_vox) {
+  if (int rc = check_problem(p)) return rc;
+  if (p->n_vox == 0) return 0;
+  int cov_device = -1;
+  double *cov_dev = is_device_ptr(p->cov, &cov_device) ? p->cov : nullptr;
+  if (cov_dev && cov_device != device) return fail(PNB_E_BADARG, "cov is device memory of another GPU");
+  return trf_host_range(p, device, chunk_vox, 0, (size_t)p->n_vox, cov_dev);
+}
+
+// One host pipeline per GPU, run concurrently by one thread each; the voxels are cut into
+// contiguous, balanced ranges and every GPU writes straight into its part of the caller's arrays
+// (no gather step: the "parameter maps to rank 0" of the multi-process mode is the D2H copy itself).
+extern "C" int pnb_trf_fit_host_multi(const pnb_trf_problem *p, const int32_t *devices, int32_t n_devices,
+                                      int64_t chunk_vox, double *const *cov_per_device) {
+  if (int rc = check_problem(p)) return rc;
+  if (n_devices < 1 || n_devices > 16) return fail(PNB_E_BADARG, "n_devices must be in [1, 16]");
+  if (p->n_vox == 0) return 0;
+  const size_t NV = (size_t)p->n_vox;
+  std::vector<int> rcs(n_devices, 0);
+  std::vector<std::string> errs(n_devices);
+  std::vector<std::thread> workers;
+  const size_t base = NV / n_devices, rem = NV % n_devices;
+  size_t start = 0;
+  for (int i = 0; i < n_devices; i++) {
+    const size_t stop = start + base + ((size_t)i < rem ? 1 : 0);
+    const int dev = devices ? devices[i] : i;
+    double *cov_dev = cov_per_device ? cov_per_device[i] : nullptr;
+    workers.emplace_back([=, &rcs, &errs] {
+      rcs[i] = trf_host_range(p, dev, chunk_vox, start, stop, cov_dev);
+      if (rcs[i]) errs[i] = g_err;  // thread-local text of this worker
+    });
+    start = stop;
+  }
+  for (auto &w : workers) w.join();
+  for (int i = 0; i < n_devices; i++)
+    if (rcs[i]) { g_err = "device " + std::to_string(devices ? devices[i] : i) + ": " + errs[i]; return rcs[i]; }
   return 0;
 }
 

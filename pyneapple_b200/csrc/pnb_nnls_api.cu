@@ -4,6 +4,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
 
 #include "../../include/pyneapple_b200.h"
 #include "pnb_internal.h"
@@ -55,7 +58,7 @@ const bool g_disable_v3 = [] { const char *e = std::getenv("PNB_NNLS_NO_V3"); re
 // it sends the voxel to the robust path.  2e-7 keeps the worst case a factor 5 inside the 1e-6
 // absolute parity tolerance; PNB_NNLS_CERT_ZTOL overrides it (measurements).
 const double g_cert_ztol = [] { const char *e = std::getenv("PNB_NNLS_CERT_ZTOL"); return e ? std::atof(e) : 2e-7; }();
-std::mutex g_mu;
+std::mutex g_mu[16];  // per device: the host pipelines of different GPUs run concurrently
 
 // (re)allocate a device buffer of `need` elements; pointer and capacity stay consistent on failure
 template <class T> int grow(T **ptr, size_t *cap, size_t need) {
@@ -215,7 +218,7 @@ extern "C" int pnb_nnls_fit_device(const pnb_nnls_problem *p, void *cuda_stream)
   if (p->n_vox == 0) return 0;
   int dev = 0;
   PNBI_CUDA(cudaGetDevice(&dev));
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::mutex> lk(g_mu[dev & 15]);
   NnlsCtx &C = g_ctx[dev & 15];
   // Device-path launches use slot 0's scratch, redo list and counters whatever stream they are given:
   // order each launch after the previous one (a no-op on the same stream), so two launches in flight
@@ -229,13 +232,14 @@ extern "C" int pnb_nnls_fit_device(const pnb_nnls_problem *p, void *cuda_stream)
   return rc;
 }
 
-extern "C" int pnb_nnls_fit_host(const pnb_nnls_problem *p, int device, int64_t chunk_vox) {
-  if (int rc = check(p)) return rc;
-  if (p->n_vox == 0) return 0;
+namespace {
+// voxels [v0, v1) of the problem through the host pipeline of `device` (see pnb_api.cu: trf_host_range)
+int nnls_host_range(const pnb_nnls_problem *p, int device, int64_t chunk_vox, size_t v0, size_t v1) {
+  if (v1 <= v0) return 0;
   if (pnb_device_count() <= device || device < 0) return pnbi::fail(PNB_E_NODEVICE, "no such CUDA device");
   pnbi::DeviceScope dev_scope(device);
   PNBI_CUDA(dev_scope.error());
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::mutex> lk(g_mu[device & 15]);
   NnlsCtx &C = g_ctx[device & 15];
   if (C.dev_done) PNBI_CUDA(cudaEventSynchronize(C.dev_done));  // a device-path launch may still use slot 0
   const int m = p->n_b, n = p->n_bins, BW = 2 * p->rtr_halfband + 1;
@@ -244,7 +248,7 @@ extern "C" int pnb_nnls_fit_host(const pnb_nnls_problem *p, int device, int64_t 
   // pageable caller memory the call is bound by the host copies anyway and a quarter of that keeps
   // the page-locked staging blocks (3 x chunk x 8 (n_b + n_bins + 3) bytes, ~1 s per GB to lock) small
   if (chunk_vox <= 0) chunk_vox = staged ? (1 << 16) : (1 << 18);
-  if (chunk_vox > p->n_vox) chunk_vox = p->n_vox;
+  if ((size_t)chunk_vox > v1 - v0) chunk_vox = (int64_t)(v1 - v0);
   const size_t Cn = (size_t)chunk_vox;
   if (!C.streams[0])
     for (auto &s : C.streams) PNBI_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
@@ -260,7 +264,6 @@ extern "C" int pnb_nnls_fit_host(const pnb_nnls_problem *p, int device, int64_t 
   if (int rc = grow(&C.rtr, &C.cap_rtr, (size_t)n * BW)) return rc;
   PNBI_CUDA(cudaMemcpy(C.B, p->basis, (size_t)m * n * sizeof(double), cudaMemcpyHostToDevice));
   PNBI_CUDA(cudaMemcpy(C.rtr, p->rtr_band, (size_t)n * BW * sizeof(double), cudaMemcpyHostToDevice));
-  const size_t NV = (size_t)p->n_vox;
   const size_t D = sizeof(double), I = sizeof(int);
   const size_t o_y = 0, o_coef = o_y + Cn * m * D, o_rn = o_coef + Cn * n * D, o_r2 = o_rn + Cn * D;
   const size_t o_st = o_r2 + Cn * D, o_it = o_st + Cn * I, pin_bytes = o_it + Cn * I;
@@ -287,8 +290,8 @@ extern "C" int pnb_nnls_fit_host(const pnb_nnls_problem *p, int device, int64_t 
     return 0;
   };
   int s = 0;
-  for (size_t start = 0; start < NV; start += Cn, s = (s + 1) % kSlots) {
-    const size_t nv = (NV - start < Cn) ? NV - start : Cn;
+  for (size_t start = v0; start < v1; start += Cn, s = (s + 1) % kSlots) {
+    const size_t nv = (v1 - start < Cn) ? v1 - start : Cn;
     cudaStream_t st = C.streams[s];
     const double *src_y = p->signal + start * m;
     if (staged) {
@@ -320,12 +323,43 @@ extern "C" int pnb_nnls_fit_host(const pnb_nnls_problem *p, int device, int64_t 
   for (auto &st : C.streams) PNBI_CUDA(cudaStreamSynchronize(st));
   return 0;
 }
+}  // namespace
+
+extern "C" int pnb_nnls_fit_host(const pnb_nnls_problem *p, int device, int64_t chunk_vox) {
+  if (int rc = check(p)) return rc;
+  return nnls_host_range(p, device, chunk_vox, 0, (size_t)p->n_vox);
+}
+
+extern "C" int pnb_nnls_fit_host_multi(const pnb_nnls_problem *p, const int32_t *devices, int32_t n_devices,
+                                       int64_t chunk_vox) {
+  if (int rc = check(p)) return rc;
+  if (n_devices < 1 || n_devices > 16) return pnbi::fail(PNB_E_BADARG, "n_devices must be in [1, 16]");
+  const size_t NV = (size_t)p->n_vox;
+  std::vector<int> rcs(n_devices, 0);
+  std::vector<std::string> errs(n_devices);
+  std::vector<std::thread> workers;
+  const size_t base = NV / n_devices, rem = NV % n_devices;
+  size_t start = 0;
+  for (int i = 0; i < n_devices; i++) {
+    const size_t stop = start + base + ((size_t)i < rem ? 1 : 0);
+    const int dev = devices ? devices[i] : i;
+    workers.emplace_back([=, &rcs, &errs] {
+      rcs[i] = nnls_host_range(p, dev, chunk_vox, start, stop);
+      if (rcs[i]) errs[i] = pnb_last_error();
+    });
+    start = stop;
+  }
+  for (auto &w : workers) w.join();
+  for (int i = 0; i < n_devices; i++)
+    if (rcs[i]) return pnbi::fail(rcs[i], "device " + std::to_string(devices ? devices[i] : i) + ": " + errs[i]);
+  return 0;
+}
 
 extern "C" int pnb_sizeof_nnls_problem(void) { return (int)sizeof(pnb_nnls_problem); }
 
 extern "C" int64_t pnb_nnls_last_redo_count(int device) {
   if (device < 0 || device > 15) return -1;
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::mutex> lk(g_mu[device]);
   NnlsCtx &C = g_ctx[device];
   if (!C.last_redo) return 0;
   unsigned long long v = 0;

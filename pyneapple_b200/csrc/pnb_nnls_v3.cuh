@@ -711,7 +711,7 @@ cudaError_t nnls_v3_launch(const NnlsDeviceArgs &a, cudaStream_t stream) {
   auto kern = nnls_v3_kernel<MT, WK>;
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return err;
-  static int sms = 0;
+  static thread_local int sms = 0;
   if (!sms) {
     int dev = 0;
     err = cudaGetDevice(&dev);

@@ -382,9 +382,10 @@ template <class M, int BLOCK> size_t trf_smem_bytes(int n_b) {
 template <class M, int BLOCK, int METHOD = 0> cudaError_t trf_launch(const TrfDeviceArgs &a, cudaStream_t stream) {
   const size_t smem = trf_smem_bytes<M, BLOCK>(a.n_b);
   auto kern = trf_kernel<M, BLOCK, METHOD>;
-  static int blocks_per_sm_cache = -1;
-  static size_t smem_cache = 0;
-  static int sm_count = 0;
+  // per thread: the multi-GPU host entry drives one device from each of its threads
+  static thread_local int blocks_per_sm_cache = -1;
+  static thread_local size_t smem_cache = 0;
+  static thread_local int sm_count = 0;
   cudaError_t err;
   if (smem > 200 * 1024) return cudaErrorInvalidValue;  // n_b too large for this block size
   if (smem > 48 * 1024) {

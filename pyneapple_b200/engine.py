@@ -74,14 +74,20 @@ def trf_fit(
     jac_mode: int = JAC_ANALYTIC,
     x_scale=None,
     x_scale_jac: bool = False,
-    want_cov: bool = True,
-    device: int = 0,
+    want_cov=True,
+    device=0,
     chunk_vox: int = 0,
     out: dict | None = None,
     method: str = "trf",
 ):
     """Fit all voxels.  ``p0``/``lb``/``ub``: ``(n_all,)`` or ``(n_all, n_vox)`` over
     ``desc.all_names`` (frozen rows of ``p0`` carry the fixed values).
+
+    ``device``: a CUDA ordinal, a list of ordinals or ``"all"`` — with several GPUs the host path
+    shards the voxels into contiguous ranges, one pipeline per GPU in one call
+    (``pnb_trf_fit_host_multi``).  ``want_cov``: ``True`` / ``"lazy"`` computes the covariances and
+    leaves them on the GPU(s) behind a :class:`~pyneapple_b200._lazy.LazyArray` (host path), ``"eager"``
+    copies them to the host with the other results, ``False`` skips them.
 
     Returns ``dict(params (n_all, n_vox), cov (n_vox, n_free, n_free) | None,
     status, nfev, njev, cost)``.
@@ -132,13 +138,28 @@ def trf_fit(
     prob.p0_per_voxel = int(p0.ndim == 2)
     prob.bounds_per_voxel = int(lb.ndim == 2)
 
+    devices = _lib.resolve_devices(device)
+    if len(devices) > n_vox:
+        devices = devices[: max(1, n_vox)]
     o = out or {}
     params = o.get("params")
     if params is None:
         params = np.empty((n_all, n_vox))
-    cov = o.get("cov") if want_cov else None
-    if want_cov and cov is None:
-        cov = np.empty((n_vox, n_free, n_free))
+    lazy = want_cov is True or want_cov == "lazy"
+    cov = cov_parts = None
+    if want_cov and not lazy:
+        cov = o.get("cov")
+        if cov is None:
+            cov = np.empty((n_vox, n_free, n_free))
+    elif lazy and n_vox:
+        import torch
+
+        cov_parts = [(a, z, torch.empty((z - a, n_free, n_free), dtype=torch.float64, device=f"cuda:{d}"))
+                     for (a, z), d in zip(_lib.shard_ranges(n_vox, len(devices)), devices)]
+        for d in set(devices):
+            # the blocks may be recycled memory with work still queued on torch's stream; the library
+            # writes them from its own streams
+            torch.cuda.current_stream(d).synchronize()
     status = o.get("status") if o.get("status") is not None else np.empty(n_vox, np.int32)
     nfev = o.get("nfev") if o.get("nfev") is not None else np.empty(n_vox, np.int32)
     njev = o.get("njev") if o.get("njev") is not None else np.empty(n_vox, np.int32)
@@ -152,8 +173,22 @@ def trf_fit(
     prob.status, prob.nfev = status.ctypes.data, nfev.ctypes.data
     prob.njev, prob.cost = njev.ctypes.data, cost.ctypes.data
     prob.r_squared = r2.ctypes.data
-    _lib.check(lib.pnb_trf_fit_host(C.byref(prob), int(device), int(chunk_vox)), "pnb_trf_fit_host")
+    if len(devices) == 1:
+        if cov_parts:
+            prob.cov = cov_parts[0][2].data_ptr()
+        _lib.check(lib.pnb_trf_fit_host(C.byref(prob), devices[0], int(chunk_vox)), "pnb_trf_fit_host")
+    else:
+        dev_arr = (C.c_int32 * len(devices))(*devices)
+        cov_ptrs = None
+        if cov_parts:
+            cov_ptrs = (C.c_void_p * len(devices))(*[t.data_ptr() for _, _, t in cov_parts])
+        _lib.check(lib.pnb_trf_fit_host_multi(C.byref(prob), dev_arr, len(devices), int(chunk_vox), cov_ptrs),
+                   "pnb_trf_fit_host_multi")
     del keep
+    if cov_parts:
+        from ._lazy import LazyArray
+
+        cov = LazyArray((n_vox, n_free, n_free), cov_parts)
     return dict(params=params, cov=cov, status=status, nfev=nfev, njev=njev, cost=cost, r2=r2)
 
 
@@ -246,7 +281,7 @@ def rtr_band(reg_matrix: np.ndarray):
     return band, W
 
 
-def nnls_fit(basis, reg_matrix, signal, max_iter: int, *, device: int = 0, chunk_vox: int = 0,
+def nnls_fit(basis, reg_matrix, signal, max_iter: int, *, device=0, chunk_vox: int = 0,
              out: dict | None = None, algorithm: str = "auto"):
     """Batched ``scipy.optimize.nnls([basis; reg_matrix], [signal; 0], maxiter=max_iter)``.
 
@@ -309,7 +344,13 @@ def nnls_fit(basis, reg_matrix, signal, max_iter: int, *, device: int = 0, chunk
     prob.coefficients, prob.residual = coef.ctypes.data, res.ctypes.data
     prob.status, prob.iterations = status.ctypes.data, iters.ctypes.data
     prob.r_squared = r2.ctypes.data
-    _lib.check(lib.pnb_nnls_fit_host(C.byref(prob), int(device), int(chunk_vox)), "pnb_nnls_fit_host")
+    devices = _lib.resolve_devices(device)
+    if len(devices) == 1:
+        _lib.check(lib.pnb_nnls_fit_host(C.byref(prob), devices[0], int(chunk_vox)), "pnb_nnls_fit_host")
+    else:
+        dev_arr = (C.c_int32 * len(devices))(*devices)
+        _lib.check(lib.pnb_nnls_fit_host_multi(C.byref(prob), dev_arr, len(devices), int(chunk_vox)),
+                   "pnb_nnls_fit_host_multi")
     return dict(coefficients=coef, residual=res, status=status, iterations=iters, r2=r2)
 
 

@@ -78,7 +78,7 @@ class IDEALFitter(BaseFitter):
     def _interpolate_array(self, array, target_shape):
         """Host-callable resampler with the reference's signature (ideal.py:299-320)."""
         return interpolate_array(array, target_shape, self.interpolation_method,
-                                 device=getattr(self.solver, "device", 0))
+                                 device=getattr(self.solver, "primary_device", 0))
 
     # ---- fit -----------------------------------------------------------------------------
     def fit(self, xdata, image, segmentation=None, z_range=None, **fit_kwargs):
@@ -133,7 +133,7 @@ class IDEALFitter(BaseFitter):
         solver = self.solver
         names = solver.model.param_names
         n_params = len(names)
-        dev = torch.device("cuda", solver.device)
+        dev = torch.device("cuda", solver.primary_device)
         f64 = dict(dtype=torch.float64, device=dev)
         p0_vals = torch.tensor([solver.p0[n] for n in names], **f64)
         lo_vals = torch.tensor([solver.bounds[n][0] for n in names], **f64)

@@ -94,7 +94,7 @@ class SegmentedFitter(BaseFitter):
         if not device_ok:
             raise TypeError("SegmentedFitter needs B200 CurveFitSolver instances for both steps")
         pixel_to_fit = self._extract_pixel_data(image, segmentation)
-        dev = torch.device("cuda", self.step2_solver.device)
+        dev = torch.device("cuda", self.step2_solver.primary_device)
         y_dev = engine.to_device(np.ascontiguousarray(pixel_to_fit), dev)
         # ---- step 1 on the b-value subset --------------------------------------
         sub_idx = torch.as_tensor(np.nonzero(bmask)[0], device=dev)

@@ -26,6 +26,17 @@ _HONOURED_KWARGS = {"xtol", "gtol", "x_scale"}
 _IGNORED_KWARGS = {"n_pools"}
 
 
+def _unreferenced(arrays: dict) -> bool:
+    """True when nothing but ``arrays`` itself references its values (views count: they keep their
+    base alive).  Expected count per array: the dict, the loop variable, getrefcount's argument."""
+    import sys
+
+    for a in arrays.values():
+        if sys.getrefcount(a) > 3:
+            return False
+    return True
+
+
 class CurveFitSolver(BaseSolver):
     """Bounded non-linear least squares for every voxel on the GPU.
 
@@ -59,13 +70,20 @@ class CurveFitSolver(BaseSolver):
         self.use_jacobian = use_jacobian and hasattr(model, "jacobian")
         self.n_pools = solver_kwargs.pop("n_pools", None)
         self.jac = solver_kwargs.pop("jac", "reference")
+        # GPU(s) of the host path: an ordinal, a list of ordinals or "all" (one call, voxels sharded
+        # over the node's GPUs); the device-resident drivers use the first one
         self.device = solver_kwargs.pop("device", 0)
         self.chunk_vox = solver_kwargs.pop("chunk_vox", 0)
+        # True / "lazy": covariances are computed and stay on the GPU until somebody reads them
+        # (diagnostics_["pcov"] is then a LazyArray); "eager": shipped with the other results; False: skipped
         self.want_cov = solver_kwargs.pop("want_cov", True)
-        # opt-in: keep page-locked output buffers between fits (results are then views
-        # that the next fit overwrites) -- removes the pageable D2H staging cost
-        self.pinned_outputs = solver_kwargs.pop("pinned_outputs", False)
+        # result arrays in page-locked memory (no staging copy on the way back).  "auto": from the
+        # second fit of the same shape on (locking ~1 GB costs more than one staged download);
+        # True: always; False: never.  A cached block is only reused when nothing outside the solver
+        # still references the arrays of the previous fit.
+        self.pinned_outputs = solver_kwargs.pop("pinned_outputs", "auto")
         self._out_cache = None
+        self._last_out_key = None
         if self.jac not in ("reference", "analytic", "2-point"):
             raise ValueError("jac must be 'reference', 'analytic' or '2-point'")
         unknown = set(solver_kwargs) - _HONOURED_KWARGS - _IGNORED_KWARGS
@@ -135,7 +153,7 @@ class CurveFitSolver(BaseSolver):
             # only supplies R^2 at p0.
             res["status"][...] = engine.ST_LM_BOUNDED
             if res.get("cov") is not None:
-                res["cov"][...] = np.nan
+                res["cov"] = np.full(tuple(res["cov"].shape), np.nan)
         self._store(res, free_names, n_pixels)
         return self
 
@@ -275,7 +293,7 @@ class CurveFitSolver(BaseSolver):
             ftol=self.tol, xtol=self.solver_kwargs.get("xtol", 1e-8),
             gtol=self.solver_kwargs.get("gtol", 1e-8), jac_mode=jac_mode,
             x_scale=xs_full, x_scale_jac=x_scale_jac,
-            want_cov=self.want_cov if want_cov is None else want_cov, device=self.device,
+            want_cov=self.want_cov if want_cov is None else want_cov, device=self.primary_device,
             method=self._ls_method(),
         )
         res["free_names"] = free_names
@@ -291,25 +309,46 @@ class CurveFitSolver(BaseSolver):
         self._store(host, free_names, host["params"].shape[1])
         return self
 
+    @property
+    def primary_device(self) -> int:
+        from .. import _lib
+
+        return _lib.resolve_devices(self.device)[0]
+
     def _pinned_out(self, n_all, n_free, n_pixels, ydata):
-        if not self.pinned_outputs or engine._is_torch_cuda(ydata):
+        if not self.pinned_outputs or engine._is_torch_cuda(ydata) or n_pixels < 65536:
             return None
         from .. import _lib
 
-        key = (n_all, n_free, n_pixels, bool(self.want_cov))
-        if self._out_cache is None or self._out_cache[0] != key:
-            out = dict(
-                params=_lib.pinned_empty((n_all, n_pixels)),
-                status=_lib.pinned_empty((n_pixels,), np.int32),
-                nfev=_lib.pinned_empty((n_pixels,), np.int32),
-                njev=_lib.pinned_empty((n_pixels,), np.int32),
-                cost=_lib.pinned_empty((n_pixels,)),
-                r2=_lib.pinned_empty((n_pixels,)),
-            )
-            if self.want_cov:
-                out["cov"] = _lib.pinned_empty((n_pixels, n_free, n_free))
-            self._out_cache = (key, out)
-        return self._out_cache[1]
+        eager = bool(self.want_cov) and self.want_cov is not True and self.want_cov != "lazy"
+        key = (n_all, n_free, n_pixels, eager)
+        if self.pinned_outputs == "auto" and self._last_out_key != key:
+            self._last_out_key = key
+            return None
+        self._last_out_key = key
+        cached = self._out_cache
+        if cached is not None and cached[0] == key:
+            # reuse only when the previous fit's arrays are referenced by nobody else (views held by
+            # a caller keep their base alive: count = cache dict + getrefcount's argument)
+            if _unreferenced(cached[1]):
+                return cached[1]
+        out = dict(
+            params=_lib.pinned_empty((n_all, n_pixels)),
+            status=_lib.pinned_empty((n_pixels,), np.int32),
+            nfev=_lib.pinned_empty((n_pixels,), np.int32),
+            njev=_lib.pinned_empty((n_pixels,), np.int32),
+            cost=_lib.pinned_empty((n_pixels,)),
+            r2=_lib.pinned_empty((n_pixels,)),
+        )
+        if eager:
+            out["cov"] = _lib.pinned_empty((n_pixels, n_free, n_free))
+        self._out_cache = (key, out)
+        return out
+
+    def _reset_state(self):
+        super()._reset_state()
+        # drop the solver's own references to the previous fit's arrays (see _pinned_out)
+        self.status_ = self.nfev_ = self.njev_ = self.cost_ = self.r_squared_ = None
 
     def _store(self, res, free_names, n_pixels):
         rows = [res["params"][r] for r in self._free_rows]  # views of the (n_all, n_vox) output

@@ -44,7 +44,8 @@ class NNLSSolver(BaseSolver):
         self.n_pools = solver_kwargs.pop("n_pools", None)
         self.device = solver_kwargs.pop("device", 0)
         self.chunk_vox = solver_kwargs.pop("chunk_vox", 0)
-        self.pinned_outputs = solver_kwargs.pop("pinned_outputs", False)
+        self.pinned_outputs = solver_kwargs.pop("pinned_outputs", "auto")  # see CurveFitSolver
+        self._last_out_key = None
         self.algorithm = solver_kwargs.pop("algorithm", "auto")
         self._out_cache = None
         self._peaks_cache = None
@@ -53,6 +54,12 @@ class NNLSSolver(BaseSolver):
         self.status_ = None
         self.iterations_ = None
         self.r_squared_ = None
+
+    @property
+    def primary_device(self) -> int:
+        from .. import _lib
+
+        return _lib.resolve_devices(self.device)[0]
 
     def get_regularization_matrix(self) -> np.ndarray:
         return regularization_matrix(self.model.n_bins, self.reg_order, self.mu)
@@ -75,18 +82,27 @@ class NNLSSolver(BaseSolver):
             signal = signal[None, :]
         self.n_pixels = signal.shape[0]
         out = None
-        if self.pinned_outputs and not on_device:
+        self.status_ = self.iterations_ = self.r_squared_ = None
+        key = (self.n_pixels, basis.shape[1])
+        use_pinned = bool(self.pinned_outputs) and not on_device and self.n_pixels >= 16384
+        if use_pinned and self.pinned_outputs == "auto" and self._last_out_key != key:
+            use_pinned = False  # first fit of this shape: locking the pages costs more than one staged download
+        self._last_out_key = key
+        if use_pinned:
             from .. import _lib
+            from .curvefit import _unreferenced
 
-            key = (self.n_pixels, basis.shape[1])
-            if self._out_cache is None or self._out_cache[0] != key:
-                self._out_cache = (key, dict(
+            cached = self._out_cache
+            if cached is not None and cached[0] == key and _unreferenced(cached[1]):
+                out = cached[1]
+            else:
+                out = dict(
                     coefficients=_lib.pinned_empty((self.n_pixels, basis.shape[1])),
                     residual=_lib.pinned_empty((self.n_pixels,)),
                     status=_lib.pinned_empty((self.n_pixels,), np.int32),
                     iterations=_lib.pinned_empty((self.n_pixels,), np.int32),
-                    r2=_lib.pinned_empty((self.n_pixels,))))
-            out = self._out_cache[1]
+                    r2=_lib.pinned_empty((self.n_pixels,)))
+                self._out_cache = (key, out)
         res = engine.nnls_fit(basis, reg, signal, self.max_iter, device=self.device,
                               chunk_vox=self.chunk_vox, out=out, algorithm=self.algorithm)
         if on_device:
@@ -137,7 +153,7 @@ class NNLSSolver(BaseSolver):
         basis = self.model.get_basis(xdata)
         reg = self.get_regularization_matrix()
         n_vox, K = signal.shape[0], (0 if cutoffs is None else len(cutoffs))
-        dev = torch.device("cuda", self.device)
+        dev = torch.device("cuda", self.primary_device)
         # page-locked result arrays: the downloads are asynchronous and run at PCIe speed (a pageable
         # destination costs ~100 ms per million voxels, most of the fit time)
         pe = _lib.pinned_empty

@@ -215,3 +215,47 @@ def test_fitter_construction_contract():
     assert xb.min() == 200 and img.shape[-1] == xb.size
     with pytest.raises(ValueError):
         SegmentedFitter(mono, s, fixed_from_step1=["D"])  # "D" is not a step-2 parameter without a mapping
+
+
+def test_lazy_array_behaves_like_the_array_it_becomes():
+    import torch
+
+    from pyneapple_b200._lazy import LazyArray
+
+    full = np.arange(7 * 2 * 2, dtype=np.float64).reshape(7, 2, 2)
+    parts = [(0, 3, torch.as_tensor(full[:3])), (3, 7, torch.as_tensor(full[3:]))]
+    lz = LazyArray(full.shape, parts)
+    assert lz.shape == (7, 2, 2) and lz.ndim == 3 and len(lz) == 7 and lz.on_device
+    assert np.array_equal(lz[4], full[4]) and np.array_equal(lz[-1], full[-1]) and lz.on_device  # one block only
+    with pytest.raises(IndexError):
+        lz[7]
+    mask = np.array([1, 0, 0, 1, 0, 0, 1], bool)
+    assert np.array_equal(lz[mask], full[mask]) and not lz.on_device  # anything else materialises
+    assert np.array_equal(np.asarray(lz), full) and np.isnan(lz).sum() == 0
+    assert np.array_equal(lz.reshape(7, 4), full.reshape(7, 4))
+    assert np.array_equal(np.asarray(LazyArray(full.shape, parts), dtype=np.float32), full.astype(np.float32))
+
+
+def test_pinned_output_blocks_are_only_reused_when_nobody_else_holds_them():
+    from pyneapple_b200.solvers.curvefit import _unreferenced
+
+    cache = {"params": np.zeros((4, 10)), "status": np.zeros(10, np.int32)}
+    assert _unreferenced(cache)
+    row = cache["params"][1]  # a view, like solver.params_["D1"]
+    assert not _unreferenced(cache)
+    del row
+    assert _unreferenced(cache)
+    held = cache["status"]
+    assert not _unreferenced(cache)
+    del held
+
+
+def test_device_argument_forms():
+    from pyneapple_b200 import _lib
+
+    assert _lib.resolve_devices(3) == [3] and _lib.resolve_devices([1, 0]) == [1, 0]
+    assert _lib.resolve_devices("all")[0] == 0
+    with pytest.raises(ValueError):
+        _lib.resolve_devices("some")
+    assert _lib.shard_ranges(10, 3) == [(0, 4), (4, 7), (7, 10)]
+    assert _lib.shard_ranges(2, 4) == [(0, 1), (1, 2), (2, 2), (2, 2)]

@@ -151,7 +151,8 @@ def test_fused_pipeline_with_large_chunks_orders_uploads_after_the_kernels():
     from pyneapple_b200.solvers import NNLSSolver
 
     cfg = synth.CONFIGS["C3"]
-    b, y, _ = synth.sample_voxels(cfg, 4 * 65536 + 777)
+    b, img, _ = synth.make_volume(cfg, 0, 5)
+    y = np.ascontiguousarray(img.reshape(-1, 16)[: 4 * 65536 + 777])
     assert y[:65536].nbytes >= (4 << 20)
     model = models.NNLSModel(d_range=(0.0008, 0.5), n_bins=250)
     solver = NNLSSolver(model=model, reg_order=2, mu=0.02, max_iter=250)
@@ -171,7 +172,8 @@ def test_to_device_loop_does_not_overwrite_memory_a_queued_kernel_still_reads():
     from pyneapple_b200.solvers.nnls import regularization_matrix
 
     cfg = synth.CONFIGS["C3"]
-    b, y, _ = synth.sample_voxels(cfg, 3 * 49152)
+    b, img, _ = synth.make_volume(cfg, 0, 3)
+    y = np.ascontiguousarray(img.reshape(-1, 16)[: 3 * 49152])
     model = models.NNLSModel(d_range=(0.0008, 0.5), n_bins=250)
     basis, R = model.get_basis(b), regularization_matrix(250, 2, 0.02)
     whole = engine.nnls_fit(basis, R, torch.as_tensor(y).cuda(), 250)["coefficients"].cpu().numpy()
