@@ -126,9 +126,21 @@ def case_triexp():
 
 
 def case_constrained_c5():
+    """SLSQP goldens: 4 096 voxels of config C5 (the planted 5 % sub-population has the constraint
+    active), and per-voxel fixed parameters (constrained_curvefit.py:170-177): a fixed D3 keeps both
+    fractions free (constraint applies), a fixed f1 leaves one fraction (the reference then applies no
+    constraint at all)."""
     cfg, p0, bounds = _cfg_args("C5")
-    b, y, _ = synth.sample_voxels(cfg, 256)
+    b, y, _ = synth.sample_voxels(cfg, 4096)
     _run_curvefit("slsqp_triexp_c5", "triexp", {}, b, y, p0, bounds,
+                  cls=ConstrainedCurveFitSolver, fraction_constraint=True)
+    b, y, _ = synth.sample_voxels(cfg, 512, z=7)
+    rng = np.random.default_rng(55)
+    d3 = rng.uniform(5e-4, 2e-3, size=y.shape[0])
+    _run_curvefit("slsqp_triexp_c5_pixfixed_D3", "triexp", {}, b, y, p0, bounds, pixel_fixed={"D3": d3},
+                  cls=ConstrainedCurveFitSolver, fraction_constraint=True)
+    f1 = rng.uniform(0.05, 0.25, size=y.shape[0])
+    _run_curvefit("slsqp_triexp_c5_pixfixed_f1", "triexp", {}, b, y, p0, bounds, pixel_fixed={"f1": f1},
                   cls=ConstrainedCurveFitSolver, fraction_constraint=True)
 
 

@@ -30,7 +30,7 @@ import numpy as np
 from .. import engine
 from ..models import (MODEL_BI_REDUCED, MODEL_BI_S0, MODEL_TRI_REDUCED, MODEL_TRI_S0, ModelDesc,
                       _all_names)
-from .base import PixelResults
+from ..validation import bounds_vectors as V_bounds
 from .curvefit import CurveFitSolver
 
 log = logging.getLogger("pyneapple_b200")
@@ -75,96 +75,174 @@ class ConstrainedCurveFitSolver(CurveFitSolver):
         self.n_active_ = 0
 
     def fit(self, xdata, ydata, p0=None, bounds=None, pixel_fixed_params=None, **fit_kwargs):
+        """Both phases run on the GPU (``fit_device``); a numpy ``ydata`` is uploaded once (sharded over
+        the solver's devices when it has several), results come back as numpy arrays."""
+        from concurrent.futures import ThreadPoolExecutor
+
+        from .. import _lib
         from .. import validation as V
 
         self._reset_state()
+        _lib.require_device()
+        import torch
+
         xdata = np.asarray(xdata)
         on_device = engine._is_torch_cuda(ydata)
-        if on_device:
-            ydata = ydata.cpu().numpy()  # orchestration of the two phases is done on host arrays
-        ydata = np.asarray(ydata)
+        if not on_device:
+            ydata = np.asarray(ydata)
         V.validate_data_shapes(xdata, ydata)
         n_pixels = ydata.shape[0] if ydata.ndim > 1 else 1
         if ydata.ndim == 1:
             ydata = ydata[None, :]
         p0_m, lb_m, ub_m = self._validate_p0_and_bounds(p0, bounds, n_pixels)
-        # phase 1: box-bounded problem, tight tolerances, analytic Jacobian
-        saved = (self.tol, self.max_iter, dict(self.solver_kwargs))
-        self.tol = min(self.tol, _TIGHT)
-        self.solver_kwargs.update(xtol=_TIGHT, gtol=_TIGHT)
-        self.max_iter = max(4 * saved[1], 1000)
-        try:
-            res, free_names = self._solve(xdata, ydata, p0_m, lb_m, ub_m, pixel_fixed_params, n_pixels)
-        finally:
-            self.tol, self.max_iter, self.solver_kwargs = saved
-        desc = self._desc
-        all_names = list(desc.all_names)
-        pix_fixed = set(pixel_fixed_params or {}) & set(all_names)
-        fracs = [n for n in free_names if n.startswith("f")] if self.fraction_constraint else []
-        self.n_active_ = 0
-        if len(fracs) >= 2:
-            i1, i2 = all_names.index("f1"), all_names.index("f2")
-            par = res["params"]
-            viol = (par[i1] + par[i2] > 1.0) & (res["status"] > 0)
-            idx = np.nonzero(viol)[0]
-            self.n_active_ = int(idx.size)
-            if idx.size:
-                self._solve_on_face(xdata, ydata, idx, res, lb_m, ub_m, all_names, pixel_fixed_params, pix_fixed)
-        # iteration limit: the reference reports result.x with success=False (not p0)
-        self._store(res, free_names, n_pixels)
+        devices = [ydata.device.index] if on_device else _lib.resolve_devices(self.device)
+        ranges = _lib.shard_ranges(n_pixels, len(devices)) if len(devices) > 1 else [(0, n_pixels)]
+
+        def part(arr, a, z):  # per-voxel rows follow the voxels, vectors are shared
+            if arr is None or np.ndim(arr) < 2:
+                return arr
+            return arr[:, a:z]
+
+        def run(k):
+            (a, z), d = ranges[k], devices[k]
+            if z <= a:
+                return None
+            with torch.cuda.device(d):
+                y = ydata[a:z] if on_device else engine.to_device(np.ascontiguousarray(ydata[a:z], np.float64),
+                                                                  torch.device("cuda", d))
+                pf = None
+                if pixel_fixed_params:
+                    pf = {k_: torch.as_tensor(np.ascontiguousarray(np.asarray(v, float)[a:z])).to(y.device)
+                          for k_, v in pixel_fixed_params.items()}
+                up = lambda arr: arr if np.ndim(arr) < 2 else engine.to_device(np.ascontiguousarray(arr), y.device)  # noqa: E731
+                res = self.fit_device(xdata, y, p0=up(part(p0_m, a, z)),
+                                      bounds=(up(part(lb_m, a, z)), up(part(ub_m, a, z))), pixel_fixed_params=pf)
+                lazy_cov = res.pop("cov") if (self.want_cov is True or self.want_cov == "lazy") else None
+                host = {k_: (engine.to_host(v) if hasattr(v, "cpu") else v) for k_, v in res.items()}
+                host["cov_dev"] = lazy_cov
+                return host
+
+        if len(ranges) == 1:
+            parts = [run(0)]
+        else:
+            with ThreadPoolExecutor(len(ranges)) as pool:
+                parts = list(pool.map(run, range(len(ranges))))
+        live = [(r, p) for r, p in zip(ranges, parts) if p is not None]
+        first = live[0][1]
+        res = {"free_names": first["free_names"], "free_rows": first["free_rows"]}
+        for key in ("params", "status", "nfev", "njev", "cost", "r2"):
+            vals = [p[key] for _, p in live]
+            res[key] = vals[0] if len(vals) == 1 else np.concatenate(vals, axis=-1)
+        n_free = len(first["free_rows"])
+        if first["cov_dev"] is not None:
+            from .._lazy import LazyArray
+
+            res["cov"] = LazyArray((n_pixels, n_free, n_free), [(a, z, p["cov_dev"]) for (a, z), p in live])
+        elif first.get("cov") is not None:
+            res["cov"] = np.concatenate([p["cov"] for _, p in live], axis=0)
+        else:
+            res["cov"] = None
+        self.n_active_ = int(sum(p["n_active"] for _, p in live))
+        self._free_rows = res["free_rows"]
+        self._store(res, res["free_names"], n_pixels)
+        # the reference reports SLSQP's iteration count (result.nit); the closest quantity here is the
+        # number of residual evaluations of the two TRF phases
         self.pixel_results_.n_iterations = res["nfev"]
         return self
 
-    def _solve_on_face(self, xdata, ydata, idx, res, lb_m, ub_m, all_names, pixel_fixed_params, pix_fixed):
+    def fit_device(self, xdata, y_dev, p0=None, bounds=None, pixel_fixed_params=None, want_cov=None):
+        """Device-resident constrained fit: phase 1 (box-bounded TRF, tight tolerances), violation mask,
+        compaction, re-fit on the face ``f1 + f2 = 1`` and scatter, all on the GPU of ``y_dev`` with one
+        host synchronisation (the number of voxels on the face sizes the second launch).  Arguments and
+        result as :meth:`CurveFitSolver.fit_device`, plus ``n_active``.
+
+        A voxel that exhausts ``max(4 max_iter, 1000)`` evaluations in either phase is reported like a
+        failed ``curve_fit``: ``status 0``, parameters = its start values.  (SLSQP would report its last
+        iterate with ``success=False``; the two iteration limits are not comparable.)"""
+        import torch
+
+        saved = (self.tol, self.max_iter, dict(self.solver_kwargs), self.jac)
+        self.tol = min(self.tol, _TIGHT)
+        self.solver_kwargs.update(xtol=_TIGHT, gtol=_TIGHT)
+        self.max_iter = max(4 * saved[1], 1000)
+        self.jac = "analytic"
+        try:
+            res = super().fit_device(xdata, y_dev, p0=p0, bounds=bounds, pixel_fixed_params=pixel_fixed_params,
+                                     want_cov=want_cov)
+        finally:
+            self.tol, self.max_iter, self.solver_kwargs, self.jac = saved
+        res["n_active"] = 0
+        free_names = res["free_names"]
+        fracs = [n for n in free_names if n.startswith("f")] if self.fraction_constraint else []
+        if len(fracs) < 2:
+            return res
         desc = self._desc
+        all_names = list(desc.all_names)
         model_names = list(self.model.param_names)
+        par = res["params"]
+        i1, i2 = all_names.index("f1"), all_names.index("f2")
+        viol = (par[i1] + par[i2] > 1.0) & (res["status"] > 0)
+        idx = viol.nonzero().squeeze(1)
+        nv = int(idx.numel())  # the one host synchronisation
+        res["n_active"] = nv
+        if nv == 0:
+            return res
+        dev = y_dev.device
+        pix_fixed = set(pixel_fixed_params or {}) & set(all_names)
         face_id = MODEL_BI_S0 if desc.model_id == MODEL_TRI_S0 else MODEL_BI_REDUCED
         face_names = _all_names(face_id, desc.t1_mode)
         face_desc = ModelDesc(model_id=face_id, t1_mode=desc.t1_mode, repetition_time=desc.repetition_time,
                               mixing_time=desc.mixing_time, all_names=tuple(face_names), fixed={})
-        nv = idx.size
-        par = res["params"]
+        lb_def, ub_def = V_bounds(self.bounds, model_names)
+        lb_src = bounds[0] if bounds is not None else lb_def
+        ub_src = bounds[1] if bounds is not None else ub_def
 
-        def bound_of(arr, name):
+        def bound_of(src, name):
+            """Bound row of a model parameter on the face voxels: tensor (nv,) or float; None if fixed."""
             if name in desc.fixed or name in pix_fixed:
                 return None
-            row = arr[model_names.index(name)]
-            return row[idx] if np.ndim(row) else np.full(nv, float(row))
+            row = src[model_names.index(name)]
+            if isinstance(row, torch.Tensor) and row.ndim:
+                return row.index_select(0, idx)
+            return float(row)
 
-        src = {"f1": "f1", "D1": "D1", "D2": "D2", "S0": "S0", "T1": "T1"}
-        P0 = np.empty((len(face_names), nv))
-        LB = np.full((len(face_names), nv), -np.inf)
-        UB = np.full((len(face_names), nv), np.inf)
+        def as_row(v):
+            return v if isinstance(v, torch.Tensor) else torch.full((nv,), float(v), dtype=torch.float64, device=dev)
+
+        P0, LB, UB = [], [], []
         frozen = 0
         for j, nm in enumerate(face_names):
-            full_name = src[nm]
-            P0[j] = par[all_names.index(full_name)][idx]
-            lo, hi = bound_of(lb_m, full_name), bound_of(ub_m, full_name)
+            P0.append(par[all_names.index(nm)].index_select(0, idx))
+            lo, hi = bound_of(lb_src, nm), bound_of(ub_src, nm)
             if lo is None:
                 frozen |= 1 << j
-            else:
-                LB[j], UB[j] = lo, hi
+                lo, hi = -np.inf, np.inf
+            LB.append(as_row(lo))
+            UB.append(as_row(hi))
         # fold the bounds of f2 = 1 - f1 into those of f1 and start from the projection onto the face
         j1 = face_names.index("f1")
-        lo2, hi2 = bound_of(lb_m, "f2"), bound_of(ub_m, "f2")
-        LB[j1] = np.maximum(LB[j1], 1.0 - hi2)
-        UB[j1] = np.minimum(UB[j1], 1.0 - lo2)
-        f1, f2 = par[all_names.index("f1")][idx], par[all_names.index("f2")][idx]
-        P0[j1] = np.clip(f1 - 0.5 * (f1 + f2 - 1.0), LB[j1], UB[j1])
-        r2 = engine.trf_fit(face_desc, xdata, np.ascontiguousarray(ydata[idx]), P0, LB, UB, frozen,
+        lo2, hi2 = as_row(bound_of(lb_src, "f2")), as_row(bound_of(ub_src, "f2"))
+        LB[j1] = torch.maximum(LB[j1], 1.0 - hi2)
+        UB[j1] = torch.minimum(UB[j1], 1.0 - lo2)
+        f1, f2 = P0[j1], par[i2].index_select(0, idx)
+        P0[j1] = torch.minimum(torch.maximum(f1 - 0.5 * (f1 + f2 - 1.0), LB[j1]), UB[j1])
+        r2 = engine.trf_fit(face_desc, np.asarray(xdata, float), y_dev.index_select(0, idx),
+                            torch.stack(P0), torch.stack(LB), torch.stack(UB), frozen,
                             max_nfev=max(4 * self.max_iter, 1000), ftol=_TIGHT, xtol=_TIGHT, gtol=_TIGHT,
-                            jac_mode=engine.JAC_ANALYTIC, want_cov=False, device=self.device)
+                            jac_mode=engine.JAC_ANALYTIC, want_cov=False)
         ok = r2["status"] > 0
         for j, nm in enumerate(face_names):
-            row = all_names.index(src[nm])
-            par[row][idx[ok]] = r2["params"][j][ok]
-        par[all_names.index("f2")][idx[ok]] = 1.0 - r2["params"][j1][ok]
-        res["nfev"][idx] += r2["nfev"]
-        res["status"][idx[~ok]] = 0
-        res["cost"][idx[ok]] = r2["cost"][ok]
-        if res.get("r2") is not None:
-            res["r2"][idx[ok]] = r2["r2"][ok]  # same signal, same prediction on the face
+            row = par[all_names.index(nm)]
+            row.index_copy_(0, idx, torch.where(ok, r2["params"][j], row.index_select(0, idx)))
+        row2 = par[i2]
+        row2.index_copy_(0, idx, torch.where(ok, 1.0 - r2["params"][j1], row2.index_select(0, idx)))
+        res["nfev"].index_add_(0, idx, r2["nfev"])
+        res["status"].index_copy_(0, idx, torch.where(ok, res["status"].index_select(0, idx),
+                                                      torch.zeros_like(r2["status"])))
+        res["cost"].index_copy_(0, idx, torch.where(ok, r2["cost"], res["cost"].index_select(0, idx)))
+        res["r2"].index_copy_(0, idx, torch.where(ok, r2["r2"], res["r2"].index_select(0, idx)))
         if res["cov"] is not None:
             # J^T J is singular on the face (dS/dD3 = -b f3 e3 = 0): np.linalg.inv raises ->
             # NaN covariance (constrained_curvefit.py:300-305)
-            res["cov"][idx] = np.nan
+            res["cov"].index_fill_(0, idx, float("nan"))
+        return res

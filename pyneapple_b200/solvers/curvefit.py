@@ -270,8 +270,12 @@ class CurveFitSolver(BaseSolver):
                     else:
                         rows.append(filler)
                 elif src is not None:
-                    rows.append(src[model_names.index(name)])
-                    per_voxel = True
+                    v = src[model_names.index(name)]
+                    if isinstance(v, torch.Tensor) and v.ndim >= 1:
+                        rows.append(v)
+                        per_voxel = True
+                    else:  # a vector over the parameters: one value for all voxels
+                        rows.append(float(v))
                 else:
                     rows.append(float(default[model_names.index(name)]))
             if not per_voxel:
