@@ -3,27 +3,35 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-A *step* is one pass of the hot path over one full synthetic volume of the
-workload BASELINE.json's metric is quoted on (configs[1]: pixelwise biexp
-bounded curvefit, S0 mode, 256 x 256 x 64 voxels x 16 b-values = 4 194 304
-fits), i.e. what ``CurveFitSolver.fit`` does for that volume.
+A *step* is one pass of the hot path over one full synthetic volume of the workload BASELINE.json's
+metric is quoted on (configs[1]: pixelwise biexp bounded curvefit, S0 mode, 256 x 256 x 64 voxels x
+16 b-values = 4 194 304 fits), i.e. what ``CurveFitSolver.fit`` does for that volume.
 
-* ``value``      — voxels/s with the volume already resident in HBM
-                   (``pnb_trf_fit_device``), timed with CUDA events on the
-                   launching stream; multi-GPU: every rank fits its own volume
-                   (weak scaling, z-slabs of an N-times deeper volume), the
-                   parameter maps are gathered to rank 0 (NCCL) inside the
-                   timed region, time = max over ranks.
-* ``e2e``        — the same metric through the reference-facing call with HOST
-                   buffers (``CurveFitSolver.fit`` -> ``pnb_trf_fit_host``):
-                   pinned host input, H2D / kernels / D2H inside the timed region.
-* ``roofline``   — FP64-arithmetic roofline of the TRF kernel (it is FP64-CUDA-core
-                   bound, not HBM- or tensor-bound) plus the HBM
-                   fraction for completeness.
-* ``cpu_baseline`` — the oracle port (same SciPy calls as the reference, joblib
-                   over all host cores) on a bounded sample of the same workload.
+Top-level keys of the one JSON line (the bi-exponential NLLS half of the metric):
 
-``--impl reference`` times only that CPU path and prints the same JSON shape.
+* ``value``        voxels/s with the volume already resident in HBM (``pnb_trf_fit_device``), CUDA
+                   events on the launching stream.  N GPUs: weak scaling over the z-slabs of ONE
+                   N-times deeper volume (rank r fits slices 64 r .. 64 r + 63, its own part of the
+                   parameter fields), the parameter maps are gathered to rank 0 (NCCL) inside the
+                   timed region, overlapped with the next step's kernel; time = max over ranks.
+* ``e2e``          the same metric through the reference-facing call with HOST buffers
+                   (``CurveFitSolver.fit`` -> ``pnb_trf_fit_host``): page-locked input, H2D / kernels /
+                   D2H inside the timed region, covariances computed and left on the GPU (the default;
+                   ``e2e_eager_cov`` ships them too).  ``e2e_pageable``: plain numpy arrays, what an
+                   unmodified Pyneapple script passes.  ``e2e_fitter``: ``PixelWiseFitter.fit``.
+                   ``e2e_one_process`` (N > 1): rank 0 alone drives all N GPUs with ONE call
+                   (``device="all"`` -> ``pnb_trf_fit_host_multi``) over the whole N-slab volume.
+* ``roofline``     FP64-arithmetic roofline of the TRF kernel (FP64 CUDA-core bound, not HBM- or
+                   tensor-bound): model fraction, the hardware FP64-pipe utilisation
+                   and DRAM traffic of the bench-size launch from the committed ncu capture.
+* ``cpu_baseline`` the UNMODIFIED reference (``baseline/_ref``, multi_threading=True, n_pools=-1) on a
+                   bounded sample of the same workload on the box's host cores (kind "reference";
+                   "port" = oracle/ref_port.py, the same SciPy calls, only if the reference is absent).
+* ``nnls_value`` / ``nnls_e2e`` / ``nnls_roofline`` / ``nnls_cpu_baseline``  the 250-bin NNLS half (config C3).
+* ``c5``           constrained tri-exponential fit of the fixed 512 x 512 x 128 x 24 volume (config C5),
+                   STRONG scaling: the volume's z-slabs are spread over the N GPUs.
+
+``--impl reference`` times only the reference's CPU path and prints the same JSON shape.
 """
 
 from __future__ import annotations
@@ -39,12 +47,17 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 os.environ.setdefault("PYNEAPPLE_QUIET", "1")
+os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")  # the gather overlaps the next step's kernel
 
 import numpy as np  # noqa: E402
 
 METRIC = "voxel fits/sec (biexp NLLS, 250-bin NNLS) at 1/2/4/8 B200 vs scipy CPU"
 UNIT = "voxel fits/s"
 WORKLOAD = "C2: pixelwise biexp (fit_s0) bounded curvefit, 256x256x64 voxels x 16 b-values, TRF, max_iter 250, tol 1e-8"
+NNLS_WORKLOAD = ("C3: pixelwise NNLS n_bins=250, d_range [0.0008, 0.5], reg_order=2, mu=0.02, max_iter=250, "
+                 "256x256x64 voxels x 16 b-values")
+C5_WORKLOAD = ("C5: pixelwise triexp (reduced) constrained curvefit (f1+f2<=1), 512x512x128 voxels x 24 b-values, "
+               "max_iter 250, tol 1e-8")
 C_EXP = 25  # FP64 flop per exp (SURVEY.md §8d convention)
 
 
@@ -55,6 +68,20 @@ def algorithmic_flops(n, m, k_exp, nfev_sum, njev_sum):
     f_svd = 6 * (n * (n - 1) // 2) * (6 * (m + n) + 12)
     f_it = 2 * m * n + 3 * m * n + 2 * n + f_svd + 10 * 6 * n + 3 * (2 * m * n + 6 * n) + 12 * n
     return nfev_sum * f_f + njev_sum * (f_j + f_it)
+
+
+def nnls_algorithmic_flops(m, n_bins, w, iters, k_final):
+    """SURVEY.md §8(d) K4 model, evaluated from the device counters (iterations, final active size).
+
+    adds = (iters + k_final) / 2 outer iterations, mean active size ~0.6 k_final.
+    """
+    iters = np.asarray(iters, np.float64)
+    k = np.asarray(k_final, np.float64)
+    n_outer = 0.5 * (iters + k)
+    kbar = 0.6 * k
+    per_outer = 2 * m * n_bins + 2 * (2 * w + 1) * n_bins + 2 * m * kbar + (2 * w + 1) * kbar
+    per_inner = 3 * kbar * kbar + 2 * m * kbar
+    return float(np.sum(2 * m * n_bins + n_outer * per_outer + iters * per_inner))
 
 
 class ClockSampler:
@@ -119,181 +146,133 @@ class ClockSampler:
         return out
 
 
-def nnls_algorithmic_flops(m, n_bins, w, iters, k_final):
-    """SURVEY.md §8(d) K4 model, evaluated from the device counters (iterations, final active size).
-
-    adds = (iters + k_final) / 2 outer iterations, mean active size ~0.6 k_final.
-    """
-    iters = np.asarray(iters, np.float64)
-    k = np.asarray(k_final, np.float64)
-    n_outer = 0.5 * (iters + k)
-    kbar = 0.6 * k
-    per_outer = 2 * m * n_bins + 2 * (2 * w + 1) * n_bins + 2 * m * kbar + (2 * w + 1) * kbar
-    per_inner = 3 * kbar * kbar + 2 * m * kbar
-    return float(np.sum(2 * m * n_bins + n_outer * per_outer + iters * per_inner))
-
-
-def _traffic(name):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/), or None."""
+def _counters(name):
+    """ncu counters of the bench-size launch of a kernel (profiles/<name>, written from one
+    `ncu --set full --launch-count 1` capture by scripts/ncu_counters.py), or {}."""
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", name))).get("dram_bytes_per_launch")
+        return json.load(open(os.path.join(ROOT, "profiles", name)))
     except (OSError, ValueError):
-        return None
+        return {}
 
 
-def bench_nnls(args, world, rank, local_rank, dev):
-    """250-bin NNLS half of the metric: config C3 (d_range [0.0008, 0.5], reg_order 2, mu 0.02)."""
-    import torch
-    import torch.distributed as dist
+class Dist:
+    """The few collective helpers the bench needs (no-ops for one rank)."""
 
-    from pyneapple_b200 import _lib, engine, models, synth
-    from pyneapple_b200.solvers import NNLSSolver
-    from pyneapple_b200.solvers.nnls import regularization_matrix
+    def __init__(self):
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
-    base = synth.CONFIGS["C3"]
-    # weak scaling: every rank fits its own volume of the configuration (same parameter fields, its
-    # own noise), i.e. slab `rank` of a stack of C3 volumes
-    cfg = synth.Config(**{**base.__dict__, "shape": (base.shape[0], base.shape[1], args.slices)})
-    b, img, _ = synth.make_volume(cfg, 0, args.slices, replica=rank)
-    y_host = img.reshape(-1, b.shape[0])
-    del img
-    n_vox, n_b = y_host.shape
-    model = models.NNLSModel(d_range=(0.0008, 0.5), n_bins=250)
-    basis = model.get_basis(b)
-    R = regularization_matrix(250, 2, 0.02)
-    y_dev = torch.as_tensor(y_host).to(dev)
-    steps = max(1, min(args.steps, 3))
-    r = engine.nnls_fit(basis, R, y_dev, 250, device=local_rank)  # warm-up
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    nsampler = ClockSampler(0, world)
-    if rank == 0:
-        nsampler.start()
-    l0 = _lib.launch_count()
-    e0.record()
-    for _ in range(steps):
-        r = None  # release the previous step's 8.4 GB of coefficients first: no cudaMalloc in the timed region
-        r = engine.nnls_fit(basis, R, y_dev, 250, device=local_rank)
-    e1.record()
-    torch.cuda.synchronize()
-    launches = _lib.launch_count() - l0
-    nclocks = nsampler.stop() if rank == 0 else None
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms = float(ms.item())
-    value = n_vox * world * steps / (ms * 1e-3)
-    iters = r["iterations"].cpu().numpy()
-    k_final = (r["coefficients"] > 0).sum(dim=1).cpu().numpy()
-    ok_rate = float((r["status"] == 1).double().mean().item())
-    del r
-    torch.cuda.empty_cache()
-    # e2e through NNLSSolver.fit with pinned host buffers
-    y_pin = _lib.pinned_empty(y_host.shape)
-    y_pin[...] = y_host
-    solver = NNLSSolver(model=model, reg_order=2, mu=0.02, max_iter=250, device=local_rank, pinned_outputs=True)
-    solver.fit(b, y_pin)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    solver.fit(b, y_pin)
-    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = n_vox * world / float(e2e_s.item())
-    if rank != 0:
-        return None
-    flops = nnls_algorithmic_flops(n_b, 250, 2, iters, k_final)
-    kernel_ms = ms / steps
-    fp64_peak = _lib.measure_fp64_peak(local_rank)
-    alg_bytes = n_vox * (8 * n_b + 8 * 250 + 8 + 4 + 4 + 8)
-    out = {
-        "workload": "C3: pixelwise NNLS n_bins=250, d_range [0.0008, 0.5], reg_order=2, mu=0.02, max_iter=250, "
-                    "256x256x64 voxels x 16 b-values",
-        "value": value, "unit": UNIT, "steps": steps, "ms_per_step": ms / steps, "gpu_launches": int(launches),
-        "clocks": nclocks,
-        "voxels_per_gpu": n_vox, "success_rate": ok_rate, "mean_iterations": float(iters.mean()),
-        "mean_active_set": float(k_final.mean()), "max_active_set": int(k_final.max()),
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(y_host.nbytes),
-                "d2h_bytes_per_step": int(n_vox * (250 * 8 + 8 + 4 + 4 + 8)),
-                "api": "NNLSSolver.fit(numpy pinned) -> pnb_nnls_fit_host"},
-        "roofline": {"bound": "fp64", "kernel": "nnls_v3_kernel<16,2> (+ nnls_kernel<2> for the voxels it hands over)", "achieved": flops / (kernel_ms * 1e-3) / 1e12,
-                     "peak": fp64_peak, "unit": "TFLOP/s", "frac": flops / (kernel_ms * 1e-3) / 1e12 / fp64_peak,
-                     "flops_per_launch": flops, "flop_model": "SURVEY.md §8(d) K4, from device iteration counters",
-                     "kernel_ms": kernel_ms, "traffic": _traffic("nnls_traffic.json"),
-                     "hbm": {"achieved": alg_bytes / (kernel_ms * 1e-3) / 1e9, "unit": "GB/s",
-                             "algorithmic_bytes_per_launch": alg_bytes},
-                     "shared_memory": "the fast kernel moves 0.80 shared-memory wavefronts per clock and SM (1.0 = "
-                                      "the pipe's limit; profiles/r1_final_summary.md): half of them are the "
-                                      "dictionary columns of the dual pass"},
-    }
-    if not args.no_cpu_baseline:
+    def init(self, dev):
+        import torch.distributed as dist
+
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=dev)
+
+    def barrier(self):
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+
+    def max(self, value, dev):
+        import torch
+        import torch.distributed as dist
+
+        t = torch.tensor([float(value)], dtype=torch.float64, device=dev)
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum(self, value, dev):
+        import torch
+        import torch.distributed as dist
+
+        t = torch.tensor([float(value)], dtype=torch.float64, device=dev)
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def finish(self):
+        import torch.distributed as dist
+
+        if self.world > 1:
+            dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------
+# the reference's own CPU path (baseline/_ref), timed on the box's host cores
+# ----------------------------------------------------------------------------------------------
+class CpuReference:
+    """``kind`` "reference": the unmodified Pyneapple solvers from baseline/_ref with
+    multi_threading=True, n_pools=-1 (solvers/curvefit.py:201-213, nnls_solver.py:153-172);
+    "port": oracle/ref_port.py (the same SciPy calls) when the reference has not been installed."""
+
+    def __init__(self):
+        from oracle import reference
+
+        self.pyn = reference.import_reference(with_toml=False)
+        self.kind = "reference" if self.pyn is not None else "port"
+        self.cores = os.cpu_count() or 1
+
+    def _solver(self, what, cfg):
+        from pyneapple.models import BiExpModel, NNLSModel, TriExpModel
+        from pyneapple.solvers import ConstrainedCurveFitSolver, CurveFitSolver, NNLSSolver
+
+        if what == "trf":
+            return CurveFitSolver(model=BiExpModel(fit_s0=True), max_iter=250, tol=1e-8, p0=cfg.p0,
+                                  bounds=cfg.bounds, multi_threading=True, n_pools=-1)
+        if what == "nnls":
+            return NNLSSolver(model=NNLSModel(d_range=(0.0008, 0.5), n_bins=250), reg_order=2, mu=0.02,
+                              max_iter=250, multi_threading=True, n_pools=-1)
+        return ConstrainedCurveFitSolver(model=TriExpModel(), max_iter=250, tol=1e-8, p0=cfg.p0, bounds=cfg.bounds,
+                                         fraction_constraint=True, multi_threading=True, n_pools=-1)
+
+    def run(self, what, cfg, b, y):
+        """Fit ``y`` on all host cores; returns (seconds, result dict)."""
+        if self.kind == "reference":
+            s = self._solver(what, cfg)
+            t = time.perf_counter()
+            s.fit(b, y)
+            dt = time.perf_counter() - t
+            if what == "nnls":
+                return dt, {"coefficients": s.params_["coefficients"], "residual": s.diagnostics_["residual"],
+                            "success": np.array([pr.success for pr in s.pixel_results_])}
+            names = s.model.param_names
+            return dt, {"params": np.stack([np.atleast_1d(s.params_[n]) for n in names]),
+                        "success": np.array([pr.success for pr in s.pixel_results_])}
         from oracle import ref_port
 
-        cores = os.cpu_count() or 1
-        sb, sy, _ = synth.sample_voxels(base, 32768, z=0)
-        ref_port.nnls_fit(sb, sy[: 8 * cores], (0.0008, 0.5), 250, 2, 0.02, 250, n_jobs=-1)
-        t0 = time.perf_counter()
-        probe = ref_port.nnls_fit(sb, sy[: 64 * cores], (0.0008, 0.5), 250, 2, 0.02, 250, n_jobs=-1)
-        rate = 64 * cores / (time.perf_counter() - t0)
-        n = int(min(32768, max(64 * cores, rate * 10.0)))
-        t0 = time.perf_counter()
-        ref = ref_port.nnls_fit(sb, sy[:n], (0.0008, 0.5), 250, 2, 0.02, 250, n_jobs=-1)
-        dt = time.perf_counter() - t0
-        del probe
-        out["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
-                               "sample": f"{n} voxels, scipy.optimize.nnls per voxel via oracle/ref_port.py, "
-                                         f"joblib n_jobs=-1, {dt:.1f} s"}
-        chk = NNLSSolver(model=model, reg_order=2, mu=0.02, max_iter=250, device=local_rank).fit(sb, sy[:n])
-        out["parity_vs_cpu_sample"] = {
-            "voxels": n,
-            "max_abs_coefficient_diff": float(np.abs(chk.params_["coefficients"] - ref["coefficients"]).max()),
-            "max_abs_residual_diff": float(np.abs(chk.diagnostics_["residual"] - ref["residual"]).max()),
-            "success_flags_equal": bool(((chk.status_ == 1) == ref["success"]).all()),
-        }
-    return out
+        n = y.shape[0]
+        t = time.perf_counter()
+        if what == "nnls":
+            res = ref_port.nnls_fit(b, y, (0.0008, 0.5), 250, 2, 0.02, 250, n_jobs=-1)
+        else:
+            kind, names = ("biexp", ["f1", "D1", "D2", "S0"]) if what == "trf" else ("triexp", ["f1", "D1", "f2", "D2", "D3"])
+            model = ref_port.Model(kind, "s0" if what == "trf" else "reduced")
+            P0, LB, UB = (np.tile(np.array(v)[:, None], (1, n)) for v in (
+                [cfg.p0[k] for k in names], [cfg.bounds[k][0] for k in names], [cfg.bounds[k][1] for k in names]))
+            fit = ref_port.curvefit_fit if what == "trf" else ref_port.constrained_fit
+            res = fit(model, b, y, P0, LB, UB, max_iter=250, tol=1e-8, n_jobs=-1)
+        return time.perf_counter() - t, res
 
-
-def problem_arrays(cfg):
-    names = ["f1", "D1", "D2", "S0"]
-    return (names, np.array([cfg.p0[n] for n in names]), np.array([cfg.bounds[n][0] for n in names]),
-            np.array([cfg.bounds[n][1] for n in names]))
-
-
-def cpu_reference_run(b, y, cfg, n_jobs):
-    """The oracle port: one scipy curve_fit(method='trf') per voxel, joblib pool over all cores."""
-    from oracle import ref_port
-
-    names, p0, lb, ub = problem_arrays(cfg)
-    n = y.shape[0]
-    model = ref_port.Model("biexp", "s0")
-    P0, LB, UB = (np.tile(v[:, None], (1, n)) for v in (p0, lb, ub))
-    t = time.perf_counter()
-    res = ref_port.curvefit_fit(model, b, y, P0, LB, UB, max_iter=250, tol=1e-8, n_jobs=n_jobs)
-    return time.perf_counter() - t, res
-
-
-def cpu_baseline(cfg, target_seconds=15.0, max_vox=65536):
-    """Bounded sample of the workload on all host cores; returns (vox/s, description dict)."""
-    from pyneapple_b200 import synth
-
-    cores = os.cpu_count() or 1
-    b, y, _ = synth.sample_voxels(cfg, min(max_vox, 65536), z=0)
-    # warm the loky pool and probe the rate
-    cpu_reference_run(b, y[: 8 * cores], cfg, -1)
-    dt, _ = cpu_reference_run(b, y[: 32 * cores], cfg, -1)
-    rate = 32 * cores / dt
-    n = int(min(max_vox, max(64 * cores, rate * target_seconds)))
-    n = min(n, y.shape[0])
-    dt, res = cpu_reference_run(b, y[:n], cfg, -1)
-    return n / dt, {
-        "value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
-        "sample": f"{n} voxels (every k-th voxel of slice 0 of the C2 volume), scipy {__import__('scipy').__version__} "
-                  f"curve_fit per voxel via oracle/ref_port.py, joblib loky pool n_jobs=-1, {dt:.1f} s",
-    }, (b, y[:n], res)
+    def baseline(self, what, cfg, b, y, target_seconds=12.0):
+        """Bounded sample: warm the loky pool, probe the rate, then time ~target_seconds of work."""
+        c = self.cores
+        self.run(what, cfg, b, y[: 8 * c])
+        dt, _ = self.run(what, cfg, b, y[: 32 * c])
+        rate = 32 * c / dt
+        n = int(min(y.shape[0], max(64 * c, rate * target_seconds)))
+        dt, res = self.run(what, cfg, b, y[:n])
+        desc = {"trf": "CurveFitSolver (scipy curve_fit per voxel)", "nnls": "NNLSSolver (scipy.optimize.nnls per voxel)",
+                "c5": "ConstrainedCurveFitSolver (scipy SLSQP per voxel)"}[what]
+        src = ("unmodified reference from baseline/_ref, multi_threading=True, n_pools=-1 (joblib/loky over all cores)"
+               if self.kind == "reference" else "oracle/ref_port.py (the same SciPy calls), joblib n_jobs=-1")
+        return {"value": n / dt, "unit": UNIT, "cores": c, "kind": self.kind,
+                "sample": f"{n} voxels of the workload (every k-th voxel of one slice), {desc}, {src}, "
+                          f"scipy {__import__('scipy').__version__}, {dt:.1f} s"}, n, res
 
 
 def run_reference(args):
@@ -303,17 +282,18 @@ def run_reference(args):
     if rank != 0:
         return 0
     cfg = synth.CONFIGS["C2"]
-    cores = os.cpu_count() or 1
+    cpu = CpuReference()
+    cores = cpu.cores
     b, y, _ = synth.sample_voxels(cfg, 65536, z=0)
-    cpu_reference_run(b, y[: 8 * cores], cfg, -1)  # pool warm-up
-    dt, _ = cpu_reference_run(b, y[: 32 * cores], cfg, -1)
+    cpu.run("trf", cfg, b, y[: 8 * cores])  # pool warm-up
+    dt, _ = cpu.run("trf", cfg, b, y[: 32 * cores])
     rate = 32 * cores / dt
     per_step = int(min(65536, max(64 * cores, rate * max(2.0, 60.0 / max(1, args.steps + args.warmup)))))
     for _ in range(args.warmup):
-        cpu_reference_run(b, y[:per_step], cfg, -1)
+        cpu.run("trf", cfg, b, y[:per_step])
     t = time.perf_counter()
     for _ in range(args.steps):
-        cpu_reference_run(b, y[:per_step], cfg, -1)
+        cpu.run("trf", cfg, b, y[:per_step])
     total = time.perf_counter() - t
     value = per_step * args.steps / total
     line = {
@@ -321,8 +301,10 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": {"workload": WORKLOAD, "sample_per_step": per_step},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{per_step} voxels per step, scipy curve_fit per voxel, joblib n_jobs=-1"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": cpu.kind,
+                         "sample": f"{per_step} voxels per step, "
+                                   + ("the unmodified reference's CurveFitSolver(multi_threading=True, n_pools=-1) from baseline/_ref"
+                                      if cpu.kind == "reference" else "oracle/ref_port.py (same SciPy calls), joblib n_jobs=-1")},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -352,6 +334,218 @@ def _emit(line: dict):
         os.write(_REAL_STDOUT, data)
 
 
+def _guard(fn, *a, **kw):
+    """Optional sections must not take the headline down with them."""
+    try:
+        return fn(*a, **kw)
+    except Exception as exc:  # noqa: BLE001
+        import traceback
+
+        traceback.print_exc()
+        return {"error": f"{type(exc).__name__}: {exc}"}
+
+
+def problem_arrays(cfg, names):
+    return (np.array([cfg.p0[n] for n in names]), np.array([cfg.bounds[n][0] for n in names]),
+            np.array([cfg.bounds[n][1] for n in names]))
+
+
+def _time_host(fn, reps, D, dev):
+    """Wall time of ``reps`` calls of a host-API function, max over ranks."""
+    import torch
+
+    fn()
+    torch.cuda.synchronize()
+    D.barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fn()
+    return D.max(time.perf_counter() - t0, dev) / reps
+
+
+# ----------------------------------------------------------------------------------------------
+# NNLS half (config C3)
+# ----------------------------------------------------------------------------------------------
+def bench_nnls(args, D, dev, cpu):
+    import torch
+
+    from pyneapple_b200 import _lib, engine, models, synth
+    from pyneapple_b200.solvers import NNLSSolver
+    from pyneapple_b200.solvers.nnls import regularization_matrix
+
+    world, rank, local_rank = D.world, D.rank, D.local_rank
+    base = synth.CONFIGS["C3"]
+    # weak scaling over the z-slabs of one world-times deeper volume
+    cfg = synth.Config(**{**base.__dict__, "shape": (base.shape[0], base.shape[1], args.slices * world)})
+    b, img, _ = synth.make_volume(cfg, args.slices * rank, args.slices * (rank + 1))
+    y_host = img.reshape(-1, b.shape[0])
+    del img
+    n_vox, n_b = y_host.shape
+    model = models.NNLSModel(d_range=(0.0008, 0.5), n_bins=250)
+    basis = model.get_basis(b)
+    R = regularization_matrix(250, 2, 0.02)
+    y_dev = torch.as_tensor(y_host).to(dev)
+    steps = max(1, min(args.steps, 3))
+    r = engine.nnls_fit(basis, R, y_dev, 250)  # warm-up
+    D.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nsampler = ClockSampler(0, world)
+    if rank == 0:
+        nsampler.start()
+    l0 = _lib.launch_count()
+    e0.record()
+    for _ in range(steps):
+        r = None  # release the previous step's 8.4 GB of coefficients first: no cudaMalloc in the timed region
+        r = engine.nnls_fit(basis, R, y_dev, 250)
+    e1.record()
+    torch.cuda.synchronize()
+    launches = _lib.launch_count() - l0
+    nclocks = nsampler.stop() if rank == 0 else None
+    ms = D.max(e0.elapsed_time(e1), dev)
+    value = n_vox * world * steps / (ms * 1e-3)
+    redo = int(_lib.load().pnb_nnls_last_redo_count(local_rank))
+    iters = r["iterations"].cpu().numpy()
+    k_final = (r["coefficients"] > 0).sum(dim=1).cpu().numpy()
+    ok_rate = float((r["status"] == 1).double().mean().item())
+    del r, y_dev
+    torch.cuda.empty_cache()
+    # e2e through NNLSSolver.fit: page-locked host buffers / plain numpy arrays
+    y_pin = _lib.pinned_empty(y_host.shape)
+    y_pin[...] = y_host
+    solver = NNLSSolver(model=model, reg_order=2, mu=0.02, max_iter=250, device=local_rank, pinned_outputs=True)
+    e2e_s = _time_host(lambda: solver.fit(b, y_pin), 1, D, dev)
+    del solver
+    pageable = None
+    if rank == 0 and world == 1:
+        plain = NNLSSolver(model=model, reg_order=2, mu=0.02, max_iter=250, device=local_rank, pinned_outputs=False)
+        pageable = _time_host(lambda: plain.fit(b, y_host), 1, D, dev)
+        del plain
+    if rank != 0:
+        return None
+    flops = nnls_algorithmic_flops(n_b, 250, 2, iters, k_final)
+    kernel_ms = ms / steps
+    fp64_peak = _lib.measure_fp64_peak(local_rank)
+    alg_bytes = n_vox * (8 * n_b + 8 * 250 + 8 + 4 + 4 + 8)
+    ctr = _counters("r2_nnls_counters.json")
+    d2h = int(n_vox * (250 * 8 + 8 + 4 + 4 + 8))
+    out = {
+        "workload": NNLS_WORKLOAD,
+        "value": value, "unit": UNIT, "steps": steps, "ms_per_step": ms / steps, "gpu_launches": int(launches),
+        "clocks": nclocks,
+        "voxels_per_gpu": n_vox, "success_rate": ok_rate, "mean_iterations": float(iters.mean()),
+        "mean_active_set": float(k_final.mean()), "max_active_set": int(k_final.max()),
+        "handed_to_robust_kernel": redo,
+        "e2e": {"value": n_vox * world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(y_host.nbytes),
+                "d2h_bytes_per_step": d2h, "api": "NNLSSolver.fit(page-locked numpy) -> pnb_nnls_fit_host"},
+        "roofline": {"bound": "fp64", "kernel": "nnls_v3_kernel<16,2> (+ nnls_kernel<2> for the voxels it hands over)",
+                     "achieved": flops / (kernel_ms * 1e-3) / 1e12,
+                     "peak": fp64_peak, "unit": "TFLOP/s", "frac": flops / (kernel_ms * 1e-3) / 1e12 / fp64_peak,
+                     "frac_pipe": ctr.get("fp64_pipe_frac"),
+                     "flops_per_launch": flops, "flop_model": "SURVEY.md §8(d) K4, from device iteration counters",
+                     "kernel_ms": kernel_ms, "traffic": ctr.get("dram_bytes_per_launch"),
+                     "counters_source": ctr.get("source"),
+                     "hbm": {"achieved": alg_bytes / (kernel_ms * 1e-3) / 1e9, "unit": "GB/s",
+                             "algorithmic_bytes_per_launch": alg_bytes},
+                     "shared_memory_wavefronts_per_voxel": ctr.get("smem_wavefronts_per_voxel")},
+    }
+    if pageable is not None:
+        out["e2e_pageable"] = {"value": n_vox / pageable, "unit": UNIT,
+                               "api": "NNLSSolver.fit(plain numpy arrays): input and results staged through page-locked blocks"}
+    if cpu is not None:
+        sb, sy, _ = synth.sample_voxels(base, 32768, z=0)
+        cb, n, ref = cpu.baseline("nnls", base, sb, sy, 10.0)
+        out["cpu_baseline"] = cb
+        chk = NNLSSolver(model=model, reg_order=2, mu=0.02, max_iter=250, device=local_rank).fit(sb, sy[:n])
+        out["parity_vs_cpu_sample"] = {
+            "voxels": n,
+            "max_abs_coefficient_diff": float(np.abs(chk.params_["coefficients"] - ref["coefficients"]).max()),
+            "max_abs_residual_diff": float(np.abs(chk.diagnostics_["residual"] - ref["residual"]).max()),
+            "success_flags_equal": bool(((chk.status_ == 1) == ref["success"]).all()),
+        }
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# constrained tri-exponential, fixed volume, strong scaling (config C5)
+# ----------------------------------------------------------------------------------------------
+def bench_c5(args, D, dev, cpu):
+    import torch
+
+    from pyneapple_b200 import _lib, models, parallel, synth
+    from pyneapple_b200.solvers import ConstrainedCurveFitSolver
+
+    world, rank, local_rank = D.world, D.rank, D.local_rank
+    cfg = synth.CONFIGS["C5"]
+    Z = args.c5_slices
+    if Z != cfg.shape[2]:
+        cfg = synth.Config(**{**cfg.__dict__, "shape": (cfg.shape[0], cfg.shape[1], Z)})
+    z0, z1 = parallel.shard_bounds(Z, world)[rank]
+    b, img = synth.make_volume_device(cfg, z0, z1, device=dev)
+    y = img.reshape(-1, b.shape[0])
+    del img
+    n_local = y.shape[0]
+    n_total = cfg.shape[0] * cfg.shape[1] * Z
+    solver = ConstrainedCurveFitSolver(models.TriExpModel(), p0=cfg.p0, bounds=cfg.bounds, want_cov=False,
+                                       device=local_rank, **cfg.solver_kwargs)
+    sizes = [(b_ - a_) * cfg.shape[0] * cfg.shape[1] for a_, b_ in parallel.shard_bounds(Z, world)]
+    gathered = [None]
+
+    def step():
+        r = solver.fit_device(b, y)
+        if world > 1:
+            gathered[0] = parallel.gather_to_rank0(r["params"], sizes, dim=1, concat=False, out=gathered[0])
+        return r
+
+    r = step()
+    D.barrier()
+    steps = max(1, min(args.steps, 3))
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        r = step()
+    e1.record()
+    torch.cuda.synchronize()
+    launches = _lib.launch_count() - l0
+    ms = D.max(e0.elapsed_time(e1), dev) / steps
+    n_active = D.sum(r["n_active"], dev)
+    ok = D.sum(float((r["status"] > 0).sum().item()), dev)
+    feas = float((r["params"][0] + r["params"][2]).max().item())
+    nfev = D.sum(float(r["nfev"].sum().item()), dev)
+    del r, y, gathered
+    torch.cuda.empty_cache()
+    # e2e through the host API on one 16-slice slab (4.19 M voxels) of the volume, rank 0 at N = 1
+    e2e = None
+    if world == 1:
+        zs = min(16, Z)
+        hb, himg, _ = synth.make_volume(cfg, 0, zs)
+        hy = _lib.pinned_empty((himg.shape[0] * himg.shape[1] * zs, hb.shape[0]))
+        hy[...] = himg.reshape(hy.shape)
+        del himg
+        t = _time_host(lambda: solver.fit(hb, hy), 1, D, dev)
+        e2e = {"value": hy.shape[0] / t, "unit": UNIT, "voxels": int(hy.shape[0]),
+               "h2d_bytes_per_step": int(hy.nbytes), "d2h_bytes_per_step": int(hy.shape[0] * (5 * 8 + 4 * 3 + 8 * 2)),
+               "api": "ConstrainedCurveFitSolver.fit(page-locked numpy): upload, both phases on the GPU, download"}
+        del hy
+    if rank != 0:
+        return None
+    out = {
+        "workload": C5_WORKLOAD + (f" (reduced to {Z} slices)" if Z != 128 else ""),
+        "scaling": "strong", "n_gpus": world, "voxels": n_total, "voxels_per_gpu": n_local,
+        "value": n_total / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+        "gpu_launches": int(launches), "timed": "fit_device (phase 1, violation mask, compaction, face re-fit, scatter)"
+                                                 + (" + NCCL gather of the parameter maps to rank 0" if world > 1 else ""),
+        "data": "synthetic, generated on the device (pyneapple_b200.synth.make_volume_device)",
+        "constraint_active_fraction": n_active / n_total, "success_rate": ok / n_total,
+        "max_f1_plus_f2": feas, "mean_nfev": nfev / n_total, "e2e": e2e,
+    }
+    if cpu is not None:
+        sb, sy, _ = synth.sample_voxels(synth.CONFIGS["C5"], 16384, z=0)
+        cb, n, ref = cpu.baseline("c5", synth.CONFIGS["C5"], sb, sy, 10.0)
+        out["cpu_baseline"] = cb
+    return out
+
+
 def main():
     _quiet_stdout()
     ap = argparse.ArgumentParser()
@@ -361,157 +555,190 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--jac", default="reference", choices=["reference", "analytic"])
     ap.add_argument("--slices", type=int, default=64, help="z-slices per GPU (64 = the full C2 volume)")
+    ap.add_argument("--c5-slices", type=int, default=128, help="z-slices of the C5 volume (128 = the full volume)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-nnls", action="store_true")
+    ap.add_argument("--no-c5", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip e2e_pageable / e2e_fitter / e2e_one_process")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
 
     import torch
-    import torch.distributed as dist
 
     from pyneapple_b200 import _lib, engine, models, parallel, synth
+    from pyneapple_b200.fitters import PixelWiseFitter
     from pyneapple_b200.solvers import CurveFitSolver
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    D = Dist()
+    world, rank, local_rank = D.world, D.rank, D.local_rank
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: pyneapple_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    D.init(dev)
 
     base = synth.CONFIGS["C2"]
-    # weak scaling: every rank fits its own C2 volume (same parameter fields, its own noise), i.e.
-    # z-slab `rank` of a stack of `world` C2 volumes.  Cutting one world-times deeper volume instead
-    # would give every rank a different part of the parameter ranges and a different amount of work.
-    cfg = synth.Config(**{**base.__dict__, "shape": (base.shape[0], base.shape[1], args.slices)})
-    b, img, _ = synth.make_volume(cfg, 0, args.slices, replica=rank)
+    # weak scaling over the z-slabs of ONE world-times deeper volume: rank r holds slices
+    # [slices r, slices (r + 1)) — its own part of the smooth parameter fields, hence its own amount
+    # of work (at N = 1 this is exactly config C2)
+    cfg = synth.Config(**{**base.__dict__, "shape": (base.shape[0], base.shape[1], args.slices * world)})
+    b, img, _ = synth.make_volume(cfg, args.slices * rank, args.slices * (rank + 1))
     n_b = b.shape[0]
     y_host = img.reshape(-1, n_b)
-    del img
     n_vox = y_host.shape[0]
-    names, p0, lb, ub = problem_arrays(cfg)
+    names = ["f1", "D1", "D2", "S0"]
+    p0, lb, ub = problem_arrays(cfg, names)
     model = models.BiExpModel(fit_s0=True)
     desc = models.describe_model(model)
     jac_mode = engine.JAC_TWO_POINT if args.jac == "reference" else engine.JAC_ANALYTIC
 
     # ------------------------------------------------------------ device-resident steps
     y_dev = torch.as_tensor(y_host).to(dev)
-
     gathered = [None]
-    peer = None
-    # PNB_GATHER=peer: CUDA-IPC peer-memory pushes instead of the NCCL gather (slower on this pool:
-    # 36 GB/s per pusher through cudaIpc mappings against ~570 GB/s for NCCL, profiles/r1_final_multi_gpu.md)
-    if world > 1 and os.environ.get("PNB_GATHER", "nccl") == "peer":
-        try:
-            peer = parallel.PeerGather((4, n_vox), torch.float64, dev)
-        except Exception as exc:  # no CUDA IPC in this environment: NCCL gather instead
-            print(f"rank {rank}: peer-memory gather unavailable ({exc}); using the NCCL gather", file=sys.stderr)
-        ok = torch.tensor([1 if peer is not None else 0], device=dev)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if int(ok.item()) == 0:
-            peer = None
+    side = torch.cuda.Stream(dev, priority=-1) if world > 1 else None
+    cur = torch.cuda.current_stream(dev)
 
-    def device_step():
-        r = engine.trf_fit(desc, b, y_dev, p0, lb, ub, 0, max_nfev=250, ftol=1e-8, jac_mode=jac_mode,
-                           device=local_rank)
-        if world > 1:
-            # the blocks arrive stacked (world, n_params, n_vox): every rank's block is the parameter
-            # map of its z-slab
-            if peer is not None:
-                peer.push(r["params"])  # copy engines over NVLink peer memory; completed by the sync below
-            else:
-                gathered[0] = parallel.gather_to_rank0(r["params"], [n_vox] * world, dim=1, concat=False,
-                                                       out=gathered[0])
-        return r
+    def fit_on_device():
+        return engine.trf_fit(desc, b, y_dev, p0, lb, ub, 0, max_nfev=250, ftol=1e-8, jac_mode=jac_mode, want_cov="eager")
 
-    for _ in range(args.warmup):
-        r = device_step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    def enqueue_gather(res, done):
+        # the blocks arrive stacked (world, n_params, n_vox): every rank's block is the parameter map of
+        # its z-slab.  Runs on a high-priority side stream and is enqueued BEFORE the next step's kernel,
+        # so the NCCL kernel's few CTAs are placed first and the persistent TRF kernel fills the rest.
+        side.wait_event(done)
+        with torch.cuda.stream(side):
+            gathered[0] = parallel.gather_to_rank0(res["params"], [n_vox] * world, dim=1, concat=False, out=gathered[0])
+            res["params"].record_stream(side)
+
+    def run_steps(n):
+        pending = None
+        last = None
+        for _ in range(n):
+            if pending is not None:
+                enqueue_gather(*pending)
+            last = fit_on_device()
+            if world > 1:
+                pending = (last, cur.record_event())
+        if pending is not None:
+            enqueue_gather(*pending)
+            cur.wait_stream(side)
+        return last
+
+    r = run_steps(max(1, args.warmup))
+    D.barrier()
     sampler = ClockSampler(0, world)
     if rank == 0:
         sampler.start()
     launches0 = _lib.launch_count()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
-    ev[0].record()
-    for i in range(args.steps):
-        r = device_step()
-        if peer is not None and i == args.steps - 1:
-            peer.flush()  # the last event must cover the transfers still in flight on the side stream
-        ev[i + 1].record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    total_ms = ev[0].elapsed_time(ev[-1])
+    ev0.record()
+    r = run_steps(args.steps)
+    ev1.record()
+    D.barrier()
     kernel_launches = _lib.launch_count() - launches0
-    if peer is not None:
+    total_ms = D.max(ev0.elapsed_time(ev1), dev)
+    value = n_vox * world * args.steps / (total_ms * 1e-3)
+    if world > 1:
         # the blocks really are on rank 0: compare a checksum of every rank's parameters
+        import torch.distributed as dist
+
         mine = r["params"].sum().reshape(1)
         sums = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(sums, mine)
-        if rank == 0:
-            got = peer.out.sum(dim=(1, 2))
-            want = torch.cat(sums)
-            if not torch.allclose(got, want, rtol=1e-12, atol=0):
-                raise SystemExit(f"peer-memory gather delivered wrong data: {got.tolist()} vs {want.tolist()}")
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    value = n_vox * world * args.steps / (total_ms * 1e-3)
+        if rank == 0 and not torch.allclose(gathered[0].sum(dim=(1, 2)), torch.cat(sums), rtol=1e-12, atol=0):
+            raise SystemExit("the gather delivered wrong data")
 
-    # per-launch kernel duration for the roofline (kernel only, no gather): CUDA events around
-    # five back-to-back launches on the launching stream
+    # per-launch kernel duration for the roofline (kernel only, no gather): CUDA events around five
+    # back-to-back launches on the launching stream
     kev0, kev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    r = engine.trf_fit(desc, b, y_dev, p0, lb, ub, 0, max_nfev=250, ftol=1e-8, jac_mode=jac_mode, device=local_rank)
+    r = fit_on_device()
     torch.cuda.synchronize()
     kev0.record()
     for _ in range(5):
-        r = engine.trf_fit(desc, b, y_dev, p0, lb, ub, 0, max_nfev=250, ftol=1e-8, jac_mode=jac_mode,
-                           device=local_rank)
+        r = fit_on_device()
     kev1.record()
     torch.cuda.synchronize()
     kernel_ms = kev0.elapsed_time(kev1) / 5
     nfev_sum = int(r["nfev"].sum().item())
     njev_sum = int(r["njev"].sum().item())
     success = float((r["status"] > 0).double().mean().item())
+    del r, y_dev, gathered
+    torch.cuda.empty_cache()
 
     # ------------------------------------------------------------ e2e through the solver API, host buffers
     y_pin = _lib.pinned_empty(y_host.shape)
     y_pin[...] = y_host
-    solver = CurveFitSolver(model=model, p0=base.p0, bounds=base.bounds, max_iter=250, tol=1e-8,
-                            jac=args.jac, device=local_rank, pinned_outputs=True)
+    skw = dict(model=model, p0=base.p0, bounds=base.bounds, max_iter=250, tol=1e-8, jac=args.jac, device=local_rank)
     e2e_steps = max(2, min(args.steps, 5))
-    for _ in range(2):
-        solver.fit(b, y_pin)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        solver.fit(b, y_pin)
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
-    e2e_value = n_vox * world * e2e_steps / e2e_s
+    lazy = CurveFitSolver(pinned_outputs=True, **skw)
+    lazy.fit(b, y_pin)
+    e2e_s = _time_host(lambda: lazy.fit(b, y_pin), e2e_steps, D, dev)
+    del lazy
+    eager = CurveFitSolver(pinned_outputs=True, want_cov="eager", **skw)
+    eager.fit(b, y_pin)
+    e2e_eager_s = _time_host(lambda: eager.fit(b, y_pin), e2e_steps, D, dev)
+    del eager
     clocks = sampler.stop() if rank == 0 else None
     h2d = y_host.nbytes + b.nbytes + 3 * 4 * 8
-    d2h = n_vox * (4 * 8 + 16 * 8 + 4 + 4 + 4 + 8 + 8)
+    d2h_lazy = n_vox * (4 * 8 + 4 + 4 + 4 + 8 + 8)
+    d2h_eager = d2h_lazy + n_vox * 16 * 8
+    extras = {}
+    if not args.no_extras:
+        if world == 1:
+            def pageable():
+                s = CurveFitSolver(pinned_outputs=False, **skw)
+                t = _time_host(lambda: s.fit(b, y_host), 3, D, dev)
+                return {"value": n_vox / t, "unit": UNIT,
+                        "api": "CurveFitSolver.fit(plain numpy arrays): what an unmodified Pyneapple script passes; "
+                               "input and results staged through page-locked blocks, covariances stay on the GPU"}
 
-    del y_pin, solver, y_dev
+            def fitter():
+                f = PixelWiseFitter(solver=CurveFitSolver(pinned_outputs=True, **skw))
+                image = y_pin.reshape(base.shape[0], base.shape[1], args.slices, n_b)
+                t = _time_host(lambda: f.fit(b, image), 3, D, dev)
+                return {"value": n_vox / t, "unit": UNIT,
+                        "api": "PixelWiseFitter.fit(page-locked 4-D image): voxel extraction, solver.fit, R^2, FitResult assembly"}
+
+            extras["e2e_pageable"] = _guard(pageable)
+            extras["e2e_fitter"] = _guard(fitter)
+        else:
+            # ONE process, ONE call, all N GPUs: rank 0 drives every GPU of the node through
+            # pnb_trf_fit_host_multi while the other ranks wait at the barrier
+            def one_process():
+                out = None
+                try:
+                    if rank == 0:
+                        bb, whole, _ = synth.make_volume(cfg)
+                        yy = _lib.pinned_empty((whole.shape[0] * whole.shape[1] * whole.shape[2], n_b))
+                        yy[...] = whole.reshape(yy.shape)
+                        del whole
+                        s = CurveFitSolver(pinned_outputs=True, **{**skw, "device": list(range(world))})
+                        s.fit(bb, yy)
+                        s.fit(bb, yy)
+                        t0 = time.perf_counter()
+                        for _ in range(3):
+                            s.fit(bb, yy)
+                        t = (time.perf_counter() - t0) / 3
+                        out = {"value": yy.shape[0] / t, "unit": UNIT, "n_gpus": world,
+                               "api": "CurveFitSolver(device=[0..N-1]).fit(page-locked numpy) -> pnb_trf_fit_host_multi: one "
+                                      "process, contiguous voxel ranges per GPU, results written straight into the caller's arrays"}
+                finally:
+                    D.barrier()  # the other ranks wait here while rank 0 drives their GPUs
+                return out
+
+            extras["e2e_one_process"] = _guard(one_process)
+    del y_pin
     torch.cuda.empty_cache()
-    nnls = None if args.no_nnls else bench_nnls(args, world, rank, local_rank, dev)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = CpuReference()
+    nnls = None if args.no_nnls else _guard(bench_nnls, args, D, dev, cpu)
+    c5 = None if args.no_c5 else _guard(bench_c5, args, D, dev, cpu)
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        D.finish()
         return 0
 
     # ------------------------------------------------------------ roofline + baselines (rank 0)
@@ -525,24 +752,30 @@ def main():
     alg_bytes = n_vox * (8 * n_b + 8 * 4 + 8 * 16 + 4 + 4 + 4 + 8 + 8)
     achieved_tf = flops / (kernel_ms * 1e-3) / 1e12
     achieved_gbs = alg_bytes / (kernel_ms * 1e-3) / 1e9
-    traffic = _traffic("trf_traffic.json")
+    ctr = _counters("r2_trf_counters.json")
     roofline = {
-        "bound": "fp64", "kernel": "trf_kernel<Model<BiS0>,128>", "achieved": achieved_tf, "peak": fp64_peak,
+        "bound": "fp64", "kernel": "trf_kernel<Model<BiS0>,128> + cov_kernel<4>", "achieved": achieved_tf, "peak": fp64_peak,
         "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak,
+        "frac_pipe": ctr.get("fp64_pipe_frac"),
         "peak_source": "DFMA micro-benchmark run by this process (MEASURED_PEAKS.json holds no FP64 figure)",
-        "flops_per_launch": flops, "flop_model": "SURVEY.md §8(d): nfev*F_f + njev*(F_J+F_it), C_exp=25",
-        "kernel_ms": kernel_ms, "traffic": traffic,
+        "flops_per_launch": flops,
+        "flop_model": "SURVEY.md §8(d): nfev*F_f + njev*(F_J+F_it), C_exp=25.  F_it prices SciPy's Jacobi SVD of the "
+                      "augmented Jacobian (4752 of ~5800 flop per iteration at n=4, m=16); the kernel computes the same "
+                      "step from LDL^T factorisations of the 4x4 normal matrix instead, so `frac` is work-equivalent "
+                      "throughput, not executed instructions — `frac_pipe` (sm__inst_executed_pipe_fp64, ncu) is the "
+                      "hardware utilisation of the FP64 pipe",
+        "kernel_ms": kernel_ms, "traffic": ctr.get("dram_bytes_per_launch"), "counters_source": ctr.get("source"),
         "hbm": {"achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": hbm_src},
     }
     extra = {}
-    cpu = None
-    if not args.no_cpu_baseline:
-        _, cpu, (sb, sy, sres) = cpu_baseline(base)
+    cpu_line = None
+    if cpu is not None:
+        sb, sy, _ = synth.sample_voxels(base, 65536, z=0)
+        cpu_line, n_s, sres = cpu.baseline("trf", base, sb, sy, 15.0)
         # parity of the GPU path against that same CPU sample, voxel for voxel
-        solver2 = CurveFitSolver(model=model, p0=base.p0, bounds=base.bounds, max_iter=250, tol=1e-8,
-                                 jac=args.jac, device=local_rank)
-        solver2.fit(sb, sy)
+        solver2 = CurveFitSolver(**skw)
+        solver2.fit(sb, sy[:n_s])
         got = np.stack([solver2.params_[n] for n in names], axis=0)
         ok = sres["success"]
         rel = (np.abs(got - sres["params"]) / np.abs(sres["params"]))[:, ok].max(axis=0)
@@ -557,22 +790,35 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "voxels_per_gpu": n_vox, "jacobian": args.jac,
                    "l2": "inputs (537 MB per GPU) exceed the 126 MB L2, no flush needed",
-                   "multi_gpu": "z-slabs of a stack of C2 volumes, one volume (same parameter fields, own noise) per rank, parameter maps gathered to "
-                                "rank 0 in the timed region ("
-                                + ("peer-memory copies over NVLink" if peer is not None else "NCCL gather") + ")",
+                   "multi_gpu": "z-slabs of ONE N-times deeper volume (rank r = slices 64 r .. 64 r + 63, its own part of "
+                                "the parameter fields); parameter maps gathered to rank 0 (NCCL) in the timed region on "
+                                "a high-priority side stream, overlapping the next step's kernel",
                    "success_rate": success, "mean_nfev": nfev_sum / n_vox},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "steps": e2e_steps, "api": "CurveFitSolver.fit(numpy pinned) -> pnb_trf_fit_host"},
+        "e2e": {"value": n_vox * world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h_lazy), "steps": e2e_steps,
+                "api": "CurveFitSolver.fit(page-locked numpy) -> pnb_trf_fit_host; parameters, status, nfev, njev, cost, R^2 "
+                       "come back to the host, the covariances are computed and stay on the GPU until read (want_cov=True)"},
+        "e2e_eager_cov": {"value": n_vox * world / e2e_eager_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                          "d2h_bytes_per_step": int(d2h_eager), "api": "the same call with want_cov='eager' (covariances shipped too)"},
         "gpu_launches": int(kernel_launches),
         "roofline": roofline,
-        "cpu_baseline": cpu,
+        "cpu_baseline": cpu_line,
     }
+    line.update(extras)
     line.update(extra)
+    if isinstance(nnls, dict) and "error" not in nnls:
+        line["nnls_value"] = nnls["value"]
+        line["nnls_ms_per_step"] = nnls["ms_per_step"]
+        line["nnls_e2e"] = nnls["e2e"]
+        line["nnls_roofline"] = nnls["roofline"]
+        line["nnls_cpu_baseline"] = nnls.get("cpu_baseline")
+        if "e2e_pageable" in nnls:
+            line["nnls_e2e_pageable"] = nnls["e2e_pageable"]
     line["nnls"] = nnls
+    line["c5"] = c5
     _emit(line)
-    if world > 1:
-        dist.destroy_process_group()
+    D.finish()
     return 0
 
 

@@ -204,3 +204,54 @@ def sample_voxels(cfg: Config | str, n_vox: int, z: int = 0):
         raise ValueError(f"slice holds {flat.shape[0]} voxels, asked for {n_vox}")
     idx = np.arange(n_vox) * (flat.shape[0] // n_vox)
     return b, np.ascontiguousarray(flat[idx]), idx
+
+
+def make_volume_device(cfg: Config | str, z0: int = 0, z1: int | None = None, device="cuda:0", replica: int = 0):
+    """The recipe of :func:`make_volume` evaluated on a GPU (torch, float64): the same smooth
+    parameter fields (identical polynomial coefficients), jitter and noise from torch's generator
+    seeded per slab — the same distribution, not the same random numbers.  For workloads too large
+    to synthesise on the host in reasonable time (config C5: 805 M samples); benchmarks only, the
+    parity tests use :func:`make_volume`.  Returns ``(bvalues, image (X, Y, z1-z0, n_b) tensor)``.
+    """
+    import torch
+
+    if isinstance(cfg, str):
+        cfg = CONFIGS[cfg]
+    X, Y, Z = cfg.shape
+    z1 = Z if z1 is None else z1
+    dev = torch.device(device)
+    f64 = dict(dtype=torch.float64, device=dev)
+    xs = torch.linspace(0.0, 1.0, X, **f64)[:, None, None]
+    ys = torch.linspace(0.0, 1.0, Y, **f64)[None, :, None]
+    zs = torch.linspace(0.0, 1.0, Z, **f64)[z0:z1][None, None, :]
+    field_rng = np.random.default_rng([cfg.seed, 0])
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(int(cfg.seed) * 1_000_003 + 7919 * z0 + 104_729 * replica + 1)
+    t = {}
+    for name, (lo, hi) in cfg.truth.items():
+        c = field_rng.uniform(-1.0, 1.0, size=10)
+        poly = (c[0] + c[1] * xs + c[2] * ys + c[3] * zs + c[4] * xs * ys + c[5] * ys * zs
+                + c[6] * xs * zs + c[7] * xs * xs + c[8] * ys * ys + c[9] * zs * zs)
+        u = 0.5 + 0.5 * poly / float(np.abs(c).sum())
+        jit = 1.0 + 0.05 * (2.0 * torch.rand(u.shape, generator=gen, **f64) - 1.0)
+        t[name] = torch.clamp((lo + (hi - lo) * u) * jit, lo, hi)
+    if cfg.name == "C5":
+        hit = torch.rand(t["f1"].shape, generator=gen, **f64) < 0.05
+        s = t["f1"] + t["f2"]
+        scale = torch.where(hit, 1.0 / s, torch.ones_like(s))
+        t["f1"] = t["f1"] * scale
+        t["f2"] = t["f2"] * scale
+    b = torch.as_tensor(cfg.bvalues, **f64)
+    e = lambda name: torch.exp(-b * t[name][..., None])  # noqa: E731
+    if cfg.model == "monoexp":
+        img = t["S0"][..., None] * e("D")
+    elif cfg.model in ("biexp", "nnls"):
+        f1 = t["f1"][..., None]
+        img = t["S0"][..., None] * (f1 * e("D1") + (1 - f1) * e("D2"))
+    elif cfg.model == "triexp":
+        f1, f2 = t["f1"][..., None], t["f2"][..., None]
+        img = f1 * e("D1") + f2 * e("D2") + (1 - f1 - f2) * e("D3")
+    else:
+        raise ValueError(cfg.model)
+    img = img + cfg.noise_sigma * torch.randn(img.shape, generator=gen, **f64)
+    return cfg.bvalues.copy(), img.contiguous()
