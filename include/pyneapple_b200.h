@@ -252,6 +252,52 @@ typedef struct pnb_segmeans_problem {
 int pnb_segment_means_device(const pnb_segmeans_problem *prob, void *cuda_stream);
 int pnb_segment_means_host(const pnb_segmeans_problem *prob, int device);
 
+/*
+ * Model signal for every fitted voxel: replaces the per-voxel model.forward loop of
+ * BaseFitter.predict (fitters/base.py:93-128).  With flat_index the rows are scattered into an
+ * (n_out, n_b) volume that is zero where nothing was fitted (BaseFitter._reconstruct_volume,
+ * fitters/base.py:310-330).  All pointers are DEVICE pointers.
+ */
+typedef struct pnb_predict_problem {
+  int32_t model_id;          /* PNB_MODEL_*                                       */
+  int32_t t1_mode;           /* PNB_T1_*                                          */
+  double repetition_time, mixing_time;
+  int32_t n_b;               /* len(xdata)                                        */
+  int32_t n_params;          /* rows of params (all model parameters, fixed ones included) */
+  int64_t n_vox;             /* fitted voxels                                     */
+  int64_t n_out;             /* rows of signal: n_vox, or the volume's voxel count with flat_index */
+  const double *xdata;       /* (n_b)                                             */
+  const double *params;      /* (n_params, n_vox)                                 */
+  const int64_t *flat_index; /* (n_vox) C-order position of each voxel in the volume, or NULL */
+  double *signal;            /* (n_out, n_b)                                      */
+} pnb_predict_problem;
+
+int pnb_predict_device(const pnb_predict_problem *prob, void *cuda_stream);
+int pnb_sizeof_predict_problem(void);
+
+/*
+ * Row gather / scatter between a masked voxel list and a volume (DEVICE pointers):
+ *   direction 0  dst[i, :] = src[index[i], :]   image[segmentation != 0] of
+ *                BaseFitter._extract_pixel_data (fitters/base.py:280-308)
+ *   direction 1  dst[index[i], :] = src[i, :]   vol[idx] = values of _reconstruct_volume
+ *                (fitters/base.py:310-330) and reconstruct_maps (io/nifti.py:279-312; out_dtype 1
+ *                writes float32 like that function); zero_fill clears dst first.
+ */
+typedef struct pnb_rows_problem {
+  int32_t direction;         /* 0 gather, 1 scatter                               */
+  int32_t out_dtype;         /* 0 float64, 1 float32 (source is always float64)   */
+  int32_t width;             /* elements per row                                  */
+  int32_t zero_fill;         /* scatter: memset dst (n_other rows) first          */
+  int64_t n_rows;            /* rows moved = len(index)                           */
+  int64_t n_other;           /* rows of the array on the indexed side             */
+  const double *src;
+  void *dst;
+  const int64_t *index;      /* (n_rows)                                          */
+} pnb_rows_problem;
+
+int pnb_move_rows_device(const pnb_rows_problem *prob, void *cuda_stream);
+int pnb_sizeof_rows_problem(void);
+
 /* housekeeping */
 int pnb_abi_version(void);
 /* sizeof(struct pnb_trf_problem) as compiled, for binding self-checks */

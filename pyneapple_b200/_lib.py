@@ -126,6 +126,41 @@ class SegmeansProblem(C.Structure):
     ]
 
 
+class PredictProblem(C.Structure):
+    """Mirror of ``struct pnb_predict_problem``."""
+
+    _fields_ = [
+        ("model_id", C.c_int32),
+        ("t1_mode", C.c_int32),
+        ("repetition_time", C.c_double),
+        ("mixing_time", C.c_double),
+        ("n_b", C.c_int32),
+        ("n_params", C.c_int32),
+        ("n_vox", C.c_int64),
+        ("n_out", C.c_int64),
+        ("xdata", C.c_void_p),
+        ("params", C.c_void_p),
+        ("flat_index", C.c_void_p),
+        ("signal", C.c_void_p),
+    ]
+
+
+class RowsProblem(C.Structure):
+    """Mirror of ``struct pnb_rows_problem``."""
+
+    _fields_ = [
+        ("direction", C.c_int32),
+        ("out_dtype", C.c_int32),
+        ("width", C.c_int32),
+        ("zero_fill", C.c_int32),
+        ("n_rows", C.c_int64),
+        ("n_other", C.c_int64),
+        ("src", C.c_void_p),
+        ("dst", C.c_void_p),
+        ("index", C.c_void_p),
+    ]
+
+
 class ResizeProblem(C.Structure):
     """Mirror of ``struct pnb_resize_problem``."""
 
@@ -195,6 +230,10 @@ def load():
     lib.pnb_segment_means_device.restype = C.c_int
     lib.pnb_segment_means_host.argtypes = [C.POINTER(SegmeansProblem), C.c_int]
     lib.pnb_segment_means_host.restype = C.c_int
+    lib.pnb_predict_device.argtypes = [C.POINTER(PredictProblem), C.c_void_p]
+    lib.pnb_predict_device.restype = C.c_int
+    lib.pnb_move_rows_device.argtypes = [C.POINTER(RowsProblem), C.c_void_p]
+    lib.pnb_move_rows_device.restype = C.c_int
     lib.pnb_nnls_last_redo_count.argtypes = [C.c_int]
     lib.pnb_nnls_last_redo_count.restype = C.c_int64
     lib.pnb_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_int64]

@@ -401,6 +401,69 @@ def segment_means(image, segmentation, *, device: int = 0):
     return labels, means, counts, inverse.reshape(-1)
 
 
+def predict_device(desc: ModelDesc, xdata, params, flat_index=None, n_out: int | None = None):
+    """Model signal of every voxel on the GPU (``pnb_predict_device``).
+
+    ``params``: CUDA tensor ``(n_all, n_vox)`` over ``desc.all_names``.  With ``flat_index`` (CUDA int64
+    tensor, the C-order position of each voxel in a volume of ``n_out`` voxels) the rows are scattered
+    into an ``(n_out, n_b)`` tensor that is zero elsewhere; otherwise the result is ``(n_vox, n_b)``.
+    """
+    import torch
+
+    _lib.require_device()
+    lib = _lib.load()
+    dev = params.device
+    par = params.to(torch.float64).contiguous()
+    b = torch.as_tensor(np.ascontiguousarray(xdata, np.float64)).to(dev)
+    n_vox = int(par.shape[1])
+    rows = n_vox if flat_index is None else int(n_out)
+    out = torch.empty((rows, b.shape[0]), dtype=torch.float64, device=dev)
+    prob = _lib.PredictProblem()
+    prob.model_id, prob.t1_mode = desc.model_id, desc.t1_mode
+    prob.repetition_time, prob.mixing_time = desc.repetition_time, desc.mixing_time
+    prob.n_b, prob.n_params, prob.n_vox, prob.n_out = int(b.shape[0]), int(par.shape[0]), n_vox, rows
+    idx = None
+    if flat_index is not None:
+        idx = flat_index.to(device=dev, dtype=torch.int64).contiguous()
+    prob.xdata, prob.params, prob.signal = b.data_ptr(), par.data_ptr(), out.data_ptr()
+    prob.flat_index = idx.data_ptr() if idx is not None else None
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev)
+        _lib.check(lib.pnb_predict_device(C.byref(prob), C.c_void_p(stream.cuda_stream)), "pnb_predict_device")
+        for t in (b, par) + ((idx,) if idx is not None else ()):
+            t.record_stream(stream)
+    return out
+
+
+def move_rows(src, index, n_other: int, scatter: bool, out_float32: bool = False, zero_fill: bool = True):
+    """Row gather (``dst[i] = src[index[i]]``) or scatter (``dst[index[i]] = src[i]``) on the GPU
+    (``pnb_move_rows_device``).  ``src``: CUDA float64 tensor ``(rows, ...)``; ``index``: CUDA int64
+    ``(n_rows,)``; ``n_other``: rows of the array on the indexed side.  Returns the new tensor."""
+    import torch
+
+    _lib.require_device()
+    lib = _lib.load()
+    dev = src.device
+    s = src.to(torch.float64).contiguous()
+    idx = index.to(device=dev, dtype=torch.int64).contiguous()
+    n_rows = int(idx.shape[0])
+    tail = tuple(s.shape[1:])
+    width = int(np.prod(tail)) if tail else 1
+    dt = torch.float32 if out_float32 else torch.float64
+    out = torch.empty(((int(n_other) if scatter else n_rows),) + tail, dtype=dt, device=dev)
+    prob = _lib.RowsProblem()
+    prob.direction, prob.out_dtype, prob.width = int(scatter), int(out_float32), width
+    prob.zero_fill = int(zero_fill)
+    prob.n_rows, prob.n_other = n_rows, int(n_other)
+    prob.src, prob.dst, prob.index = s.data_ptr(), out.data_ptr(), idx.data_ptr()
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev)
+        _lib.check(lib.pnb_move_rows_device(C.byref(prob), C.c_void_p(stream.cuda_stream)), "pnb_move_rows_device")
+        s.record_stream(stream)
+        idx.record_stream(stream)
+    return out
+
+
 _TORCH_NP = None
 
 

@@ -28,24 +28,43 @@ class PixelIndices(Sequence):
     demand (4.19 M voxels: a 100 MB table nobody may ever look at).
     """
 
-    def __init__(self, coords: np.ndarray | None = None, full_shape: tuple | None = None):
+    def __init__(self, coords: np.ndarray | None = None, full_shape: tuple | None = None,
+                 flat: np.ndarray | None = None):
         self._array = None if coords is None else np.ascontiguousarray(coords, dtype=np.int64)
         self._shape = None if full_shape is None else tuple(int(v) for v in full_shape)
+        # masked volume given as C-order flat positions (what the device gather / scatter use):
+        # the coordinate table is only built when somebody asks for it
+        self._flat = None if flat is None else np.ascontiguousarray(flat, dtype=np.int64)
 
     @property
     def array(self) -> np.ndarray:
         if self._array is None:
-            n = int(np.prod(self._shape))
-            self._array = np.stack(np.unravel_index(np.arange(n), self._shape), axis=1).astype(np.int64)
+            flat = np.arange(int(np.prod(self._shape))) if self._flat is None else self._flat
+            self._array = np.stack(np.unravel_index(flat, self._shape), axis=1).astype(np.int64)
         return self._array
 
+    @property
+    def flat(self) -> np.ndarray | None:
+        """C-order flat position of every voxel in ``full_shape`` (``None`` when built from bare coordinates)."""
+        if self._flat is None and self._shape is not None and self._array is not None:
+            self._flat = np.ravel_multi_index(tuple(self._array.T), self._shape).astype(np.int64)
+        return self._flat
+
+    @property
+    def is_full(self) -> bool:
+        return self._array is None and self._flat is None
+
     def __len__(self):
-        return int(np.prod(self._shape)) if self._array is None else self._array.shape[0]
+        if self._array is not None:
+            return self._array.shape[0]
+        return int(np.prod(self._shape)) if self._flat is None else self._flat.shape[0]
 
     def __getitem__(self, i):
         if isinstance(i, slice):
             if self._array is None:
                 idx = np.arange(len(self))[i]
+                if self._flat is not None:
+                    idx = self._flat[idx]
                 return [tuple(int(v) for v in np.unravel_index(j, self._shape)) for j in idx]
             return [tuple(int(v) for v in row) for row in self._array[i]]
         if self._array is None:
@@ -54,7 +73,8 @@ class PixelIndices(Sequence):
                 i += n
             if not 0 <= i < n:
                 raise IndexError(i)
-            return tuple(int(v) for v in np.unravel_index(i, self._shape))
+            j = i if self._flat is None else int(self._flat[i])
+            return tuple(int(v) for v in np.unravel_index(j, self._shape))
         return tuple(int(v) for v in self._array[i])
 
     def __iter__(self):
@@ -94,9 +114,72 @@ class BaseFitter:
             raise ValueError(
                 f"xdata must be a 1D array of independent variable values, got shape {xdata.shape}."
             )
-        predictions = self._predict_flat(xdata)
         output_shape = self.image_shape[:-1] + (xdata.size,)
+        dev_pred = self._predict_device(xdata, output_shape)
+        if dev_pred is not None:
+            return dev_pred
+        predictions = self._predict_flat(xdata)
         return self._reconstruct_volume(predictions, self.pixel_indices, output_shape)
+
+    def _device_index(self):
+        """(torch device, flat-index tensor | None) of the fitted voxels, or None without a usable index."""
+        import torch
+
+        pi = self.pixel_indices
+        if not isinstance(pi, PixelIndices):
+            return None
+        dev = torch.device("cuda", getattr(self.solver, "primary_device", 0))
+        if pi.is_full:
+            return dev, None
+        if pi._shape is None:
+            pi._shape = tuple(self.image_shape[:-1])
+        flat = pi.flat
+        return dev, (None if flat is None else engine.to_device(flat, dev))
+
+    def _predict_device(self, xdata, output_shape):
+        """Prediction, scatter into the volume and nothing else on the GPU (``pnb_predict_device``; a
+        dictionary model is one FP64 GEMM); the finished ``(X, Y, Z, n)`` volume comes back."""
+        import torch
+
+        from .. import _lib
+
+        if _lib.load().pnb_device_count() < 1 or len(self.pixel_indices) < 4096:
+            return None
+        where = self._device_index()
+        if where is None:
+            return None
+        dev, flat = where
+        n_out = int(np.prod(output_shape[:-1]))
+        model = self.solver.model
+        with torch.cuda.device(dev):
+            if hasattr(model, "get_basis") and "coefficients" in self.fitted_params_:
+                coef = engine.to_device(np.ascontiguousarray(self.fitted_params_["coefficients"], np.float64), dev)
+                basis_t = torch.as_tensor(np.ascontiguousarray(model.get_basis(xdata).T)).to(dev)
+                pred = coef @ basis_t  # (n_vox, n_bins) x (n_bins, n): a plain library GEMM
+                if flat is not None:
+                    pred = engine.move_rows(pred, flat, n_out, scatter=True)
+            else:
+                desc = describe_model(model)
+                rows = []
+                n_pix = len(self.pixel_indices)
+                for n in desc.all_names:
+                    if n in self.fitted_params_:
+                        rows.append(np.atleast_1d(np.asarray(self.fitted_params_[n], dtype=np.float64)))
+                    else:
+                        rows.append(np.full(n_pix, float(desc.fixed[n])))
+                par = engine.to_device(np.ascontiguousarray(np.stack(rows)), dev)
+                pred = engine.predict_device(desc, xdata, par, flat, n_out)
+            return engine.to_host(pred).reshape(output_shape)
+
+    def reconstruct_maps(self) -> dict:
+        """Parameter volumes of the last fit, float32, zero where nothing was fitted — what the
+        reference's ``reconstruct_maps(fitter.fitted_params_, fitter.pixel_indices, image_shape[:3])``
+        (io/nifti.py:279-312) returns, without the per-voxel tuple list it builds."""
+        from ..maps import reconstruct_maps
+
+        self._check_fitted()
+        return reconstruct_maps(self.fitted_params_, self.pixel_indices, tuple(self.image_shape[:-1]),
+                                device=getattr(self.solver, "primary_device", 0))
 
     def _predict_flat(self, xdata):
         model = self.solver.model
@@ -124,15 +207,32 @@ class BaseFitter:
             )
         if segmentation is not None:
             mask = segmentation != 0
+            if self._gather_on_device(image):
+                # image[mask] in numpy is a single-threaded pass at ~1 GB/s: upload the volume once
+                # (staged, multi-threaded) and compact the masked rows on the GPU instead; the solver's
+                # device path then fits the tensor where it is
+                import torch
+
+                flat = np.flatnonzero(mask.reshape(-1))
+                self.pixel_indices = PixelIndices(full_shape=image.shape[:-1], flat=flat)
+                dev = torch.device("cuda", getattr(self.solver, "primary_device", 0))
+                img_d = engine.to_device(np.ascontiguousarray(image, dtype=np.float64).reshape(-1, self.n_measurements), dev)
+                return engine.move_rows(img_d, engine.to_device(flat, dev), img_d.shape[0], scatter=False)
             pixel_to_fit = image[mask]
-            self.pixel_indices = PixelIndices(np.argwhere(mask))
+            self.pixel_indices = PixelIndices(np.argwhere(mask), full_shape=image.shape[:-1])
         else:
             pixel_to_fit = image.reshape(-1, self.n_measurements)
             self.pixel_indices = PixelIndices(full_shape=image.shape[:-1])
         return pixel_to_fit
 
+    def _gather_on_device(self, image) -> bool:
+        from .. import _lib
+
+        return (isinstance(image, np.ndarray) and image.nbytes >= (32 << 20)
+                and _lib.load().pnb_device_count() > 0 and hasattr(self.solver, "primary_device"))
+
     def _reconstruct_volume(self, flat_values, pixel_indices, spatial_shape) -> np.ndarray:
-        if isinstance(pixel_indices, PixelIndices) and pixel_indices._array is None:
+        if isinstance(pixel_indices, PixelIndices) and pixel_indices.is_full:
             # unmasked volume: the flat order is the C order of the volume
             return np.asarray(flat_values, dtype=np.float64).reshape(spatial_shape).copy()
         vol = np.zeros(spatial_shape, dtype=np.float64)
@@ -144,6 +244,7 @@ class BaseFitter:
     def _compute_r_squared(self, xdata, pixel_signals) -> np.ndarray:
         """Host-side R^2 (fitters/base.py:142-186); the fit kernels normally provide it directly."""
         try:
+            pixel_signals = engine.to_host(pixel_signals)
             predictions = self._predict_flat(np.asarray(xdata))
             ss_res = np.sum((pixel_signals - predictions) ** 2, axis=1)
             mean = pixel_signals.mean(axis=1, keepdims=True)

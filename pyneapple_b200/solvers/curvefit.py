@@ -144,7 +144,14 @@ class CurveFitSolver(BaseSolver):
         res, free_names = self._solve(xdata, ydata, p0_m, lb_m, ub_m, pixel_fixed_params, n_pixels,
                                       max_nfev=1 if lm else None, method="dogbox" if lm else None)
         if on_device:
+            cov_dev = None
+            if (self.want_cov is True or self.want_cov == "lazy") and res.get("cov") is not None and not lm:
+                cov_dev = res.pop("cov")  # stays on the GPU until somebody reads it
             res = {k: (engine.to_host(v) if v is not None else None) for k, v in res.items()}
+            if cov_dev is not None:
+                from .._lazy import LazyArray
+
+                res["cov"] = LazyArray(tuple(cov_dev.shape), [(0, int(cov_dev.shape[0]), cov_dev)])
         if lm:
             # curve_fit rejects 'lm' for a bounded problem before it looks at the data, for every voxel
             # (scipy/optimize/_minpack_py.py: "Method 'lm' only works for unconstrained problems."): the

@@ -140,3 +140,79 @@ def test_segmentationwise_and_nnls_fitter():
     assert r.covariance is None and r.residuals is not None and r.params["coefficients"].shape[1] == 250
     host_r2 = fn._compute_r_squared(g["b"], g["image"][g["seg"] != 0])
     assert np.nanmax(np.abs(r.r_squared - host_r2)) < 1e-9
+
+
+# ---------------------------------------------------------------------------------------------
+# N1: mask gather, predict and map reconstruction on the device
+# ---------------------------------------------------------------------------------------------
+def _masked_volume():
+    from pyneapple_b200 import synth
+
+    cfg = synth.Config(**{**synth.CONFIGS["C2"].__dict__, "shape": (128, 128, 16)})
+    b, img, _ = synth.make_volume(cfg)
+    seg = synth.ellipsoid_mask(cfg.shape)
+    assert img.nbytes >= (32 << 20) and 0.3 < (seg != 0).mean() < 0.7
+    return cfg, b, img, seg
+
+
+def test_masked_fit_gathers_on_the_device_and_equals_the_host_gather(monkeypatch):
+    from pyneapple_b200 import models
+    from pyneapple_b200.fitters import PixelWiseFitter
+    from pyneapple_b200.fitters.base import BaseFitter
+    from pyneapple_b200.solvers import CurveFitSolver
+
+    cfg, b, img, seg = _masked_volume()
+    kw = dict(model=models.BiExpModel(fit_s0=True), p0=cfg.p0, bounds=cfg.bounds, max_iter=250, tol=1e-8)
+    dev = PixelWiseFitter(solver=CurveFitSolver(**kw))
+    assert dev._gather_on_device(img)
+    dev.fit(b, img, seg)
+    monkeypatch.setattr(BaseFitter, "_gather_on_device", lambda self, image: False)
+    host = PixelWiseFitter(solver=CurveFitSolver(**kw)).fit(b, img, seg)
+    assert dev.results_.n_pixels == host.results_.n_pixels == int((seg != 0).sum())
+    for n in ("f1", "D1", "D2", "S0"):
+        assert np.array_equal(dev.fitted_params_[n], host.fitted_params_[n]), n
+    assert np.array_equal(dev.results_.r_squared, host.results_.r_squared)
+    assert np.array_equal(np.asarray(dev.results_.covariance), np.asarray(host.results_.covariance))
+    assert np.array_equal(dev.pixel_indices.array, np.argwhere(seg != 0))
+    assert dev.pixel_indices[5] == tuple(np.argwhere(seg != 0)[5]) and dev.pixel_indices == host.pixel_indices
+
+
+def test_predict_and_reconstruct_maps_on_the_device_match_the_host_formulas():
+    from pyneapple_b200 import models
+    from pyneapple_b200.fitters import PixelWiseFitter
+    from pyneapple_b200.maps import reconstruct_maps
+    from pyneapple_b200.solvers import CurveFitSolver, NNLSSolver
+
+    cfg, b, img, seg = _masked_volume()
+    f = PixelWiseFitter(solver=CurveFitSolver(model=models.BiExpModel(fit_s0=True), p0=cfg.p0, bounds=cfg.bounds,
+                                              max_iter=250, tol=1e-8)).fit(b, img, seg)
+    xb = np.array([0.0, 10.0, 333.0, 1500.0, 40.0])
+    got = f.predict(xb)
+    assert got.shape == img.shape[:3] + (5,)
+    want = f._reconstruct_volume(f._predict_flat(xb), f.pixel_indices, img.shape[:3] + (5,))
+    assert np.array_equal(got == 0, want == 0) and (got[seg == 0] == 0).all()
+    np.testing.assert_allclose(got, want, rtol=4e-16 * 8, atol=0)  # pnb_exp is within 1 ulp of libm
+    # maps: float32, zero outside the mask, exactly the reference's astype + assignment
+    maps = f.reconstruct_maps()
+    idx = tuple(np.argwhere(seg != 0).T)
+    for n, v in f.fitted_params_.items():
+        vol = np.zeros(img.shape[:3], np.float32)
+        vol[idx] = np.asarray(v).astype(np.float32)
+        assert maps[n].dtype == np.float32 and np.array_equal(maps[n], vol), n
+    # values still on the GPU are scattered and converted there
+    import torch
+
+    on_dev = {n: torch.as_tensor(np.asarray(v)).cuda() for n, v in f.fitted_params_.items()}
+    maps_dev = reconstruct_maps(on_dev, f.pixel_indices, img.shape[:3])
+    for n in maps:
+        assert np.array_equal(maps_dev[n], maps[n]), n
+    # unmasked volume and a dictionary model (prediction = one FP64 GEMM)
+    sub = np.ascontiguousarray(img[:32, :32, :4])
+    g = PixelWiseFitter(solver=NNLSSolver(model=models.NNLSModel(d_range=(0.0008, 0.5), n_bins=250), reg_order=2,
+                                          mu=0.02, max_iter=250)).fit(b, sub)
+    pred = g.predict(b)
+    want = (g.fitted_params_["coefficients"] @ g.solver.model.get_basis(b).T).reshape(sub.shape)
+    np.testing.assert_allclose(pred, want, rtol=1e-12, atol=1e-9)
+    spec = g.reconstruct_maps()["coefficients"]
+    assert spec.shape == (32, 32, 4, 250) and spec.dtype == np.float32
+    assert np.array_equal(spec.reshape(-1, 250), g.fitted_params_["coefficients"].astype(np.float32))
