@@ -29,12 +29,26 @@ class PixelIndices(Sequence):
     """
 
     def __init__(self, coords: np.ndarray | None = None, full_shape: tuple | None = None,
-                 flat: np.ndarray | None = None):
+                 flat=None, n: int | None = None):
         self._array = None if coords is None else np.ascontiguousarray(coords, dtype=np.int64)
         self._shape = None if full_shape is None else tuple(int(v) for v in full_shape)
         # masked volume given as C-order flat positions (what the device gather / scatter use):
-        # the coordinate table is only built when somebody asks for it
-        self._flat = None if flat is None else np.ascontiguousarray(flat, dtype=np.int64)
+        # the coordinate table is only built when somebody asks for it.  `flat` may be a callable
+        # that fetches the positions (they may still be on the GPU); `n` is then their count.
+        self._flat_loader = flat if callable(flat) else None
+        self._n = n
+        self._flat_store = None if (flat is None or callable(flat)) else np.ascontiguousarray(flat, dtype=np.int64)
+
+    @property
+    def _flat(self):
+        if self._flat_store is None and self._flat_loader is not None:
+            self._flat_store = np.ascontiguousarray(self._flat_loader(), dtype=np.int64)
+            self._flat_loader = None
+        return self._flat_store
+
+    @_flat.setter
+    def _flat(self, value):
+        self._flat_store = value
 
     @property
     def array(self) -> np.ndarray:
@@ -52,12 +66,14 @@ class PixelIndices(Sequence):
 
     @property
     def is_full(self) -> bool:
-        return self._array is None and self._flat is None
+        return self._array is None and self._flat_store is None and self._flat_loader is None
 
     def __len__(self):
         if self._array is not None:
             return self._array.shape[0]
-        return int(np.prod(self._shape)) if self._flat is None else self._flat.shape[0]
+        if self._n is not None:
+            return int(self._n)
+        return int(np.prod(self._shape)) if self.is_full else self._flat.shape[0]
 
     def __getitem__(self, i):
         if isinstance(i, slice):
@@ -86,6 +102,29 @@ class PixelIndices(Sequence):
             return len(other) == len(self) and all(tuple(a) == tuple(b) for a, b in zip(self, other))
         except TypeError:
             return NotImplemented
+
+
+class LazyVolumes(Sequence):
+    """``list[np.ndarray]`` look-alike over CUDA tensors: an element is downloaded when it is first
+    indexed (IDEAL keeps every level's parameter map; most callers only look at the last one)."""
+
+    def __init__(self, tensors):
+        self._items = list(tensors)
+
+    def __len__(self):
+        return len(self._items)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self)))]
+        v = self._items[i]
+        if not isinstance(v, np.ndarray):
+            v = self._items[i] = engine.to_host(v)
+        return v
+
+    def device_tensor(self, i):
+        """Element ``i`` as it is stored (CUDA tensor until it has been read on the host)."""
+        return self._items[i]
 
 
 class BaseFitter:

@@ -20,7 +20,7 @@ import numpy as np
 from .. import _lib, engine
 from .. import validation as V
 from ..resize import METHODS, interpolate_array
-from .base import BaseFitter, PixelIndices
+from .base import BaseFitter, LazyVolumes, PixelIndices
 
 
 class IDEALFitter(BaseFitter):
@@ -165,9 +165,10 @@ class IDEALFitter(BaseFitter):
             img_l = interpolate_array(img_d, shape, self.interpolation_method)
             seg_l = interpolate_array(seg_d, shape, self.interpolation_method)
             mask = seg_l[..., 0] > thr
-            if not bool(mask.any()):
+            coords = mask.nonzero()  # (n_pix, 3), C order over (x, y, z) like np.where; the level's one host sync
+            if coords.shape[0] == 0:
                 mask = torch.ones(shape, dtype=torch.bool, device=dev)
-            coords = mask.nonzero()  # (n_pix, 3), C order over (x, y, z) like np.where
+                coords = mask.nonzero()
             y = img_l[mask].to(torch.float64)  # (n_pix, n_b)
             if step_index > 0:
                 p0 = p0_map[mask].T.contiguous()
@@ -182,8 +183,12 @@ class IDEALFitter(BaseFitter):
             step_maps.append(param_map)
             self.step_pixel_counts.append(int(coords.shape[0]))
         solver.store_device_result(res)
-        self.step_params = [engine.to_host(m) for m in step_maps]
-        self.pixel_indices = PixelIndices(engine.to_host(coords))
+        # every level's map stays on the GPU until it is looked at; the voxel positions likewise
+        self.step_params = LazyVolumes(step_maps)
+        sy, sz = int(shape[1]), int(shape[2])
+        flat_dev = (coords[:, 0] * sy + coords[:, 1]) * sz + coords[:, 2]
+        self.pixel_indices = PixelIndices(full_shape=shape, flat=lambda t=flat_dev: engine.to_host(t),
+                                          n=int(coords.shape[0]))
         self.fitted_params_ = {}
         for param, values in solver.params_.items():
             self.fitted_params_[param] = values

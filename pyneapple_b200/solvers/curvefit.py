@@ -315,8 +315,15 @@ class CurveFitSolver(BaseSolver):
         """Copy a :meth:`fit_device` result to the host and publish it like ``fit`` does."""
         self._reset_state()
         free_names, self._free_rows = res["free_names"], res["free_rows"]
+        cov_dev = None
+        if (self.want_cov is True or self.want_cov == "lazy") and res.get("cov") is not None:
+            cov_dev = res["cov"]  # stays on the GPU until somebody reads it
         host = {k: (engine.to_host(v) if hasattr(v, "cpu") else v) for k, v in res.items()
-                if k not in ("free_names", "free_rows")}
+                if k not in ("free_names", "free_rows", "n_active") and not (k == "cov" and cov_dev is not None)}
+        if cov_dev is not None:
+            from .._lazy import LazyArray
+
+            host["cov"] = LazyArray(tuple(cov_dev.shape), [(0, int(cov_dev.shape[0]), cov_dev)])
         self._store(host, free_names, host["params"].shape[1])
         return self
 
