@@ -47,7 +47,12 @@ enum {
 enum { PNB_T1_NONE = 0, PNB_T1_STANDARD = 1, PNB_T1_STEAM = 2 };
 /* SciPy least_squares method behind curve_fit (solvers/curvefit.py:295-306, `method` keyword):
  * scipy/optimize/_lsq/trf.py (trf_bounds) or scipy/optimize/_lsq/dogbox.py */
-enum { PNB_METHOD_TRF = 0, PNB_METHOD_DOGBOX = 1 };
+enum { PNB_METHOD_TRF = 0, PNB_METHOD_DOGBOX = 1,
+       /* curve_fit(method="lm") -> leastsq -> MINPACK lmdif / lmder (scipy/optimize/_minpack_py.py);
+        * unbounded problems only (the caller passes -inf / +inf bounds); per-voxel status: 1 gtol,
+        * 2 ftol, 3 xtol, 4 both (success); 0 maxfev reached, -6 / -7 / -8 = leastsq's info 6 / 7 / 8
+        * ("ftol / xtol / gtol is too small"): failures, params = p0 */
+       PNB_METHOD_LM = 2 };
 
 enum {
   PNB_E_BADARG = -1,      /* inconsistent sizes / null pointers */
@@ -63,7 +68,8 @@ enum {
   PNB_ST_BAD_BOUNDS = -1,  /* "Each lower bound must be strictly less than each upper bound." */
   PNB_ST_INFEASIBLE = -2,  /* "Initial guess is outside of provided bounds" */
   PNB_ST_NONFINITE_Y = -3, /* "array must not contain infs or NaNs" */
-  PNB_ST_NONFINITE_F0 = -4 /* "Residuals are not finite in the initial point." */
+  PNB_ST_NONFINITE_F0 = -4, /* "Residuals are not finite in the initial point." */
+  PNB_ST_LM_FTOL_SMALL = -6, PNB_ST_LM_XTOL_SMALL = -7, PNB_ST_LM_GTOL_SMALL = -8 /* PNB_METHOD_LM */
 };
 
 /*
@@ -94,7 +100,8 @@ typedef struct pnb_trf_problem {
   double ftol;               /* CurveFitSolver.tol                             */
   double xtol;               /* SciPy default 1e-8                             */
   double gtol;               /* SciPy default 1e-8                             */
-  int32_t jac_mode;          /* 0 analytic, 1 SciPy '2-point' finite differences */
+  int32_t jac_mode;          /* 0 analytic, 1 SciPy '2-point' finite differences (trf / dogbox),
+                                2 MINPACK forward differences, fdjac2 (lm)        */
   int32_t x_scale_jac;       /* 1: x_scale='jac'                               */
   int32_t method;            /* PNB_METHOD_TRF (curve_fit's default with bounds) or
                                 PNB_METHOD_DOGBOX: least_squares(method=...)      */

@@ -514,6 +514,39 @@ def case_t1():
     run("trf_triexp_full_steam_modelfixed", "triexp", mk, b24, y, p0f, bf)
 
 
+def case_lm():
+    """method = "lm" on problems without bounds: curve_fit -> leastsq -> MINPACK lmdif (forward
+    differences) or, with a fixed parameter, lmder (analytic Jacobian); maxfev = max_iter."""
+    inf = float("inf")
+
+    def free(bounds):
+        return {k: (-inf, inf) for k in bounds}
+
+    cfg, p0, bounds = _cfg_args("C1")
+    b, y, _ = synth.sample_voxels(cfg, 256, z=4)
+    _run_curvefit("lm_mono_c1", "monoexp", {}, b, y, p0, free(bounds), method="lm")
+    cfg, p0, bounds = _cfg_args("C2")
+    b, y, _ = synth.sample_voxels(cfg, 512, z=6)
+    _run_curvefit("lm_biexp_s0_c2", "biexp", {"fit_s0": True}, b, y, p0, free(bounds), method="lm")
+    for mi in (3, 8, 14, 30):  # maxfev counts the forward-difference evaluations too
+        _run_curvefit(f"lm_biexp_s0_maxiter{mi}", "biexp", {"fit_s0": True}, b, y[:64], p0, free(bounds),
+                      method="lm", max_iter=mi)
+    rng = np.random.default_rng(79)
+    d1 = rng.uniform(8e-4, 2e-3, size=128)
+    _run_curvefit("lm_biexp_s0_pixfixed_D1", "biexp", {"fit_s0": True}, b, y[:128], p0, free(bounds),
+                  pixel_fixed={"D1": d1}, method="lm")
+    yn = y[:128] / y[:128, :1]
+    p0r = {k: p0[k] for k in ("f1", "D1", "D2")}
+    _run_curvefit("lm_biexp_reduced", "biexp", {}, b, yn, p0r, free(p0r), method="lm")
+    cfg5, p05, b5 = _cfg_args("C5")
+    bb, yy, _ = synth.sample_voxels(cfg5, 128, z=3)
+    _run_curvefit("lm_triexp_reduced", "triexp", {}, bb, yy, p05, free(b5), method="lm")
+    # degenerate signals: zeros, constants, a NaN
+    good = synth.sample_voxels(cfg, 4, z=3)[1]
+    yd = np.stack([np.zeros(16), np.full(16, 300.0), np.r_[np.nan, good[0][1:]], good[1], 1e-3 * good[2]])
+    _run_curvefit("lm_biexp_s0_degenerate", "biexp", {"fit_s0": True}, b, yd, p0, free(bounds), method="lm")
+
+
 CASES = {k[5:]: v for k, v in globals().items() if k.startswith("case_")}
 
 if __name__ == "__main__":

@@ -142,7 +142,8 @@ void parallel_memcpy(void *dst, const void *src, size_t bytes) {
 
 #define PNB_DECL(id, t1)                                                                            \
   extern "C" cudaError_t pnb_trf_launch_##id##_##t1(const pnb::TrfDeviceArgs *, cudaStream_t);     \
-  extern "C" cudaError_t pnb_dogbox_launch_##id##_##t1(const pnb::TrfDeviceArgs *, cudaStream_t);
+  extern "C" cudaError_t pnb_dogbox_launch_##id##_##t1(const pnb::TrfDeviceArgs *, cudaStream_t);  \
+  extern "C" cudaError_t pnb_lm_launch_##id##_##t1(const pnb::TrfDeviceArgs *, cudaStream_t);
 PNB_DECL(0, 0) PNB_DECL(1, 0) PNB_DECL(2, 0) PNB_DECL(3, 0) PNB_DECL(4, 0) PNB_DECL(5, 0) PNB_DECL(6, 0)
 #ifdef PNB_WITH_T1
 PNB_DECL(0, 1) PNB_DECL(1, 1) PNB_DECL(2, 1) PNB_DECL(3, 1) PNB_DECL(4, 1) PNB_DECL(5, 1) PNB_DECL(6, 1)
@@ -154,16 +155,18 @@ namespace {
 #define PNB_ROW(name, t1) {name##_0_##t1, name##_1_##t1, name##_2_##t1, name##_3_##t1, name##_4_##t1, name##_5_##t1, name##_6_##t1}
 #define PNB_NOROW {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}
 LaunchFn trf_launcher(int model_id, int t1_mode, int method = 0) {
-  static const LaunchFn table[2][3][7] = {
+  static const LaunchFn table[3][3][7] = {
 #ifdef PNB_WITH_T1
       {PNB_ROW(pnb_trf_launch, 0), PNB_ROW(pnb_trf_launch, 1), PNB_ROW(pnb_trf_launch, 2)},
       {PNB_ROW(pnb_dogbox_launch, 0), PNB_ROW(pnb_dogbox_launch, 1), PNB_ROW(pnb_dogbox_launch, 2)},
+      {PNB_ROW(pnb_lm_launch, 0), PNB_ROW(pnb_lm_launch, 1), PNB_ROW(pnb_lm_launch, 2)},
 #else
       {PNB_ROW(pnb_trf_launch, 0), PNB_NOROW, PNB_NOROW},
       {PNB_ROW(pnb_dogbox_launch, 0), PNB_NOROW, PNB_NOROW},
+      {PNB_ROW(pnb_lm_launch, 0), PNB_NOROW, PNB_NOROW},
 #endif
   };
-  if (model_id < 0 || model_id > 6 || t1_mode < 0 || t1_mode > 2 || method < 0 || method > 1) return nullptr;
+  if (model_id < 0 || model_id > 6 || t1_mode < 0 || t1_mode > 2 || method < 0 || method > 2) return nullptr;
   return table[method][t1_mode][model_id];
 }
 
@@ -176,8 +179,8 @@ int check_problem(const pnb_trf_problem *p) {
   if (!p) return fail(PNB_E_BADARG, "null problem");
   if (p->model_id < 0 || p->model_id > 6 || p->t1_mode < 0 || p->t1_mode > 2)
     return fail(PNB_E_UNSUPPORTED, "unknown model_id / t1_mode");
-  if (p->method != PNB_METHOD_TRF && p->method != PNB_METHOD_DOGBOX)
-    return fail(PNB_E_UNSUPPORTED, "method must be PNB_METHOD_TRF or PNB_METHOD_DOGBOX");
+  if (p->method != PNB_METHOD_TRF && p->method != PNB_METHOD_DOGBOX && p->method != PNB_METHOD_LM)
+    return fail(PNB_E_UNSUPPORTED, "method must be PNB_METHOD_TRF, PNB_METHOD_DOGBOX or PNB_METHOD_LM");
   if (!trf_launcher(p->model_id, p->t1_mode, p->method))
     return fail(PNB_E_UNSUPPORTED, "this build has no kernel for the requested model / T1 mode");
   if (p->n_params != model_n_params(p->model_id, p->t1_mode))
@@ -185,7 +188,9 @@ int check_problem(const pnb_trf_problem *p) {
   if (p->n_b < 1 || p->n_b > 512) return fail(PNB_E_BADARG, "n_b must be in [1, 512]");
   if (p->n_vox < 0) return fail(PNB_E_BADARG, "n_vox < 0");
   if (p->max_nfev < 1) return fail(PNB_E_BADARG, "max_nfev must be positive");
-  if (p->jac_mode != 0 && p->jac_mode != 1) return fail(PNB_E_BADARG, "jac_mode must be 0 or 1");
+  if (p->jac_mode < 0 || p->jac_mode > 2) return fail(PNB_E_BADARG, "jac_mode must be 0, 1 or 2");
+  if ((p->jac_mode == 2) != (p->method == PNB_METHOD_LM) && p->jac_mode != 0)
+    return fail(PNB_E_BADARG, "jac_mode 2 (MINPACK forward differences) goes with PNB_METHOD_LM, jac_mode 1 with trf / dogbox");
   if (p->n_vox > 0 &&
       (!p->xdata || !p->ydata || !p->p0 || !p->lb || !p->ub || !p->params || !p->status || !p->nfev))
     return fail(PNB_E_BADARG, "null array pointer");

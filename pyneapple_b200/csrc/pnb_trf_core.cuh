@@ -40,9 +40,9 @@ namespace pnb {
 struct TrfOptions {
   double ftol, xtol, gtol;
   int max_nfev;
-  int jac_mode;      // 0 analytic Jacobian, 1 SciPy '2-point' finite differences
+  int jac_mode;      // 0 analytic Jacobian, 1 SciPy '2-point' finite differences, 2 MINPACK forward differences (fdjac2)
   int x_scale_jac;   // x_scale == 'jac'
-  int method;        // 0 'trf', 1 'dogbox' (pnb_dogbox_core.cuh)
+  int method;        // 0 'trf', 1 'dogbox' (pnb_dogbox_core.cuh), 2 'lm' (pnb_lm_core.cuh)
   unsigned frozen;   // bit j set: parameter j is fixed at its p0 value
   double x_scale[8];
   double tr, tm;     // repetition / mixing time of the T1 variants
@@ -484,11 +484,17 @@ PNB_HD void trf_evaluate(const double (&xe)[M::NP], const TrfOptions &O, int m, 
       const bool fitting = fabs(h) <= dmax(lower, upper);
       if (violated && fitting) h = -h;
       if (!fitting) h = (upper >= lower) ? upper : -lower;
+      if (O.jac_mode == 2) {
+        // minpack/fdjac2.f: h = eps * |x|, eps = sqrt(max(epsfcn, epsmch)); h = eps when x = 0
+        h = rstep * fabs(xk);
+        if (h == 0.0) h = rstep;
+      }
       double xt[N];
 #pragma unroll
       for (int j = 0; j < N; j++) xt[j] = xe[j];
       xt[k] = xk + h;
-      dx[k] = 1.0 / (xt[k] - xk);  // the quotient below multiplies (<= 1 ulp from SciPy's division)
+      // the quotient below multiplies (<= 1 ulp from SciPy's division); MINPACK divides by h itself
+      dx[k] = (O.jac_mode == 2) ? 1.0 / h : 1.0 / (xt[k] - xk);
       M::prepare(xt, O.tr, O.tm, pk[k]);
     }
     for (int r = 0; r < m; r++) {

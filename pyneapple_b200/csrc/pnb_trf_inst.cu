@@ -1,5 +1,5 @@
 // One translation unit per (model, T1 mode, method): compiled with
-//   -DPNB_MODEL_ID=<0..6> -DPNB_T1MODE=<0..2> [-DPNB_METHOD=1 for dogbox]
+//   -DPNB_MODEL_ID=<0..6> -DPNB_T1MODE=<0..2> [-DPNB_METHOD=1 for dogbox, 2 for lm]
 // so the seven-plus register-heavy kernels build in parallel.
 #include "pnb_trf_kernel.cuh"
 
@@ -13,7 +13,9 @@
 #ifndef PNB_METHOD
 #define PNB_METHOD 0
 #endif
-#if PNB_METHOD == 1
+#if PNB_METHOD == 2
+#define PNB_CAT_(a, b, c) pnb_lm_launch_##a##_##b
+#elif PNB_METHOD == 1
 #define PNB_CAT_(a, b, c) pnb_dogbox_launch_##a##_##b
 #else
 #define PNB_CAT_(a, b, c) pnb_trf_launch_##a##_##b

@@ -26,6 +26,7 @@
 #include <cuda_runtime.h>
 
 #include "pnb_dogbox_core.cuh"
+#include "pnb_lm_core.cuh"
 
 namespace pnb {
 
@@ -115,6 +116,7 @@ __global__ void __launch_bounds__(BLOCK, PNB_TRF_MINBLOCKS) trf_kernel(const Trf
 
   TrfLane<M> S;
   DogboxLane<M> DB;  // METHOD == 1 only
+  LmLane<M> LM;      // METHOD == 2 only
   long long cur = -1, nxt = -1;
   int buf = 0, nxt_buf = 0;  // which half of the double buffers holds `cur` / receives `nxt`
   bool first_eval = false;
@@ -197,11 +199,14 @@ __global__ void __launch_bounds__(BLOCK, PNB_TRF_MINBLOCKS) trf_kernel(const Trf
       // ---- prepare a trial step -------------------------------------------------
       bool go = true;
       if (S.need_prologue) {
-        go = (METHOD == 1) ? dbx_prologue<M>(S, DB, O) : trf_prologue<M>(S, O, my_lb, my_ub, BLOCK);
+        go = (METHOD == 2) ? lm_prologue<M>(S, LM, O)
+             : (METHOD == 1) ? dbx_prologue<M>(S, DB, O) : trf_prologue<M>(S, O, my_lb, my_ub, BLOCK);
         S.need_prologue = false;
       }
       if (go) {
-        if (METHOD == 1) {
+        if (METHOD == 2) {
+          lm_trial<M>(S, LM, O);
+        } else if (METHOD == 1) {
           dbx_trial<M>(S, DB, O, my_lb, my_ub, BLOCK);
         } else {
           double p_h[N];
@@ -220,12 +225,14 @@ __global__ void __launch_bounds__(BLOCK, PNB_TRF_MINBLOCKS) trf_kernel(const Trf
       trf_evaluate<M>(S.x_new, O, m, yb, my_lb, my_ub, BLOCK, c, g, A);
       if (first_eval) {
         first_eval = false;
-        const bool ok0 = (METHOD == 1) ? dbx_after_first_eval<M>(S, DB, O, c, g, A, my_lb, my_ub, BLOCK)
-                                       : trf_after_first_eval<M>(S, O, c, g, A, my_lb, my_ub, BLOCK);
+        const bool ok0 = (METHOD == 2) ? lm_after_first_eval<M>(S, LM, O, c, g, A)
+                         : (METHOD == 1) ? dbx_after_first_eval<M>(S, DB, O, c, g, A, my_lb, my_ub, BLOCK)
+                                         : trf_after_first_eval<M>(S, O, c, g, A, my_lb, my_ub, BLOCK);
         if (!ok0) finished = true;
       } else {
-        S.need_prologue = (METHOD == 1) ? dbx_after_trial<M>(S, DB, O, c, g, A, my_lb, my_ub, BLOCK)
-                                        : trf_after_trial<M>(S, O, c, g, A);
+        S.need_prologue = (METHOD == 2) ? lm_after_trial<M>(S, LM, O, c, g, A)
+                          : (METHOD == 1) ? dbx_after_trial<M>(S, DB, O, c, g, A, my_lb, my_ub, BLOCK)
+                                          : trf_after_trial<M>(S, O, c, g, A);
       }
     }
     __syncwarp();

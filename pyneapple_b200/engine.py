@@ -35,7 +35,33 @@ STATUS_MESSAGES = {
 
 JAC_ANALYTIC = 0
 JAC_TWO_POINT = 1
-METHODS = {"trf": 0, "dogbox": 1}  # PNB_METHOD_*: scipy.optimize.least_squares(method=...)
+JAC_MINPACK_FORWARD = 2  # fdjac2 of MINPACK's lmdif (method "lm" without an analytic Jacobian)
+# PNB_METHOD_*: scipy.optimize.least_squares(method=...) for "trf" / "dogbox", MINPACK through leastsq for "lm"
+METHODS = {"trf": 0, "dogbox": 1, "lm": 2}
+ST_LM_TOO_FEW_DATA = -9  # not a kernel status: method='lm' with more parameters than measurements
+# leastsq's xtol / gtol defaults (curve_fit(method="lm") does not override them)
+LM_XTOL, LM_GTOL = 1.49012e-8, 0.0
+
+
+def status_message(status: int, method: str = "trf", *, max_nfev: int = 0, ftol: float = 0.0, xtol: float = 0.0,
+                   gtol: float = 0.0, n_params: int = 0, n_data: int = 0):
+    """The text SciPy's exception carries for a failed voxel (``None`` for a success), as the
+    reference stores it in ``_PixelFitResult.message`` (solvers/curvefit.py:308-317)."""
+    status = int(status)
+    if status > 0:
+        return None
+    if method == "lm" and status in (0, -6, -7, -8, ST_LM_TOO_FEW_DATA):
+        # scipy/optimize/_minpack_py.py: leastsq's `errors` table, raised by curve_fit as RuntimeError
+        if status == ST_LM_TOO_FEW_DATA:
+            return f"The number of func parameters={n_params} must not exceed the number of data points={n_data}"
+        text = {
+            0: f"Number of calls to function has reached maxfev = {max_nfev}.",
+            -6: f"ftol={ftol:f} is too small, no further reduction in the sum of squares\n  is possible.",
+            -7: f"xtol={xtol:f} is too small, no further improvement in the approximate\n  solution is possible.",
+            -8: f"gtol={gtol:f} is too small, func(x) is orthogonal to the columns of\n  the Jacobian to machine precision.",
+        }[status]
+        return "Optimal parameters not found: " + text
+    return STATUS_MESSAGES[status]
 
 
 def _is_torch_cuda(x) -> bool:
@@ -108,7 +134,7 @@ def trf_fit(
     prob.jac_mode = int(jac_mode)
     prob.x_scale_jac = int(bool(x_scale_jac))
     if method not in METHODS:
-        raise NotImplementedError(f"method={method!r}: SciPy's 'trf' and 'dogbox' have a B200 implementation")
+        raise NotImplementedError(f"method={method!r}: SciPy's 'trf', 'dogbox' and 'lm' have a B200 implementation")
     prob.method = METHODS[method]
     xs = np.ones(8)
     if x_scale is not None:

@@ -145,6 +145,12 @@ class BaseFitter:
     def get_fitted_params(self):
         return self.fitted_params_
 
+    def _drop_previous_results(self):
+        """Release this fitter's references to the previous fit's arrays before fitting again: the
+        solvers reuse their page-locked result blocks only when nobody else still holds them."""
+        self.results_ = None
+        self.fitted_params_ = {}
+
     def predict(self, xdata: np.ndarray, **predict_kwargs) -> np.ndarray:
         """Model signal for every fitted voxel, ``(X, Y, Z, len(xdata))`` (fitters/base.py:93-128)."""
         self._check_fitted()

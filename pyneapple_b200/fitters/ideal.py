@@ -107,6 +107,7 @@ class IDEALFitter(BaseFitter):
         image = self._validate_image_dims(np.asarray(image))
         self.n_measurements = len(xdata)
         _t0 = time.perf_counter()
+        self._drop_previous_results()
         if not np.allclose(self.dim_steps[-1], image.shape[: self.ideal_dims]):
             raise ValueError("The last step in dim_steps must match the spatial dimensions of the image.")
         if segmentation is not None:

@@ -13,6 +13,7 @@ from .base import BaseFitter
 class PixelWiseFitter(BaseFitter):
     def fit(self, xdata, image, segmentation=None, fixed_param_maps=None, **fit_kwargs):
         _t0 = time.perf_counter()
+        self._drop_previous_results()
         xdata = np.asarray(xdata)
         V.validate_xdata(xdata)
         V.validate_data_shapes(xdata, image)

@@ -26,6 +26,7 @@ class SegmentationWiseFitter(BaseFitter):
         self.image_shape = image.shape
         segmentation = V.validate_segmentation(np.asarray(segmentation), image.shape)
         _t0 = time.perf_counter()
+        self._drop_previous_results()
         segs_to_fit = self._extract_segmentation_mean_signals(image, segmentation)
         pixel_fixed_params = None
         if fixed_param_maps is not None:

@@ -87,6 +87,7 @@ class SegmentedFitter(BaseFitter):
         self.n_measurements = len(xdata)
         self.image_shape = image.shape
         _t0 = time.perf_counter()
+        self._drop_previous_results()
         if segmentation is not None:
             segmentation = V.validate_segmentation(np.asarray(segmentation), image.shape)
         bmask = self._bvalue_mask(xdata)

@@ -127,7 +127,7 @@ class CurveFitSolver(BaseSolver):
         self._reset_state()
         if self.method not in engine.METHODS and self.method != "lm":
             raise NotImplementedError(
-                f"method={self.method!r}: SciPy's 'trf' and 'dogbox' have a B200 implementation"
+                f"method={self.method!r}: SciPy's 'trf', 'dogbox' and 'lm' have a B200 implementation"
             )
         xdata = np.asarray(xdata)
         on_device = engine._is_torch_cuda(ydata)
@@ -139,26 +139,32 @@ class CurveFitSolver(BaseSolver):
             ydata = ydata[None, :]
         p0_m, lb_m, ub_m = self._validate_p0_and_bounds(p0, bounds, n_pixels)
         lm = self.method == "lm"
-        if lm and not (np.isfinite(np.asarray(lb_m)).any() or np.isfinite(np.asarray(ub_m)).any()):
-            raise NotImplementedError("method='lm' on an unbounded problem (MINPACK) has no B200 implementation")
-        res, free_names = self._solve(xdata, ydata, p0_m, lb_m, ub_m, pixel_fixed_params, n_pixels,
-                                      max_nfev=1 if lm else None, method="dogbox" if lm else None)
+        bounded = bool(np.isfinite(np.asarray(lb_m)).any() or np.isfinite(np.asarray(ub_m)).any())
+        lm_rejected = lm and bounded
+        n_free_model = len(self.model.param_names) - len(set(pixel_fixed_params or {}) & set(self.model.param_names))
+        lm_too_few = lm and not bounded and n_free_model > xdata.shape[0]
+        if lm_rejected or lm_too_few:
+            # curve_fit raises before it looks at the data; one dogbox evaluation supplies R^2 at p0
+            res, free_names = self._solve(xdata, ydata, p0_m, lb_m, ub_m, pixel_fixed_params, n_pixels,
+                                          max_nfev=1, method="dogbox")
+        else:
+            res, free_names = self._solve(xdata, ydata, p0_m, lb_m, ub_m, pixel_fixed_params, n_pixels)
         if on_device:
             cov_dev = None
-            if (self.want_cov is True or self.want_cov == "lazy") and res.get("cov") is not None and not lm:
+            if (self.want_cov is True or self.want_cov == "lazy") and res.get("cov") is not None and not (lm_rejected or lm_too_few):
                 cov_dev = res.pop("cov")  # stays on the GPU until somebody reads it
             res = {k: (engine.to_host(v) if v is not None else None) for k, v in res.items()}
             if cov_dev is not None:
                 from .._lazy import LazyArray
 
                 res["cov"] = LazyArray(tuple(cov_dev.shape), [(0, int(cov_dev.shape[0]), cov_dev)])
-        if lm:
+        if lm_rejected or lm_too_few:
             # curve_fit rejects 'lm' for a bounded problem before it looks at the data, for every voxel
             # (scipy/optimize/_minpack_py.py: "Method 'lm' only works for unconstrained problems."): the
             # reference's solver turns that into success=False, params = p0, NaN covariance
             # (solvers/curvefit.py:308-317).  The single evaluation above (dogbox leaves x0 = p0 untouched)
             # only supplies R^2 at p0.
-            res["status"][...] = engine.ST_LM_BOUNDED
+            res["status"][...] = engine.ST_LM_BOUNDED if lm_rejected else engine.ST_LM_TOO_FEW_DATA
             if res.get("cov") is not None:
                 res["cov"] = np.full(tuple(res["cov"].shape), np.nan)
         self._store(res, free_names, n_pixels)
@@ -208,15 +214,14 @@ class CurveFitSolver(BaseSolver):
         LB = full(lb_m, per_voxel_bd, -np.inf, False)
         UB = full(ub_m, per_voxel_bd, np.inf, False)
 
-        if self.jac == "reference":
-            jac_mode = engine.JAC_ANALYTIC if fixed_names else engine.JAC_TWO_POINT
-        else:
-            jac_mode = engine.JAC_ANALYTIC if self.jac == "analytic" else engine.JAC_TWO_POINT
+        jac_mode, xtol, gtol = self._jac_and_tols(fixed_names, method or self._ls_method())
         xs_full, x_scale_jac = self._x_scale_args(all_names, model_names)
+        self._fit_opts = dict(method=method or self._ls_method(), xtol=xtol, gtol=gtol, n_data=int(np.asarray(xdata).shape[0]),
+                              n_params=len(all_names) - len(fixed_names))
         res = engine.trf_fit(
             desc, xdata, ydata, P0, LB, UB, frozen,
             max_nfev=self.max_iter if max_nfev is None else max_nfev, ftol=self.tol,
-            xtol=self.solver_kwargs.get("xtol", 1e-8), gtol=self.solver_kwargs.get("gtol", 1e-8),
+            xtol=xtol, gtol=gtol,
             jac_mode=jac_mode, x_scale=xs_full, x_scale_jac=x_scale_jac,
             want_cov=self.want_cov, device=self.device, chunk_vox=self.chunk_vox,
             out=self._pinned_out(len(all_names), len(all_names) - len(fixed_names), n_pixels, ydata),
@@ -224,6 +229,20 @@ class CurveFitSolver(BaseSolver):
         )
         self._free_rows = [all_names.index(n) for n in free_names]
         return res, free_names
+
+    def _jac_and_tols(self, fixed_names, method):
+        """Jacobian mode and xtol / gtol for the engine: the reference's rule (analytic Jacobian only
+        when a parameter is fixed, curvefit.py:274-293) and SciPy's defaults for the method
+        (least_squares: 1e-8 / 1e-8; leastsq behind method="lm": 1.49012e-8 / 0)."""
+        lm = method == "lm"
+        fd = engine.JAC_MINPACK_FORWARD if lm else engine.JAC_TWO_POINT
+        if self.jac == "reference":
+            jac_mode = engine.JAC_ANALYTIC if fixed_names else fd
+        else:
+            jac_mode = engine.JAC_ANALYTIC if self.jac == "analytic" else fd
+        xtol = self.solver_kwargs.get("xtol", engine.LM_XTOL if lm else 1e-8)
+        gtol = self.solver_kwargs.get("gtol", engine.LM_GTOL if lm else 1e-8)
+        return jac_mode, float(xtol), float(gtol)
 
     def _x_scale_args(self, all_names, model_names):
         """``x_scale`` of ``least_squares`` (forwarded by the reference, curvefit.py:305) as the
@@ -294,15 +313,14 @@ class CurveFitSolver(BaseSolver):
         P0 = assemble(p0, p0_def, 0.0, True)
         LB = assemble(None if bounds is None else bounds[0], lb_def, -np.inf, False)
         UB = assemble(None if bounds is None else bounds[1], ub_def, np.inf, False)
-        if self.jac == "reference":
-            jac_mode = engine.JAC_ANALYTIC if fixed_names else engine.JAC_TWO_POINT
-        else:
-            jac_mode = engine.JAC_ANALYTIC if self.jac == "analytic" else engine.JAC_TWO_POINT
+        jac_mode, xtol, gtol = self._jac_and_tols(fixed_names, self._ls_method())
         xs_full, x_scale_jac = self._x_scale_args(all_names, model_names)
+        self._fit_opts = dict(method=self._ls_method(), xtol=xtol, gtol=gtol, n_data=int(np.asarray(xdata).shape[0]),
+                              n_params=len(all_names) - len(fixed_names))
         res = engine.trf_fit(
             desc, np.asarray(xdata, float), y_dev, P0, LB, UB, frozen, max_nfev=self.max_iter,
-            ftol=self.tol, xtol=self.solver_kwargs.get("xtol", 1e-8),
-            gtol=self.solver_kwargs.get("gtol", 1e-8), jac_mode=jac_mode,
+            ftol=self.tol, xtol=xtol,
+            gtol=gtol, jac_mode=jac_mode,
             x_scale=xs_full, x_scale_jac=x_scale_jac,
             want_cov=self.want_cov if want_cov is None else want_cov, device=self.primary_device,
             method=self._ls_method(),
@@ -381,7 +399,9 @@ class CurveFitSolver(BaseSolver):
             pcov = np.broadcast_to(np.nan, (n_pixels, len(free_names), len(free_names)))
         self.pixel_results_ = PixelResults(
             params=rows, covariance=pcov, status=status,
-            messages=lambda i, s=status: engine.STATUS_MESSAGES[int(s[i])] if s[i] <= 0 else None,
+            messages=lambda i, s=status, o=dict(getattr(self, "_fit_opts", {})): engine.status_message(
+                s[i], "lm" if self.method == "lm" else o.get("method", "trf"), max_nfev=self.max_iter, ftol=self.tol,
+                xtol=o.get("xtol", 0.0), gtol=o.get("gtol", 0.0), n_params=o.get("n_params", 0), n_data=o.get("n_data", 0)),
         )
         self.params_ = {
             name: [float(rows[i][0])] if n_pixels == 1 else rows[i]

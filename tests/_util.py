@@ -63,6 +63,19 @@ DBX_T1_CASES = {
     "dbx_biexp_s0_steam_pixfixed": ("biexp", "s0"),
     "dbx_triexp_reduced_steam_pixfixed": ("triexp", "reduced"),
 }
+# method = "lm" goldens (oracle/make_golden.py: case_lm): unbounded problems through MINPACK
+LM_CASES = {
+    "lm_mono_c1": ("monoexp", "s0"),
+    "lm_biexp_s0_c2": ("biexp", "s0"),
+    "lm_biexp_s0_maxiter3": ("biexp", "s0"),
+    "lm_biexp_s0_maxiter8": ("biexp", "s0"),
+    "lm_biexp_s0_maxiter14": ("biexp", "s0"),
+    "lm_biexp_s0_maxiter30": ("biexp", "s0"),
+    "lm_biexp_s0_pixfixed_D1": ("biexp", "s0"),
+    "lm_biexp_reduced": ("biexp", "reduced"),
+    "lm_triexp_reduced": ("triexp", "reduced"),
+    "lm_biexp_s0_degenerate": ("biexp", "s0"),
+}
 # T1 fitted next to a free amplitude: S0 and T1 enter only through S0 * C(T1), so the minimiser is a
 # curve; parity is checked on the identifiable quantities (D, S0 * C(T1)) and the residual
 T1_AMPLITUDE_ONLY = {"trf_mono_t1", "trf_mono_steam"}

@@ -16,7 +16,7 @@ _LIB = None
 def build(force=False):
     srcs = [os.path.join(_HERE, "trf_hostsim.cpp")] + [
         os.path.join(_HERE, "..", "..", "pyneapple_b200", "csrc", f)
-        for f in ("pnb_trf_core.cuh", "pnb_dogbox_core.cuh", "pnb_models.cuh", "pnb_hd.cuh")
+        for f in ("pnb_trf_core.cuh", "pnb_dogbox_core.cuh", "pnb_lm_core.cuh", "pnb_models.cuh", "pnb_hd.cuh")
     ]
     newest = max(os.path.getmtime(s) for s in srcs)
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < newest:

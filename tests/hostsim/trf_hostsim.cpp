@@ -7,6 +7,7 @@
 #include <cmath>
 using std::exp; using std::sqrt; using std::fabs; using std::copysign; using std::nextafter;
 #include "../../pyneapple_b200/csrc/pnb_dogbox_core.cuh"
+#include "../../pyneapple_b200/csrc/pnb_lm_core.cuh"
 
 using namespace pnb;
 
@@ -47,6 +48,24 @@ static void run_one(const TrfOptions &O, int m, const double *b, const double *y
       dbx_trial<M>(S, DB, O, lb, ub, 1);
       trf_evaluate<M>(S.x_new, O, m, yb, lb, ub, 1, c, g, A);
       S.need_prologue = dbx_after_trial<M>(S, DB, O, c, g, A, lb, ub, 1);
+    }
+  }
+  LmLane<M> LM;
+  if (O.method == 2 && S.status == kStRunning) {
+    // the same calls, in the same order, as trf_kernel<M, BLOCK, 2>
+    running = trf_begin<M>(S, O, p0v, lb, ub, 1, yfin);
+    if (running) {
+      trf_evaluate<M>(S.x, O, m, yb, lb, ub, 1, c, g, A);
+      running = lm_after_first_eval<M>(S, LM, O, c, g, A);
+    }
+    while (running) {
+      if (S.need_prologue) {
+        if (!lm_prologue<M>(S, LM, O)) break;
+        S.need_prologue = false;
+      }
+      lm_trial<M>(S, LM, O);
+      trf_evaluate<M>(S.x_new, O, m, yb, lb, ub, 1, c, g, A);
+      S.need_prologue = lm_after_trial<M>(S, LM, O, c, g, A);
     }
   }
   while (running && O.method == 0) {

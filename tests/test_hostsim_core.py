@@ -9,7 +9,7 @@ from __future__ import annotations
 import numpy as np
 import pytest
 
-from _util import (DBX_CASES, DBX_T1_CASES, T1_AMPLITUDE_ONLY, TRF_CASES, TRF_T1_CASES, full_problem,
+from _util import (DBX_CASES, DBX_T1_CASES, LM_CASES, T1_AMPLITUDE_ONLY, TRF_CASES, TRF_T1_CASES, full_problem,
                    rel_err)
 from hostsim import hostsim
 from oracle import c_oracle
@@ -181,3 +181,51 @@ def test_t1_goldens_core_matches_reference(name):
         return
     err = rel_err(par[ok], P["ref_params"][ok]).max(axis=1)
     assert (err > 1e-4).sum() == 0, (int((err > 1e-4).sum()), float(err.max()))
+
+
+@pytest.mark.parametrize("name", sorted(LM_CASES))
+def test_lm_core_matches_reference(name):
+    """pnb_lm_core.cuh (MINPACK lmdif / lmder restated on the normal matrix) against the reference run
+    with method="lm" on unbounded problems: same success flags (maxfev counts the forward-difference
+    evaluations), parameters within north_star's 1e-4 (measured ~1e-8), failures return p0."""
+    kind, m = LM_CASES[name]
+    P = full_problem(name)
+    jm = 2 if P["uses_fd"] else 0
+    r = hostsim.trf_fit(c_oracle.MODEL_IDS[(kind, m)], P["b"], P["y"], P["P0"], P["LB"], P["UB"],
+                        frozen=P["frozen"], ftol=P["tol"], xtol=1.49012e-8, gtol=0.0, max_nfev=P["max_iter"],
+                        jac_mode=jm, method=2)
+    free = [i for i in range(len(P["all_names"])) if not P["frozen"][i]]
+    par = r["params"][:, free]
+    assert ((r["status"] > 0) == P["ref_success"]).all(), (r["status"], P["ref_success"])
+    fail = ~P["ref_success"]
+    assert np.array_equal(par[fail], P["ref_params"][fail])
+    ok = P["ref_success"].copy()
+    if name == "lm_biexp_s0_degenerate":
+        # all-zero and constant signals have no unique minimiser (S0 -> 0 frees everything else):
+        # both answers must reproduce the signal equally well
+        from oracle import ref_port
+
+        mdl = ref_port.Model(kind, m)
+        for v in (0, 1):
+            ours = np.linalg.norm(mdl.forward(P["b"], *r["params"][v]) - P["y"][v])
+            ref = np.linalg.norm(mdl.forward(P["b"], *P["ref_params"][v]) - P["y"][v])
+            assert ours <= ref * (1 + 1e-6) + 1e-6
+            ok[v] = False
+    if ok.any():
+        err = rel_err(par[ok], P["ref_params"][ok]).max(axis=1)
+        off = np.where(ok)[0][err > 1e-4]
+        # without bounds a few voxels have a flat direction (a fast component that has decayed before the
+        # first non-zero b-value leaves its D free): the parameter gate applies to identifiable voxels,
+        # the residual gate to all
+        assert off.size <= max(0, int(0.02 * ok.sum())), (off, err.max())
+        if off.size:
+            from oracle import ref_port
+
+            mdl = ref_port.Model(kind, m)
+            for v in off:
+                ours = np.linalg.norm(mdl.forward(P["b"], *r["params"][v]) - P["y"][v])
+                ref = np.linalg.norm(mdl.forward(P["b"], *P["ref_params"][v]) - P["y"][v])
+                assert abs(ours - ref) <= 1e-6 * ref
+        assert np.median(err) < 1e-6
+        cerr = rel_err(r["cov"][ok], P["ref_pcov"][ok]).reshape(int(ok.sum()), -1).max(axis=1)
+        assert np.nanmedian(cerr) < 1e-3
