@@ -124,6 +124,12 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
   // last W bins read their own row (12 % of all shared-memory wavefronts went into those rows)
   double wt[C::BWK];
   unsigned bmask = 0xffu;
+  // bins >= n do not exist (zero dictionary rows): they are never candidates, whatever the
+  // Toeplitz weights make of the neighbouring coefficients
+  unsigned nomask = 0;
+#pragma unroll
+  for (int q = 0; q < NQ; q++)
+    if (NQ * lane + q >= n) nomask |= 1u << q;
   if (LB > 0) {
     const int jmid = n / 2, rmid = (jmid & 7) * 32 + (jmid >> 3);
     bool same = true;
@@ -139,7 +145,9 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
 #pragma unroll
       for (int q = 0; q < NQ; q++) {
         const int j = NQ * lane + q;
-        if (j < W || j >= n - W) bmask |= 1u << q;
+        // only bins that exist: with n = 250 the six padding bins of lane 31 used to take the slow
+        // row-from-shared-memory path alone, the other 31 lanes idle (9 % of the kernel's samples)
+        if (j < n && (j < W || j >= n - W)) bmask |= 1u << q;
       }
     }
   }
@@ -253,7 +261,7 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
             xw[t] = xs_raw[q8 * C::XR + lane + 1 + dl];
           }
         }
-        const unsigned skip = inP | rej;
+        const unsigned skip = inP | rej | nomask;
 #pragma unroll
         for (int q = 0; q < NQ; q++) {
           const int row = q * 32 + lane;

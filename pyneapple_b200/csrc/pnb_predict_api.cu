@@ -32,6 +32,7 @@ __global__ void __launch_bounds__(TV) predict_kernel(const PredictArgs a) {
   extern __shared__ double tile[];
   const int nb = a.n_b, ld = nb | 1;
   double *bs = tile + (size_t)TV * ld;
+  pnb::exp_tab_init(threadIdx.x, TV);  // pnb_exp's table lives in shared memory
   for (int i = threadIdx.x; i < nb; i += TV) bs[i] = a.b[i];
   __syncthreads();
   for (long long base = (long long)blockIdx.x * TV; base < a.n_vox; base += (long long)gridDim.x * TV) {

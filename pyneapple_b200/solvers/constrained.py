@@ -73,6 +73,7 @@ class ConstrainedCurveFitSolver(CurveFitSolver):
             self._fraction_names = []
             self._fraction_indices = []
         self.n_active_ = 0
+        self.n_released_ = 0
 
     def fit(self, xdata, ydata, p0=None, bounds=None, pixel_fixed_params=None, **fit_kwargs):
         """Both phases run on the GPU (``fit_device``); a numpy ``ydata`` is uploaded once (sharded over
@@ -142,7 +143,8 @@ class ConstrainedCurveFitSolver(CurveFitSolver):
             res["cov"] = np.concatenate([p["cov"] for _, p in live], axis=0)
         else:
             res["cov"] = None
-        self.n_active_ = int(sum(p["n_active"] for _, p in live))
+        self.n_active_ = int(sum(p["n_active"] for _, p in live))      # box-bounded minimiser violated the constraint
+        self.n_released_ = int(sum(p["n_released"] for _, p in live))  # ... and left the face again in phase 3
         self._free_rows = res["free_rows"]
         self._store(res, res["free_names"], n_pixels)
         # the reference reports SLSQP's iteration count (result.nit); the closest quantity here is the
@@ -172,6 +174,7 @@ class ConstrainedCurveFitSolver(CurveFitSolver):
         finally:
             self.tol, self.max_iter, self.solver_kwargs, self.jac = saved
         res["n_active"] = 0
+        res["n_released"] = 0
         free_names = res["free_names"]
         fracs = [n for n in free_names if n.startswith("f")] if self.fraction_constraint else []
         if len(fracs) < 2:
@@ -245,4 +248,93 @@ class ConstrainedCurveFitSolver(CurveFitSolver):
             # J^T J is singular on the face (dS/dD3 = -b f3 e3 = 0): np.linalg.inv raises ->
             # NaN covariance (constrained_curvefit.py:300-305)
             res["cov"].index_fill_(0, idx, float("nan"))
+        res["n_released"] = self._release_from_face(xdata, y_dev, res, idx, face_desc, face_names, r2, lb_src, ub_src,
+                                                    bound_of, pixel_fixed_params, bounds, p0)
         return res
+
+    def _release_from_face(self, xdata, y_dev, res, idx, face_desc, face_names, r2, lb_src, ub_src, bound_of,
+                           pixel_fixed_params, bounds, p0):
+        """Phase 3: is the face point a constrained minimiser?  On the face the third component has no
+        weight, so ``D3`` is free — and the Kuhn-Tucker multiplier of ``f1 + f2 <= 1`` depends on it:
+        ``dF/df1 = r . A C (e1 - e3(D3))``.  The point is optimal only if no ``D3`` within its bounds
+        offers a descent direction into the interior.  Voxels where one does (the box-bounded phase had
+        ended in a different basin of this non-convex problem) are re-fitted with the full model from
+        the face point with the most promising ``D3``; the result is kept when it is feasible and better.
+        Returns the number of voxels released."""
+        import torch
+
+        desc = self._desc
+        all_names = list(desc.all_names)
+        if "D3" in desc.fixed or "D3" in (pixel_fixed_params or {}) or int(idx.numel()) == 0:
+            return 0
+        dev = y_dev.device
+        nv = int(idx.numel())
+        b = torch.as_tensor(np.asarray(xdata, float), device=dev)
+        y_face = y_dev.index_select(0, idx)
+        resid = engine.predict_device(face_desc, xdata, r2["params"]) - y_face      # (nv, n_b)
+        d1 = r2["params"][face_names.index("D1")]
+        re1 = (resid * torch.exp(-b[None, :] * d1[:, None])).sum(dim=1)             # r . e1
+        lo3, hi3 = bound_of(lb_src, "D3"), bound_of(ub_src, "D3")
+        K = 16
+        t = torch.linspace(0.0, 1.0, K, dtype=torch.float64, device=dev)
+
+        def as_col(v):
+            return v[:, None] if isinstance(v, torch.Tensor) else torch.full((1, 1), float(v), dtype=torch.float64, device=dev)
+
+        lo, hi = as_col(lo3), as_col(hi3)
+        grid = torch.where((lo > 0) & torch.isfinite(hi), lo * (hi / lo.clamp_min(1e-300)) ** t[None, :],
+                           lo + (hi - lo) * t[None, :])                                   # (nv | 1, K)
+        if grid.shape[0] == 1:
+            re3 = resid @ torch.exp(-b[:, None] * grid[0][None, :])                       # (nv, K): one small GEMM
+        else:
+            re3 = torch.stack([(resid * torch.exp(-b[None, :] * grid[:, k:k + 1])).sum(dim=1) for k in range(K)], dim=1)
+        gain, kbest = (re1[:, None] - re3).max(dim=1)          # > 0: moving into the interior lowers the cost
+        scale = resid.norm(dim=1) * float(np.sqrt(b.shape[0]))
+        pick = (gain > 1e-9 * scale) & (r2["status"] > 0)
+        sub = pick.nonzero().squeeze(1)
+        n_rel = int(sub.numel())
+        if n_rel == 0:
+            return 0
+        vox = idx.index_select(0, sub)
+        par = res["params"]
+        d3_start = (grid.expand(nv, K) if grid.shape[0] == 1 else grid).gather(1, kbest[:, None]).squeeze(1).index_select(0, sub)
+        P0 = torch.stack([par[j].index_select(0, vox) for j in range(len(all_names))])
+        P0[all_names.index("D3")] = d3_start
+
+        def rows_of(src, default):
+            if src is None:
+                return default
+            rows = []
+            for n_ in all_names:
+                if n_ in self.model.param_names:
+                    v = src[list(self.model.param_names).index(n_)]
+                    rows.append(v.index_select(0, vox) if isinstance(v, torch.Tensor) and v.ndim else
+                                torch.full((n_rel,), float(v), dtype=torch.float64, device=dev))
+                else:
+                    rows.append(torch.full((n_rel,), float(default), dtype=torch.float64, device=dev))
+            return torch.stack(rows)
+
+        model_names = list(self.model.param_names)
+        from .. import validation as V
+
+        lb_def, ub_def = V.bounds_vectors(self.bounds, model_names)
+        LB = rows_of(bounds[0] if bounds is not None else lb_def, -np.inf)
+        UB = rows_of(bounds[1] if bounds is not None else ub_def, np.inf)
+        fixed_names = set(desc.fixed) | (set(pixel_fixed_params or {}) & set(all_names))
+        frozen = engine.frozen_mask(desc, fixed_names)
+        r3 = engine.trf_fit(desc, np.asarray(xdata, float), y_dev.index_select(0, vox), P0, LB, UB, frozen,
+                            max_nfev=max(4 * self.max_iter, 1000), ftol=_TIGHT, xtol=_TIGHT, gtol=_TIGHT,
+                            jac_mode=engine.JAC_ANALYTIC, want_cov=res["cov"] is not None)
+        i1, i2 = all_names.index("f1"), all_names.index("f2")
+        better = ((r3["status"] > 0) & (r3["params"][i1] + r3["params"][i2] <= 1.0)
+                  & (r3["cost"] < res["cost"].index_select(0, vox)))
+        for j in range(len(all_names)):
+            row = par[j]
+            row.index_copy_(0, vox, torch.where(better, r3["params"][j], row.index_select(0, vox)))
+        res["nfev"].index_add_(0, vox, r3["nfev"])
+        res["cost"].index_copy_(0, vox, torch.where(better, r3["cost"], res["cost"].index_select(0, vox)))
+        res["r2"].index_copy_(0, vox, torch.where(better, r3["r2"], res["r2"].index_select(0, vox)))
+        if res["cov"] is not None:
+            keep = res["cov"].index_select(0, vox)
+            res["cov"].index_copy_(0, vox, torch.where(better[:, None, None], r3["cov"], keep))
+        return int(better.sum().item())

@@ -337,7 +337,7 @@ class CurveFitSolver(BaseSolver):
         if (self.want_cov is True or self.want_cov == "lazy") and res.get("cov") is not None:
             cov_dev = res["cov"]  # stays on the GPU until somebody reads it
         host = {k: (engine.to_host(v) if hasattr(v, "cpu") else v) for k, v in res.items()
-                if k not in ("free_names", "free_rows", "n_active") and not (k == "cov" and cov_dev is not None)}
+                if k not in ("free_names", "free_rows", "n_active", "n_released") and not (k == "cov" and cov_dev is not None)}
         if cov_dev is not None:
             from .._lazy import LazyArray
 
