@@ -404,6 +404,39 @@ def bench_nnls(args, D, dev, cpu):
     ms = D.max(e0.elapsed_time(e1), dev)
     value = n_vox * world * steps / (ms * 1e-3)
     redo = int(_lib.load().pnb_nnls_last_redo_count(local_rank))
+    # north_star (2) A/B: h = B^T y fused into the solver kernel (above) vs materialised for all voxels
+    # by one dense FP64 tensor-core GEMM (mma.sync m8n8k4) that the solver kernel then reads
+    dual_ab = None
+    if rank == 0 and world == 1:
+        def ab():
+            rr = engine.nnls_fit(basis, R, y_dev, 250, dual_init="gemm")
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            rr = None
+            rr = engine.nnls_fit(basis, R, y_dev, 250, dual_init="gemm")
+            a1.record()
+            torch.cuda.synchronize()
+            same = bool((rr["status"] == r["status"]).all().item())
+            dmax = float((rr["coefficients"] - r["coefficients"]).abs().max().item())
+            del rr
+            h = engine.nnls_dual_gemm(basis, y_dev)
+            torch.cuda.synchronize()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for _ in range(3):
+                h = engine.nnls_dual_gemm(basis, y_dev)
+            g1.record()
+            torch.cuda.synchronize()
+            gemm_ms = g0.elapsed_time(g1) / 3
+            del h
+            nbytes = n_vox * 8 * (n_b + 250)
+            return {"fused_ms": ms / steps, "gemm_then_solve_ms": a0.elapsed_time(a1), "gemm_kernel_ms": gemm_ms,
+                    "gemm_hbm_gbs": nbytes / (gemm_ms * 1e-3) / 1e9, "gemm_tflops": 2.0 * n_b * 250 * n_vox / (gemm_ms * 1e-3) / 1e12,
+                    "same_status": same, "max_abs_coefficient_diff": dmax,
+                    "note": "the GEMM writes 8 n_bins bytes per voxel that the fused form never materialises; it replaces one of the "
+                            "~40 dual passes per voxel"}
+        dual_ab = _guard(ab)
     iters = r["iterations"].cpu().numpy()
     k_final = (r["coefficients"] > 0).sum(dim=1).cpu().numpy()
     ok_rate = float((r["status"] == 1).double().mean().item())
@@ -434,7 +467,7 @@ def bench_nnls(args, D, dev, cpu):
         "clocks": nclocks,
         "voxels_per_gpu": n_vox, "success_rate": ok_rate, "mean_iterations": float(iters.mean()),
         "mean_active_set": float(k_final.mean()), "max_active_set": int(k_final.max()),
-        "handed_to_robust_kernel": redo,
+        "handed_to_robust_kernel": redo, "dual_init_ab": dual_ab,
         "e2e": {"value": n_vox * world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(y_host.nbytes),
                 "d2h_bytes_per_step": d2h, "api": "NNLSSolver.fit(page-locked numpy) -> pnb_nnls_fit_host"},
         "roofline": {"bound": "fp64", "kernel": "nnls_v3_kernel<16,2> (+ nnls_kernel<2> for the voxels it hands over)",

@@ -149,7 +149,11 @@ typedef struct pnb_nnls_problem {
   int32_t algorithm;         /* 0 auto: inverse-update fast path, voxels it cannot certify
                                 are re-solved by the robust path; 1 robust (Cholesky +
                                 refinement) only -- use for un-regularised problems */
-  int32_t reserved;
+  int32_t dual_init;         /* how h = B^T y (the first dual) is computed on the fast path:
+                                0 fused into the solver kernel's first dual pass (default),
+                                1 materialised for all voxels by one dense FP64 tensor-core GEMM
+                                  (mma.sync m8n8k4) that the solver kernel then reads — the two
+                                  forms BASELINE.json's north_star (2) asks to be measured        */
   int64_t n_vox;
   const double *basis;       /* (n_b, n_bins)                                   */
   const double *rtr_band;    /* (n_bins, 2W+1): [j][d+W] = (mu^2 R^T R)[j][j+d] */
@@ -172,6 +176,11 @@ int pnb_nnls_fit_host(const pnb_nnls_problem *prob, int device, int64_t chunk_vo
 int pnb_nnls_fit_host_multi(const pnb_nnls_problem *prob, const int32_t *devices, int32_t n_devices,
                             int64_t chunk_vox);
 int pnb_sizeof_nnls_problem(void);
+/* H0 (n_vox, n_bins) = signal (n_vox, n_b) x basis (n_b, n_bins) on the FP64 tensor cores: the
+ * batched A^T y of NNLSSolver._fit_single_pixel's first Lawson-Hanson step (solvers/nnls_solver.py:
+ * 195-197) as one GEMM; DEVICE pointers, n_b <= 32 */
+int pnb_nnls_dual_gemm_device(int32_t n_b, int32_t n_bins, int64_t n_vox, const double *basis,
+                              const double *signal, double *h0, void *cuda_stream);
 /* voxels of the most recent auto-mode launch on `device` that were re-solved by the robust path
  * (synchronises the device) */
 int64_t pnb_nnls_last_redo_count(int device);

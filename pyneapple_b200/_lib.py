@@ -72,7 +72,7 @@ class NnlsProblem(C.Structure):
         ("rtr_halfband", C.c_int32),
         ("max_iter", C.c_int32),
         ("algorithm", C.c_int32),
-        ("reserved", C.c_int32),
+        ("dual_init", C.c_int32),
         ("n_vox", C.c_int64),
         ("basis", C.c_void_p),
         ("rtr_band", C.c_void_p),
@@ -234,6 +234,9 @@ def load():
     lib.pnb_predict_device.restype = C.c_int
     lib.pnb_move_rows_device.argtypes = [C.POINTER(RowsProblem), C.c_void_p]
     lib.pnb_move_rows_device.restype = C.c_int
+    lib.pnb_nnls_dual_gemm_device.argtypes = [C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.c_void_p]
+    lib.pnb_nnls_dual_gemm_device.restype = C.c_int
     lib.pnb_nnls_last_redo_count.argtypes = [C.c_int]
     lib.pnb_nnls_last_redo_count.restype = C.c_int64
     lib.pnb_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_int64]

@@ -11,6 +11,7 @@
 #include "../../include/pyneapple_b200.h"
 #include "pnb_internal.h"
 #include "pnb_nnls_fast.cuh"
+#include "pnb_nnls_gemm.cuh"
 
 namespace {
 
@@ -35,6 +36,8 @@ struct NnlsCtx {
   size_t scratch_cap[kSlots] = {};
   int *redo_list[kSlots] = {};
   size_t redo_cap[kSlots] = {};
+  double *h0[kSlots] = {};  // dual_init = 1: H0 = Y B materialised by the tensor-core GEMM
+  size_t h0_cap[kSlots] = {};
   unsigned long long *last_redo = nullptr;  // device counter of the most recent auto-mode launch
   // host pipeline
   cudaStream_t streams[kSlots] = {};
@@ -77,6 +80,7 @@ int check(const pnb_nnls_problem *p) {
   if (p->rtr_halfband < 0 || p->rtr_halfband > 8) return pnbi::fail(PNB_E_BADARG, "rtr_halfband must be in [0, 8]");
   if (p->max_iter < 1) return pnbi::fail(PNB_E_BADARG, "max_iter must be positive");
   if (p->algorithm != 0 && p->algorithm != 1) return pnbi::fail(PNB_E_BADARG, "algorithm must be 0 or 1");
+  if (p->dual_init != 0 && p->dual_init != 1) return pnbi::fail(PNB_E_BADARG, "dual_init must be 0 (fused) or 1 (GEMM)");
   if (p->n_vox < 0) return pnbi::fail(PNB_E_BADARG, "n_vox < 0");
   if (p->n_vox > 0 && (!p->basis || !p->rtr_band || !p->signal || !p->coefficients || !p->residual ||
                        !p->status || !p->iterations))
@@ -125,6 +129,19 @@ FastKernel fast_kernel_for(int mt) {
   return nullptr;
 }
 
+int h0_gemm(int mt, const double *y, const double *B, double *h0, long long n_vox, int m, int n, cudaStream_t stream) {
+  cudaError_t e = cudaErrorInvalidValue;
+  switch (mt) {
+    case 8: e = pnb::nnls_h0_dmma_launch<8>(y, B, h0, n_vox, m, n, stream); break;
+    case 16: e = pnb::nnls_h0_dmma_launch<16>(y, B, h0, n_vox, m, n, stream); break;
+    case 24: e = pnb::nnls_h0_dmma_launch<24>(y, B, h0, n_vox, m, n, stream); break;
+    case 32: e = pnb::nnls_h0_dmma_launch<32>(y, B, h0, n_vox, m, n, stream); break;
+  }
+  if (e != cudaSuccess) return pnbi::cuda_fail(e, "nnls_h0_dmma_kernel launch");
+  pnbi::count_launch();
+  return 0;
+}
+
 int launch(NnlsCtx &C, const pnb_nnls_problem *p, const double *B, const double *rtr, const double *y,
            long long n_vox, double *coef, double *rn, int *st, int *it, double *r2, cudaStream_t stream,
            int slot) {
@@ -163,6 +180,12 @@ int launch(NnlsCtx &C, const pnb_nnls_problem *p, const double *B, const double 
   a.B = B; a.rtr = rtr; a.y = y; a.coef = coef; a.rnorm = rn; a.status = st; a.iters = it; a.r2 = r2;
   a.scratch = C.scratch[slot];
   a.cert_ztol = g_cert_ztol;
+  a.h0 = nullptr;
+  if (p->dual_init == 1 && v3) {
+    if (int rc = grow(&C.h0[slot], &C.h0_cap[slot], (size_t)n_vox * n)) return rc;
+    if (int rc = h0_gemm(mt, y, B, C.h0[slot], n_vox, m, n, stream)) return rc;
+    a.h0 = C.h0[slot];
+  }
   a.redo_count = ctr + 1; a.redo_list = C.redo_list[slot];
   C.last_redo = use_fast ? ctr + 1 : nullptr;
   if (use_fast) {
@@ -356,6 +379,15 @@ extern "C" int pnb_nnls_fit_host_multi(const pnb_nnls_problem *p, const int32_t 
 }
 
 extern "C" int pnb_sizeof_nnls_problem(void) { return (int)sizeof(pnb_nnls_problem); }
+
+extern "C" int pnb_nnls_dual_gemm_device(int32_t n_b, int32_t n_bins, int64_t n_vox, const double *basis,
+                                         const double *signal, double *h0, void *cuda_stream) {
+  if (n_b < 1 || n_b > 32) return pnbi::fail(PNB_E_UNSUPPORTED, "the tensor-core GEMM is built for n_b <= 32");
+  if (n_bins < 1 || n_bins > 1024 || n_vox < 0) return pnbi::fail(PNB_E_BADARG, "bad sizes");
+  if (n_vox == 0) return 0;
+  if (!basis || !signal || !h0) return pnbi::fail(PNB_E_BADARG, "null array pointer");
+  return h0_gemm(pick_mt(n_b), signal, basis, h0, n_vox, n_b, n_bins, (cudaStream_t)cuda_stream);
+}
 
 extern "C" int64_t pnb_nnls_last_redo_count(int device) {
   if (device < 0 || device > 15) return -1;

@@ -65,6 +65,9 @@ struct NnlsDeviceArgs {
   // polished point would enter with the coefficient dual / pivot^2; above cert_ztol the voxel is
   // handed to the robust path (see nnls_v3_kernel, PH_CHECK)
   double cert_ztol;
+  // fast path: h = B^T y of every voxel when it has been materialised by the tensor-core GEMM
+  // (pnb_nnls_gemm.cuh); nullptr: the kernel computes it in its first dual pass
+  const double *h0;
 };
 
 // column-major packed lower triangle with leading dimension ld: element (i, c), i >= c

@@ -249,7 +249,15 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
       // ---- duals of this lane's bins, best positive one ----------------------------------------
       double best = 0.0;
       int bq = -1;
-      if (do_dual) {
+      if (do_dual && phase == PH_INIT && a.h0 != nullptr) {
+        // x = 0: the dual is h = B^T y, already computed for all voxels by the GEMM
+        const double *hp = a.h0 + vox * (long long)n + NQ * lane;
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+          const double acc = (NQ * lane + q < n) ? hp[q] : 0.0;
+          if (acc > best) { best = acc; bq = q; }
+        }
+      } else if (do_dual) {
         double xw[C::XW > 0 ? C::XW : 1];
         if (LB > 0) {
           // x[8 lane - WK .. 8 lane + 7 + WK]: own bins from the lane's column, the halo from the neighbours'

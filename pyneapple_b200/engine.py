@@ -308,7 +308,7 @@ def rtr_band(reg_matrix: np.ndarray):
 
 
 def nnls_fit(basis, reg_matrix, signal, max_iter: int, *, device=0, chunk_vox: int = 0,
-             out: dict | None = None, algorithm: str = "auto"):
+             out: dict | None = None, algorithm: str = "auto", dual_init: str = "fused"):
     """Batched ``scipy.optimize.nnls([basis; reg_matrix], [signal; 0], maxiter=max_iter)``.
 
     ``signal``: numpy ``(n_vox, n_b)`` (host path) or CUDA tensor (device path).
@@ -328,6 +328,9 @@ def nnls_fit(basis, reg_matrix, signal, max_iter: int, *, device=0, chunk_vox: i
     # SciPy's choice): go straight to the robust kernel below a relative weight of 1e-8
     reg_weight = float(np.abs(band[:, W]).max()) / float((B * B).sum(axis=0).max())
     prob.algorithm = 1 if (algorithm == "robust" or reg_weight < 1e-8) else 0
+    if dual_init not in ("fused", "gemm"):
+        raise ValueError("dual_init must be 'fused' or 'gemm'")
+    prob.dual_init = int(dual_init == "gemm")
     if _is_torch_cuda(signal):
         import torch
 
@@ -378,6 +381,26 @@ def nnls_fit(basis, reg_matrix, signal, max_iter: int, *, device=0, chunk_vox: i
         _lib.check(lib.pnb_nnls_fit_host_multi(C.byref(prob), dev_arr, len(devices), int(chunk_vox)),
                    "pnb_nnls_fit_host_multi")
     return dict(coefficients=coef, residual=res, status=status, iterations=iters, r2=r2)
+
+
+def nnls_dual_gemm(basis, signal):
+    """``signal (n_vox, n_b) @ basis (n_b, n_bins)`` on the FP64 tensor cores (``pnb_nnls_dual_gemm_device``):
+    ``h = B^T y`` of every voxel, the first dual of Lawson-Hanson.  CUDA tensors in, CUDA tensor out."""
+    import torch
+
+    _lib.require_device()
+    dev = signal.device
+    y = signal.to(torch.float64).contiguous()
+    Bd = torch.as_tensor(_as_f64(basis)).to(dev) if not _is_torch_cuda(basis) else basis.to(torch.float64).contiguous()
+    out = torch.empty((y.shape[0], Bd.shape[1]), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev)
+        _lib.check(_lib.load().pnb_nnls_dual_gemm_device(int(Bd.shape[0]), int(Bd.shape[1]), int(y.shape[0]),
+                                                          Bd.data_ptr(), y.data_ptr(), out.data_ptr(),
+                                                          C.c_void_p(stream.cuda_stream)), "pnb_nnls_dual_gemm_device")
+        y.record_stream(stream)
+        Bd.record_stream(stream)
+    return out
 
 
 def segment_means(image, segmentation, *, device: int = 0):

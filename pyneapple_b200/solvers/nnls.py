@@ -47,6 +47,8 @@ class NNLSSolver(BaseSolver):
         self.pinned_outputs = solver_kwargs.pop("pinned_outputs", "auto")  # see CurveFitSolver
         self._last_out_key = None
         self.algorithm = solver_kwargs.pop("algorithm", "auto")
+        # "fused": h = B^T y inside the solver kernel; "gemm": materialised first by the tensor-core GEMM
+        self.dual_init = solver_kwargs.pop("dual_init", "fused")
         self._out_cache = None
         self._peaks_cache = None
         self.reg_order = reg_order
@@ -104,7 +106,7 @@ class NNLSSolver(BaseSolver):
                     r2=_lib.pinned_empty((self.n_pixels,)))
                 self._out_cache = (key, out)
         res = engine.nnls_fit(basis, reg, signal, self.max_iter, device=self.device,
-                              chunk_vox=self.chunk_vox, out=out, algorithm=self.algorithm)
+                              chunk_vox=self.chunk_vox, out=out, algorithm=self.algorithm, dual_init=self.dual_init)
         if on_device:
             res = {k: engine.to_host(v) for k, v in res.items()}
         status = res["status"]

@@ -204,3 +204,35 @@ def test_c3_full_volume_default_path_equals_robust_path_on_every_voxel():
     assert n_status == 0
     assert worst <= 1e-6, f"max |coef(auto) - coef(robust)| = {worst:.3e}"
     assert n_support == 0
+
+
+def test_dual_gemm_on_the_fp64_tensor_cores_equals_the_matrix_product():
+    """``pnb_nnls_dual_gemm_device`` (mma.sync m8n8k4.f64): H0 = Y B for odd sizes, ragged tiles and
+    every supported measurement count."""
+    import torch
+
+    from pyneapple_b200 import engine
+
+    rng = np.random.default_rng(5)
+    for n_vox, m, n in ((1, 16, 250), (7, 16, 250), (4099, 16, 250), (1000, 11, 37), (513, 24, 96), (64, 32, 255), (9, 3, 5)):
+        B = rng.normal(size=(m, n))
+        Y = rng.normal(size=(n_vox, m)) * 100.0
+        got = engine.nnls_dual_gemm(B, torch.as_tensor(Y).cuda()).cpu().numpy()
+        want = Y @ B
+        assert got.shape == want.shape
+        scale = np.abs(Y) @ np.abs(B)
+        assert (np.abs(got - want) <= 4e-16 * m * scale).all(), (n_vox, m, n)
+
+
+def test_materialised_dual_gives_the_same_fits_as_the_fused_form():
+    g = load("nnls_c3_reg2")
+    from pyneapple_b200 import models
+    from pyneapple_b200.solvers import NNLSSolver
+
+    model = models.NNLSModel(d_range=tuple(g["d_range"]), n_bins=int(g["n_bins"]))
+    kw = dict(model=model, reg_order=2, mu=0.02, max_iter=250)
+    fused = NNLSSolver(**kw).fit(g["b"], g["y"])
+    gemm = NNLSSolver(dual_init="gemm", **kw).fit(g["b"], g["y"])
+    assert np.array_equal(fused.status_, gemm.status_) and np.array_equal(fused.iterations_, gemm.iterations_)
+    assert np.abs(fused.params_["coefficients"] - gemm.params_["coefficients"]).max() <= 1e-9
+    assert np.abs(gemm.params_["coefficients"] - g["coefficients"]).max() <= 1e-6
