@@ -644,9 +644,18 @@ def main():
             gathered[0] = parallel.gather_to_rank0(res["params"], [n_vox] * world, dim=1, concat=False, out=gathered[0])
             res["params"].record_stream(side)
 
+    serial_gather = os.environ.get("PNB_BENCH_GATHER", "overlap") == "serial"
+
     def run_steps(n):
         pending = None
         last = None
+        if serial_gather:  # A/B: the gather on the launching stream, behind each step's kernel
+            for _ in range(n):
+                last = fit_on_device()
+                if world > 1:
+                    gathered[0] = parallel.gather_to_rank0(last["params"], [n_vox] * world, dim=1, concat=False,
+                                                           out=gathered[0])
+            return last
         for _ in range(n):
             if pending is not None:
                 enqueue_gather(*pending)
@@ -694,6 +703,14 @@ def main():
     kev1.record()
     torch.cuda.synchronize()
     kernel_ms = kev0.elapsed_time(kev1) / 5
+    kernel_ms_per_rank = [kernel_ms]
+    if world > 1:
+        import torch.distributed as dist
+
+        mine = torch.tensor([kernel_ms], dtype=torch.float64, device=dev)
+        allk = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allk, mine)
+        kernel_ms_per_rank = [float(k.item()) for k in allk]
     nfev_sum = int(r["nfev"].sum().item())
     njev_sum = int(r["njev"].sum().item())
     success = float((r["status"] > 0).double().mean().item())
@@ -825,7 +842,8 @@ def main():
                    "l2": "inputs (537 MB per GPU) exceed the 126 MB L2, no flush needed",
                    "multi_gpu": "z-slabs of ONE N-times deeper volume (rank r = slices 64 r .. 64 r + 63, its own part of "
                                 "the parameter fields); parameter maps gathered to rank 0 (NCCL) in the timed region on "
-                                "a high-priority side stream, overlapping the next step's kernel",
+                                + ("the launching stream behind each step's kernel" if serial_gather else
+                                   "a high-priority side stream, overlapping the next step's kernel"),
                    "success_rate": success, "mean_nfev": nfev_sum / n_vox},
         "clocks": clocks,
         "e2e": {"value": n_vox * world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
@@ -835,6 +853,7 @@ def main():
         "e2e_eager_cov": {"value": n_vox * world / e2e_eager_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                           "d2h_bytes_per_step": int(d2h_eager), "api": "the same call with want_cov='eager' (covariances shipped too)"},
         "gpu_launches": int(kernel_launches),
+        "kernel_ms_per_rank": kernel_ms_per_rank,
         "roofline": roofline,
         "cpu_baseline": cpu_line,
     }

@@ -65,8 +65,19 @@ __device__ __forceinline__ void exp_tab_init(int tid, int nthreads) {
 static const double kExpTabHost[64] = PNB_EXP_TABLE;
 #endif
 
+// The out-of-range arguments must stay OUT of the instruction stream of the fast path: written
+// inline (`if (...) return exp(x);`) the compiler if-converts the branch and every call executes
+// libdevice's whole exp() next to the table version, selecting one result at the end (ncu, round 2:
+// 30 % of the TRF kernel's executed instructions sat on that one source line).  A call the compiler
+// cannot inline cannot be predicated either.
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__ double pnb_exp_out_of_range(double x) { return exp(x); }
+#else
+inline double pnb_exp_out_of_range(double x) { return exp(x); }
+#endif
+
 PNB_HD double pnb_exp(double x) {
-  if (!(fabs(x) < 690.0)) return exp(x);
+  if (__builtin_expect(!(fabs(x) < 690.0), 0)) return pnb_exp_out_of_range(x);
   const double kShift = 6755399441055744.0;  // 1.5 * 2^52: the integer lands in the low mantissa bits
   const double t = fma(x, 92.33248261689366, kShift);
   const double nf = t - kShift;
@@ -94,4 +105,11 @@ PNB_HD double pnb_exp(double x) {
   return out;
 #endif
 }
+
+// pnb_exp as a real call, for cold paths that must not be inlined into (and if-converted with) a hot one
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__ double pnb_exp_cold(double x) { return pnb_exp(x); }
+#else
+inline double pnb_exp_cold(double x) { return pnb_exp(x); }
+#endif
 }  // namespace pnb

@@ -145,8 +145,10 @@ template <int ID, int T1MODE> struct Model {
       e[k] = e0[k];
       if (L::d(k) == j) {
         const double t = b * (pk.nd[k] - p0.nd[k]);
+        // the second alternative is a call (never taken for finite-difference steps), so the compiler
+        // cannot turn the choice into "compute both, select one"
         e[k] = (fabs(t) < 1e-4) ? e0[k] + e0[k] * (t * (1.0 + t * (0.5 + t * (1.0 / 6.0))))
-                                : pnb_exp(b * pk.nd[k]);
+                                : pnb_exp_cold(b * pk.nd[k]);
       }
     }
     return combine(pk, e);

@@ -77,7 +77,7 @@ def test_contract_vs_reference_slsqp():
     # the constraint is active on the planted sub-population, and those voxels sit on the face
     assert 0.01 * 4096 < s.n_active_ < 0.1 * 4096
     on_face = got[0] + got[2] > 1.0 - 1e-12
-    assert on_face.sum() == s.n_active_ - s.n_released_ and 0 <= s.n_released_ <= 0.1 * s.n_active_
+    assert on_face.sum() == s.n_active_ - s.n_released_ and 0 <= s.n_released_ <= 0.5 * s.n_active_
     assert np.isnan(np.asarray(s.diagnostics_["pcov"])[on_face]).all()
     assert np.isfinite(np.asarray(s.diagnostics_["pcov"])[~on_face]).all()
     # (iii) tightly converged: polishing our answer with SLSQP(ftol=1e-15) does not move it
