@@ -61,6 +61,8 @@ const bool g_disable_v3 = [] { const char *e = std::getenv("PNB_NNLS_NO_V3"); re
 // it sends the voxel to the robust path.  2e-7 keeps the worst case a factor 5 inside the 1e-6
 // absolute parity tolerance; PNB_NNLS_CERT_ZTOL overrides it (measurements).
 const double g_cert_ztol = [] { const char *e = std::getenv("PNB_NNLS_CERT_ZTOL"); return e ? std::atof(e) : 2e-7; }();
+// PNB_NNLS_SCREEN=0 switches the FP32 screening of the fast kernel's dual pass off (A/B measurements)
+const int g_screen = [] { const char *e = std::getenv("PNB_NNLS_SCREEN"); return (e && e[0] == '0') ? 0 : 1; }();
 std::mutex g_mu[16];  // per device: the host pipelines of different GPUs run concurrently
 
 // (re)allocate a device buffer of `need` elements; pointer and capacity stay consistent on failure
@@ -181,6 +183,7 @@ int launch(NnlsCtx &C, const pnb_nnls_problem *p, const double *B, const double 
   a.scratch = C.scratch[slot];
   a.cert_ztol = g_cert_ztol;
   a.h0 = nullptr;
+  a.screen = g_screen;
   if (p->dual_init == 1 && v3) {
     if (int rc = grow(&C.h0[slot], &C.h0_cap[slot], (size_t)n_vox * n)) return rc;
     if (int rc = h0_gemm(mt, y, B, C.h0[slot], n_vox, m, n, stream)) return rc;

@@ -68,6 +68,7 @@ struct NnlsDeviceArgs {
   // fast path: h = B^T y of every voxel when it has been materialised by the tensor-core GEMM
   // (pnb_nnls_gemm.cuh); nullptr: the kernel computes it in its first dual pass
   const double *h0;
+  int screen;  // fast path: FP32 screening of the dual pass (1 = on; exact either way, see nnls_v3_kernel)
 };
 
 // column-major packed lower triangle with leading dimension ld: element (i, c), i >= c

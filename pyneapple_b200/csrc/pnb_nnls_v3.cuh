@@ -64,9 +64,12 @@ template <int MT, int WK> struct NnlsV3Cfg {
   static constexpr int T1 = ((K1 * (K1 + 1) / 2 - KB * (KB + 1) / 2) + 1) & ~1;  // one tier-1 area
   static constexpr int T2 = ((KC * (KC + 1) / 2 - K1 * (K1 + 1) / 2) + 1) & ~1;  // one tier-2 area
   static constexpr int PER_WARP = NX + 3 * KC + MT + KC + TB;
+  static constexpr int LDF = MT + 4;           // row stride (floats) of the FP32 copy of the dictionary: 128-bit
+                                               // loads of consecutive lanes stay bank-conflict free
+  static constexpr int BF = (NR * LDF + 1) / 2;  // doubles taken by the FP32 copy (only with screening)
   static constexpr int SHARED = NR * LD + NR * LB + NR + 2;
-  __host__ __device__ static constexpr size_t smem_doubles(int warps, int e1, int e2) {
-    return (size_t)SHARED + (size_t)e1 * T1 + (size_t)e2 * T2 + (size_t)warps * PER_WARP;
+  __host__ __device__ static constexpr size_t smem_doubles(int warps, int e1, int e2, bool screen) {
+    return (size_t)SHARED + (screen ? BF : 0) + (size_t)e1 * T1 + (size_t)e2 * T2 + (size_t)warps * PER_WARP;
   }
 };
 
@@ -85,7 +88,8 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
   double *rtrs = Bt + NR * LD;             // [NR][LB], same row order, taps centred on WK
   double *gdiag = rtrs + NR * LB;          // [NR], natural bin order
   int *pool_mask = reinterpret_cast<int *>(gdiag + NR);
-  double *pool1 = gdiag + NR + 2;                      // n_e1 areas of T1 doubles (rows KB .. K1-1)
+  float *Bf = reinterpret_cast<float *>(gdiag + NR + 2);  // [NR][LDF] FP32 copy of Bt (screening pass)
+  double *pool1 = gdiag + NR + 2 + (a.screen ? C::BF : 0);  // n_e1 areas of T1 doubles (rows KB .. K1-1)
   double *pool2 = pool1 + (size_t)n_e1 * C::T1;        // n_e2 areas of T2 doubles (rows K1 .. KC-1)
   double *wbase = pool2 + (size_t)n_e2 * C::T2 + (size_t)wid * C::PER_WARP;
   double *xs_raw = wbase;                  // NX, x[j] at xs_raw[xpos(j)]
@@ -102,6 +106,11 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
     const int row = i / LD, b = i - row * LD;
     const int j = NQ * (row & 31) + (row >> 5);
     Bt[i] = (j < n && b < m) ? a.B[(size_t)b * n + j] : 0.0;
+  }
+  for (int i = threadIdx.x; a.screen && i < NR * C::LDF; i += nthreads) {
+    const int row = i / C::LDF, b = i - row * C::LDF;
+    const int j = NQ * (row & 31) + (row >> 5);
+    Bf[i] = (j < n && b < m) ? (float)a.B[(size_t)b * n + j] : 0.0f;
   }
   if (LB > 0) {
     for (int i = threadIdx.x; i < NR * LB; i += nthreads) {
@@ -180,6 +189,7 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
     int phase = PH_INIT, pass = 0;
     bool do_dual = true;
     double hmax = 0.0, rel = 1.0, zscale = 0.0;
+    bool screen_ok = a.screen != 0;  // FP32 screening of the dual pass still pays for this voxel
     int jc = -1;          // PH_CHECK: the candidate whose would-be coefficient is being computed
     double wjc = 0.0;     // ... and its dual
 
@@ -270,31 +280,88 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
           }
         }
         const unsigned skip = inP | rej | nomask;
-#pragma unroll
-        for (int q = 0; q < NQ; q++) {
+        // (mu^2 R^T R x)_j of the lane's bin q
+        auto band_q = [&](int q) -> double {
+          if (LB == 0) return 0.0;
           const int row = q * 32 + lane;
-          double acc = col_dot(row, rr);
-          if (LB > 0) {
-            double b0 = 0.0, b1 = 0.0;
-            if ((bmask >> q) & 1u) {
-              // first / last W bins (or a regulariser that is not Toeplitz): the row from shared memory
-              const double2 *rp = reinterpret_cast<const double2 *>(rtrs + row * LB);
+          double b0 = 0.0, b1 = 0.0;
+          if ((bmask >> q) & 1u) {
+            // first / last W bins (or a regulariser that is not Toeplitz): the row from shared memory
+            const double2 *rp = reinterpret_cast<const double2 *>(rtrs + row * LB);
 #pragma unroll
-              for (int t = 0; t < LB / 2; t++) {
-                const double2 v = rp[t];
-                b0 += v.x * xw[q + 2 * t];
-                if (2 * t + 1 < C::BWK) b1 += v.y * xw[q + 2 * t + 1];
-              }
-            } else {
+            for (int t = 0; t < LB / 2; t++) {
+              const double2 v = rp[t];
+              b0 += v.x * xw[q + 2 * t];
+              if (2 * t + 1 < C::BWK) b1 += v.y * xw[q + 2 * t + 1];
+            }
+          } else {
 #pragma unroll
-              for (int t = 0; t < C::BWK; t += 2) {
-                b0 += wt[t] * xw[q + t];
-                if (t + 1 < C::BWK) b1 += wt[t + 1] * xw[q + t + 1];
+            for (int t = 0; t < C::BWK; t += 2) {
+              b0 += wt[t] * xw[q + t];
+              if (t + 1 < C::BWK) b1 += wt[t + 1] * xw[q + t + 1];
+            }
+          }
+          return b0 + b1;
+        };
+        bool exact_pass = true;
+        if (screen_ok && phase != PH_VERIFY) {
+          // ---- FP32 screening.  Half of this kernel's shared-memory traffic was the FP64 dictionary in
+          // this pass, and all the pass has to deliver is the arg-max.  The dictionary products are taken
+          // in FP32 first (half the bytes, the idle FP32 pipe): |w32_j - w_j| <= E = 2e-6 ||r||_1 (18
+          // roundings of 2^-24 on sum_b |B_bj r_b|, B <= 1, doubled), so the exact arg-max is among the bins
+          // with w32_j >= max w32 - 2 E — 1.3 bins on average — and only those are evaluated in FP64,
+          // with the same instructions as the full pass: the result is bit-identical.  When the largest
+          // dual has come down to the FP32 noise (the last few additions) the voxel returns to the full
+          // FP64 pass for good.
+          float r32[MT];
+          double rn1 = 0.0;
+#pragma unroll
+          for (int b = 0; b < MT; b++) { r32[b] = (float)rr[b]; rn1 += fabs(rr[b]); }
+          const double E = 2e-6 * rn1;
+          float w32[NQ];
+          double lmax = 0.0;
+#pragma unroll
+          for (int q = 0; q < NQ; q++) {
+            const float4 *bp = reinterpret_cast<const float4 *>(Bf + (q * 32 + lane) * C::LDF);
+            float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+            for (int t = 0; t < MT / 4; t++) {
+              const float4 v = bp[t];
+              s0 = fmaf(v.x, r32[4 * t], s0);
+              s1 = fmaf(v.y, r32[4 * t + 1], s1);
+              s0 = fmaf(v.z, r32[4 * t + 2], s0);
+              s1 = fmaf(v.w, r32[4 * t + 3], s1);
+            }
+            const double w = (double)(s0 + s1) - band_q(q);
+            w32[q] = (float)w;
+            if (!((skip >> q) & 1u) && w > lmax) lmax = w;
+          }
+          const unsigned hi = (unsigned)__double2hiint(lmax);
+          const unsigned mhi = __reduce_max_sync(FULL, hi);
+          const unsigned lo = (hi == mhi) ? (unsigned)__double2loint(lmax) : 0u;
+          const unsigned mlo = __reduce_max_sync(FULL, lo);
+          const double wmax32 = __hiloint2double((int)mhi, (int)mlo);
+          if (wmax32 > 32.0 * E) {
+            exact_pass = false;
+            const float thr = (float)(wmax32 - 2.0 * E - 2e-7 * wmax32);  // w32 itself is rounded to float
+#pragma unroll
+            for (int q = 0; q < NQ; q++) {
+              if (!((skip >> q) & 1u) && w32[q] >= thr) {
+                const double acc = col_dot(q * 32 + lane, rr) - band_q(q);
+                if (acc > best) { best = acc; bq = q; }
               }
             }
-            acc -= b0 + b1;
+          } else {
+            screen_ok = false;
           }
-          if (!((skip >> q) & 1u) && acc > best) { best = acc; bq = q; }
+        }
+        if (exact_pass) {
+#pragma unroll
+          for (int q = 0; q < NQ; q++) {
+            double acc = col_dot(q * 32 + lane, rr);
+            if (LB > 0) acc -= band_q(q);
+            if (!((skip >> q) & 1u) && acc > best) { best = acc; bq = q; }
+          }
         }
       }
       int j = -1, jrow = 0;
@@ -718,11 +785,12 @@ cudaError_t nnls_v3_launch(const NnlsDeviceArgs &a, cudaStream_t stream) {
   using C = NnlsV3Cfg<MT, WK>;
   constexpr size_t budget = 227 * 1024;
   int warps = PNB_V3_MAXWARPS, e1 = 3, e2 = 1;
-  while (warps > 4 && C::smem_doubles(warps, e1, e2) * sizeof(double) > budget) warps--;
-  while (e1 > 1 && C::smem_doubles(warps, e1, e2) * sizeof(double) > budget) e1--;
-  if (C::smem_doubles(warps, e1, e2) * sizeof(double) > budget) e2 = 0;
-  if (C::smem_doubles(warps, e1, e2) * sizeof(double) > budget) e1 = 0;
-  const size_t smem = C::smem_doubles(warps, e1, e2) * sizeof(double);
+  const bool sc = a.screen != 0;
+  while (warps > 4 && C::smem_doubles(warps, e1, e2, sc) * sizeof(double) > budget) warps--;
+  while (e1 > 1 && C::smem_doubles(warps, e1, e2, sc) * sizeof(double) > budget) e1--;
+  if (C::smem_doubles(warps, e1, e2, sc) * sizeof(double) > budget) e2 = 0;
+  if (C::smem_doubles(warps, e1, e2, sc) * sizeof(double) > budget) e1 = 0;
+  const size_t smem = C::smem_doubles(warps, e1, e2, sc) * sizeof(double);
   if (smem > budget) return cudaErrorInvalidConfiguration;
   auto kern = nnls_v3_kernel<MT, WK>;
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
