@@ -104,6 +104,12 @@ class ClockSampler:
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            # nvidia-smi's start-up (NVML attaching to every GPU of the box) perturbs running kernels for
+            # tens of milliseconds: let it finish before anything is timed (measured: +2 ms per 13 ms step
+            # when the first poll fell into a 150 ms timed region)
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < 3.0:
+                time.sleep(0.02)
         except OSError:
             self.proc = None
 
@@ -166,8 +172,20 @@ class Dist:
     def init(self, dev):
         import torch.distributed as dist
 
+        self.cpu_group = None
         if self.world > 1:
             dist.init_process_group("nccl", device_id=dev)
+            # a CPU-side group: ranks that must wait WITHOUT occupying their GPU (an NCCL barrier is a
+            # spinning kernel) while rank 0 drives all GPUs from one process
+            self.cpu_group = dist.new_group(backend="gloo")
+
+    def cpu_barrier(self):
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier(group=self.cpu_group)
 
     def barrier(self):
         import torch
@@ -386,12 +404,12 @@ def bench_nnls(args, D, dev, cpu):
     R = regularization_matrix(250, 2, 0.02)
     y_dev = torch.as_tensor(y_host).to(dev)
     steps = max(1, min(args.steps, 3))
-    r = engine.nnls_fit(basis, R, y_dev, 250)  # warm-up
-    D.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     nsampler = ClockSampler(0, world)
     if rank == 0:
         nsampler.start()
+    r = engine.nnls_fit(basis, R, y_dev, 250)  # warm-up
+    D.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = _lib.launch_count()
     e0.record()
     for _ in range(steps):
@@ -667,11 +685,11 @@ def main():
             cur.wait_stream(side)
         return last
 
-    r = run_steps(max(1, args.warmup))
-    D.barrier()
     sampler = ClockSampler(0, world)
     if rank == 0:
         sampler.start()
+    r = run_steps(max(1, args.warmup))
+    D.barrier()
     launches0 = _lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
@@ -758,6 +776,7 @@ def main():
             # pnb_trf_fit_host_multi while the other ranks wait at the barrier
             def one_process():
                 out = None
+                D.cpu_barrier()
                 try:
                     if rank == 0:
                         bb, whole, _ = synth.make_volume(cfg)
@@ -775,7 +794,7 @@ def main():
                                "api": "CurveFitSolver(device=[0..N-1]).fit(page-locked numpy) -> pnb_trf_fit_host_multi: one "
                                       "process, contiguous voxel ranges per GPU, results written straight into the caller's arrays"}
                 finally:
-                    D.barrier()  # the other ranks wait here while rank 0 drives their GPUs
+                    D.cpu_barrier()  # the other ranks wait here (on the CPU) while rank 0 drives their GPUs
                 return out
 
             extras["e2e_one_process"] = _guard(one_process)

@@ -222,6 +222,20 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
       return acc;
     };
 
+    // h = B^T y materialised by the tensor-core GEMM (dual_init = 1): the lane's best candidate of the
+    // first trip comes from there.  Kept out of the trip loop: global loads inside it cost the
+    // whole kernel 50 % (measured, round 2) although they execute once per voxel.
+    const bool have_h0 = a.h0 != nullptr;
+    double best_h0 = 0.0;
+    int bq_h0 = -1;
+    if (have_h0 && mode == 1) {
+      const double *hp = a.h0 + vox * (long long)n + NQ * lane;
+#pragma unroll
+      for (int q = 0; q < NQ; q++) {
+        const double acc = (NQ * lane + q < n) ? hp[q] : 0.0;
+        if (acc > best_h0) { best_h0 = acc; bq_h0 = q; }
+      }
+    }
     if (mode == 1) for (;;) {
       // ---- rs = y - B_P z (k = 0: rs = y) ----------------------------------------------------
       {
@@ -259,14 +273,8 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
       // ---- duals of this lane's bins, best positive one ----------------------------------------
       double best = 0.0;
       int bq = -1;
-      if (do_dual && phase == PH_INIT && a.h0 != nullptr) {
-        // x = 0: the dual is h = B^T y, already computed for all voxels by the GEMM
-        const double *hp = a.h0 + vox * (long long)n + NQ * lane;
-#pragma unroll
-        for (int q = 0; q < NQ; q++) {
-          const double acc = (NQ * lane + q < n) ? hp[q] : 0.0;
-          if (acc > best) { best = acc; bq = q; }
-        }
+      if (phase == PH_INIT && have_h0) {
+        best = best_h0; bq = bq_h0;  // x = 0: the dual is h = B^T y, read before the loop
       } else if (do_dual) {
         double xw[C::XW > 0 ? C::XW : 1];
         if (LB > 0) {
