@@ -61,8 +61,9 @@ const bool g_disable_v3 = [] { const char *e = std::getenv("PNB_NNLS_NO_V3"); re
 // it sends the voxel to the robust path.  2e-7 keeps the worst case a factor 5 inside the 1e-6
 // absolute parity tolerance; PNB_NNLS_CERT_ZTOL overrides it (measurements).
 const double g_cert_ztol = [] { const char *e = std::getenv("PNB_NNLS_CERT_ZTOL"); return e ? std::atof(e) : 2e-7; }();
-// PNB_NNLS_SCREEN=0 switches the FP32 screening of the fast kernel's dual pass off (A/B measurements)
-const int g_screen = [] { const char *e = std::getenv("PNB_NNLS_SCREEN"); return (e && e[0] == '0') ? 0 : 1; }();
+// PNB_NNLS_SCREEN=1 switches the FP32 screening of the fast kernel's dual pass on; it only has an effect in
+// a library built with -DPNB_V3_SCREEN (an experiment that lost, see pnb_nnls_v3.cuh)
+const int g_screen = [] { const char *e = std::getenv("PNB_NNLS_SCREEN"); return (e && e[0] == '1') ? 1 : 0; }();
 std::mutex g_mu[16];  // per device: the host pipelines of different GPUs run concurrently
 
 // (re)allocate a device buffer of `need` elements; pointer and capacity stay consistent on failure

@@ -47,6 +47,26 @@ namespace pnb {
 #ifndef PNB_V3_MAXWARPS
 #define PNB_V3_MAXWARPS 12
 #endif
+// unroll factors of the dual pass over the lane's eight bins (code size against instruction-level
+// parallelism: see the note on the instruction cache in the kernel)
+#ifndef PNB_V3_UQ32
+#define PNB_V3_UQ32 2
+#endif
+#ifndef PNB_V3_UQX
+#define PNB_V3_UQX 8
+#endif
+// FP32 screening of the dual pass (-DPNB_V3_SCREEN): built and measured in round 2, off by default.
+// It does what it was designed for — ncu: 16 % fewer shared-memory wavefronts, FP64 pipe 22 % -> 11 %,
+// bit-identical spectra — and the kernel gets SLOWER (full C3 volume: 474 -> 538 ms): the FP32 copy of
+// the dictionary costs two of the twelve warps per SM (-10 % on its own) and the added serial work per
+// trip costs more than the saved bandwidth returns; the kernel is bound by dependent-instruction
+// latency at three warps per scheduler, not by the shared-memory pipe alone
+// (profiles/r2_nnls_experiments.md).
+#ifndef PNB_V3_SCREEN
+#define PNB_V3_NO_SCREEN 1
+#endif
+#define PNB_PRAGMA_(x) _Pragma(#x)
+#define PNB_UNROLL(n) PNB_PRAGMA_(unroll n)
 
 template <int MT, int WK> struct NnlsV3Cfg {
   static constexpr int NQ = 8;                 // bins per lane
@@ -189,7 +209,11 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
     int phase = PH_INIT, pass = 0;
     bool do_dual = true;
     double hmax = 0.0, rel = 1.0, zscale = 0.0;
+#ifdef PNB_V3_NO_SCREEN
+    const bool screen_ok = false;    // (variant without the screening code, for measurements)
+#else
     bool screen_ok = a.screen != 0;  // FP32 screening of the dual pass still pays for this voxel
+#endif
     int jc = -1;          // PH_CHECK: the candidate whose would-be coefficient is being computed
     double wjc = 0.0;     // ... and its dual
 
@@ -311,6 +335,19 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
           }
           return b0 + b1;
         };
+        // the regulariser term of the lane's eight bins, once per trip (every use below reads these
+        // registers: inlining band_q at each use tripled the loop body and the kernel started to wait
+        // for instruction fetch — 2.3 no_instruction stalls per issue, 50 % slower)
+        double bandv[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; q++) bandv[q] = band_q(q);
+        // element q (a run-time index) of a register array
+        auto pick = [](const double (&v)[NQ], int q) -> double {
+          double r = v[0];
+#pragma unroll
+          for (int t = 1; t < NQ; t++) r = (q == t) ? v[t] : r;
+          return r;
+        };
         bool exact_pass = true;
         if (screen_ok && phase != PH_VERIFY) {
           // ---- FP32 screening.  Half of this kernel's shared-memory traffic was the FP64 dictionary in
@@ -326,9 +363,11 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
 #pragma unroll
           for (int b = 0; b < MT; b++) { r32[b] = (float)rr[b]; rn1 += fabs(rr[b]); }
           const double E = 2e-6 * rn1;
+          // rolled loops from here on: the whole kernel has to stay under 4096 instructions (64 KB), the
+          // instruction cache it is served from — 88 instructions above that it ran 50 % slower
           float w32[NQ];
           double lmax = 0.0;
-#pragma unroll
+          PNB_UNROLL(PNB_V3_UQ32)
           for (int q = 0; q < NQ; q++) {
             const float4 *bp = reinterpret_cast<const float4 *>(Bf + (q * 32 + lane) * C::LDF);
             float s0 = 0.0f, s1 = 0.0f;
@@ -340,8 +379,10 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
               s0 = fmaf(v.z, r32[4 * t + 2], s0);
               s1 = fmaf(v.w, r32[4 * t + 3], s1);
             }
-            const double w = (double)(s0 + s1) - band_q(q);
-            w32[q] = (float)w;
+            const double w = (double)(s0 + s1) - pick(bandv, q);
+#pragma unroll
+            for (int t = 0; t < NQ; t++)
+              if (q == t) w32[t] = (float)w;
             if (!((skip >> q) & 1u) && w > lmax) lmax = w;
           }
           const unsigned hi = (unsigned)__double2hiint(lmax);
@@ -352,22 +393,28 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
           if (wmax32 > 32.0 * E) {
             exact_pass = false;
             const float thr = (float)(wmax32 - 2.0 * E - 2e-7 * wmax32);  // w32 itself is rounded to float
+            // the candidates (1.3 per trip on average), one rolled loop: q selects its registers
+            unsigned cand = 0;
 #pragma unroll
-            for (int q = 0; q < NQ; q++) {
-              if (!((skip >> q) & 1u) && w32[q] >= thr) {
-                const double acc = col_dot(q * 32 + lane, rr) - band_q(q);
-                if (acc > best) { best = acc; bq = q; }
-              }
+            for (int q = 0; q < NQ; q++)
+              if (!((skip >> q) & 1u) && w32[q] >= thr) cand |= 1u << q;
+#pragma unroll 1
+            while (cand) {
+              const int q = __ffs(cand) - 1;
+              cand &= cand - 1;
+              const double acc = col_dot(q * 32 + lane, rr) - pick(bandv, q);
+              if (acc > best) { best = acc; bq = q; }
             }
           } else {
+#ifndef PNB_V3_NO_SCREEN
             screen_ok = false;
+#endif
           }
         }
         if (exact_pass) {
-#pragma unroll
+          PNB_UNROLL(PNB_V3_UQX)
           for (int q = 0; q < NQ; q++) {
-            double acc = col_dot(q * 32 + lane, rr);
-            if (LB > 0) acc -= band_q(q);
+            const double acc = col_dot(q * 32 + lane, rr) - pick(bandv, q);
             if (!((skip >> q) & 1u) && acc > best) { best = acc; bq = q; }
           }
         }
@@ -789,8 +836,12 @@ namespace pnb {
 // Launch one CTA per SM with as many warps (<= PNB_V3_MAXWARPS) and extension areas (3 + 1) as
 // shared memory holds.  Returns cudaErrorInvalidConfiguration when not even 4 warps fit.
 template <int MT, int WK>
-cudaError_t nnls_v3_launch(const NnlsDeviceArgs &a, cudaStream_t stream) {
+cudaError_t nnls_v3_launch(const NnlsDeviceArgs &a_in, cudaStream_t stream) {
   using C = NnlsV3Cfg<MT, WK>;
+  NnlsDeviceArgs a = a_in;
+#ifdef PNB_V3_NO_SCREEN
+  a.screen = 0;  // the screening code is not in this build: no shared memory for the FP32 dictionary either
+#endif
   constexpr size_t budget = 227 * 1024;
   int warps = PNB_V3_MAXWARPS, e1 = 3, e2 = 1;
   const bool sc = a.screen != 0;
