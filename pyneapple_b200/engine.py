@@ -218,6 +218,28 @@ def trf_fit(
     return dict(params=params, cov=cov, status=status, nfev=nfev, njev=njev, cost=cost, r2=r2)
 
 
+_CONSTS: dict = {}
+
+
+def _small_const(a, dev):
+    """Device copy of a small host vector (b-values, broadcast p0 / bounds, the NNLS dictionary),
+    cached by content.  Uploading it on every call is a pageable H2D copy, i.e. a synchronisation of the
+    stream: back-to-back device-path launches then wait for each other on the host, and every host
+    hiccup lands in the step time (measured: 13.4 -> 18.9 ms per C2 step while nvidia-smi was polling)."""
+    import torch
+
+    arr = np.ascontiguousarray(a, np.float64)
+    if arr.nbytes > (1 << 16):
+        return torch.as_tensor(arr).to(dev)
+    key = (str(dev), arr.shape, arr.tobytes())
+    t = _CONSTS.get(key)
+    if t is None:
+        if len(_CONSTS) > 256:
+            _CONSTS.clear()
+        t = _CONSTS[key] = torch.as_tensor(arr).to(dev)
+    return t
+
+
 def _trf_fit_device(lib, prob, desc, xdata, ydata, p0, lb, ub, n_free, want_cov):
     import torch
 
@@ -231,7 +253,7 @@ def _trf_fit_device(lib, prob, desc, xdata, ydata, p0, lb, ub, n_free, want_cov)
     def dev_f64(a):
         if isinstance(a, torch.Tensor):
             return a.to(device=dev, dtype=torch.float64).contiguous()
-        return torch.as_tensor(np.ascontiguousarray(a, np.float64)).to(dev)
+        return _small_const(a, dev)
 
     b = dev_f64(xdata)
     p0, lb, ub = dev_f64(p0), dev_f64(lb), dev_f64(ub)
@@ -339,8 +361,8 @@ def nnls_fit(basis, reg_matrix, signal, max_iter: int, *, device=0, chunk_vox: i
         if y.ndim != 2 or y.shape[1] != n_b:
             raise ValueError(f"signal must be (n_vox, {n_b}), got {tuple(y.shape)}")
         n_vox = y.shape[0]
-        Bd = torch.as_tensor(B).to(dev)
-        bd = torch.as_tensor(band).to(dev)
+        Bd = _small_const(B, dev)
+        bd = _small_const(band, dev)
         coef = torch.empty((n_vox, n_bins), dtype=torch.float64, device=dev)
         res = torch.empty(n_vox, dtype=torch.float64, device=dev)
         status = torch.empty(n_vox, dtype=torch.int32, device=dev)
