@@ -35,6 +35,9 @@ from .curvefit import CurveFitSolver
 
 log = logging.getLogger("pyneapple_b200")
 
+# ftol = xtol = gtol of the three phases.  Measured on the 4 096-voxel SLSQP golden against a 1e-15 solution
+# (TRF stops on the first criterion met): 1e-13 leaves max 1e-5 / median 2e-8 relative in the parameters at 13.8
+# evaluations per voxel, 1e-11 max 9e-5 at 11.9 — too close to the 1e-4 of the contract to buy 14 % of speed with
 _TIGHT = 1e-13
 
 
