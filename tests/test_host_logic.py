@@ -259,3 +259,34 @@ def test_device_argument_forms():
         _lib.resolve_devices("some")
     assert _lib.shard_ranges(10, 3) == [(0, 4), (4, 7), (7, 10)]
     assert _lib.shard_ranges(2, 4) == [(0, 1), (1, 2), (2, 2), (2, 2)]
+
+
+def test_status_messages_are_scipys_texts():
+    from pyneapple_b200 import engine
+
+    m = engine.status_message
+    assert m(2) is None and m(4, "lm") is None
+    assert m(0) == "Optimal parameters not found: The maximum number of function evaluations is exceeded."
+    assert m(-3, "lm") == "array must not contain infs or NaNs"
+    assert m(0, "lm", max_nfev=8) == "Optimal parameters not found: Number of calls to function has reached maxfev = 8."
+    assert m(-6, "lm", ftol=1e-8).startswith("Optimal parameters not found: ftol=0.000000 is too small, no further reduction")
+    assert m(-7, "lm", xtol=1.49012e-8).startswith("Optimal parameters not found: xtol=0.000000 is too small")
+    assert m(-5, "lm") == "Method 'lm' only works for unconstrained problems. Use 'trf' or 'dogbox' instead."
+    assert m(engine.ST_LM_TOO_FEW_DATA, "lm", n_params=3, n_data=2) == (
+        "The number of func parameters=3 must not exceed the number of data points=2")
+
+
+def test_small_constants_are_uploaded_once(monkeypatch):
+    """Device-path launches reuse the device copies of b-values / broadcast p0 / bounds (no stream
+    synchronisation per call); checked on the CPU with torch's cpu device standing in."""
+    import torch
+
+    from pyneapple_b200 import engine
+
+    engine._CONSTS.clear()
+    a = engine._small_const(np.array([1.0, 2.0, 3.0]), torch.device("cpu"))
+    b = engine._small_const([1.0, 2.0, 3.0], torch.device("cpu"))
+    c = engine._small_const(np.array([1.0, 2.0, 4.0]), torch.device("cpu"))
+    assert a is b and c is not a and torch.equal(c, torch.tensor([1.0, 2.0, 4.0], dtype=torch.float64))
+    big = engine._small_const(np.zeros(1 << 14), torch.device("cpu"))
+    assert big is not engine._small_const(np.zeros(1 << 14), torch.device("cpu"))
