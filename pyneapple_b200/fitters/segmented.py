@@ -79,6 +79,9 @@ class SegmentedFitter(BaseFitter):
         return xdata[mask], image[..., mask]
 
     def fit(self, xdata, image, segmentation=None, **fit_kwargs):
+        from .. import _lib
+
+        _lib.require_device()  # EngineError, not a torch error, when there is no GPU
         import torch
 
         xdata = np.asarray(xdata)

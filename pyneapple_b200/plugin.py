@@ -30,11 +30,19 @@ FITTERS = {"pixelwise": "PixelWiseFitter", "segmentationwise": "SegmentationWise
 
 
 def _mixed(ours: type, theirs: type) -> type:
+    if issubclass(theirs, ours):  # somebody already put a mixed class where Pyneapple's was
+        return theirs
     return type(ours.__name__, (ours, theirs), {"__module__": ours.__module__, "__doc__": ours.__doc__})
 
 
+_CLASSES: tuple | None = None
+
+
 def plugin_classes() -> tuple[dict, dict]:
-    """B200 solver / fitter classes, mixed with Pyneapple's when it is importable."""
+    """B200 solver / fitter classes, mixed with Pyneapple's when it is importable (built once)."""
+    global _CLASSES
+    if _CLASSES is not None:
+        return _CLASSES
     from . import fitters as our_fitters
     from . import solvers as our_solvers
 
@@ -51,6 +59,8 @@ def plugin_classes() -> tuple[dict, dict]:
     for key, name in FITTERS.items():
         cls = getattr(our_fitters, name)
         f[key] = _mixed(cls, getattr(ref_fitters, name)) if ref_fitters else cls
+    if ref_solvers is not None:
+        _CLASSES = (s, f)
     return s, f
 
 

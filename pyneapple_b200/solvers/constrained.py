@@ -98,7 +98,7 @@ class ConstrainedCurveFitSolver(CurveFitSolver):
         n_pixels = ydata.shape[0] if ydata.ndim > 1 else 1
         if ydata.ndim == 1:
             ydata = ydata[None, :]
-        p0_m, lb_m, ub_m = self._validate_p0_and_bounds(p0, bounds, n_pixels)
+        p0_m, lb_m, ub_m = self._p0_and_bounds(p0, bounds, n_pixels)
         devices = [ydata.device.index] if on_device else _lib.resolve_devices(self.device)
         ranges = _lib.shard_ranges(n_pixels, len(devices)) if len(devices) > 1 else [(0, n_pixels)]
 

@@ -137,7 +137,7 @@ class CurveFitSolver(BaseSolver):
         n_pixels = ydata.shape[0] if ydata.ndim > 1 else 1
         if ydata.ndim == 1:
             ydata = ydata[None, :]
-        p0_m, lb_m, ub_m = self._validate_p0_and_bounds(p0, bounds, n_pixels)
+        p0_m, lb_m, ub_m = self._p0_and_bounds(p0, bounds, n_pixels)
         lm = self.method == "lm"
         bounded = bool(np.isfinite(np.asarray(lb_m)).any() or np.isfinite(np.asarray(ub_m)).any())
         lm_rejected = lm and bounded
@@ -270,6 +270,9 @@ class CurveFitSolver(BaseSolver):
         ``model.param_names``).  Returns the engine's dict of CUDA tensors plus
         ``free_names``; call :meth:`store_device_result` to publish it as ``params_`` etc.
         """
+        from .. import _lib
+
+        _lib.require_device()
         import torch
 
         desc = self._desc
@@ -414,8 +417,18 @@ class CurveFitSolver(BaseSolver):
 
     # ------------------------------------------------------------------
     def _validate_p0_and_bounds(self, p0, bounds, n_pixels):
-        """Reference ``_validate_p0_and_bounds`` (curvefit.py:319-392) without the tiling:
-        returns ``(p0, lb, ub)`` as ``(n_params,)`` vectors or ``(n_params, n_pixels)`` arrays."""
+        """The reference's ``_validate_p0_and_bounds`` (curvefit.py:319-392): ``(p0, (lower, upper))``,
+        each ``(n_params, n_pixels)``.  Scalars are broadcast views (read-only, no ``np.tile`` copy)."""
+        p0_m, lb_m, ub_m = self._p0_and_bounds(p0, bounds, n_pixels)
+
+        def wide(a):
+            return a if a.ndim == 2 else np.broadcast_to(a[:, None], (a.shape[0], n_pixels))
+
+        return wide(p0_m), (wide(lb_m), wide(ub_m))
+
+    def _p0_and_bounds(self, p0, bounds, n_pixels):
+        """Same validation, without the widening: ``(p0, lb, ub)`` as ``(n_params,)`` vectors or
+        ``(n_params, n_pixels)`` arrays (what the engine takes)."""
         names = self.model.param_names
         if p0 is not None:
             if isinstance(p0, dict):

@@ -13,7 +13,9 @@ Pyneapple on the box's host cores.  The documented route,
 fails in this image (the build backend ``hatchling`` is not installed and there is no index to get
 it from).  Pyneapple is pure Python with ``packages = ["src/pyneapple"]`` (pyproject.toml:108-109), so
 the wheel that install would produce is exactly the ``src/pyneapple`` tree: the fallback copies it.
-Also copied: the three example TOML files the parity tests load (examples/configs, examples/parameters).
+Also copied: the example TOML files the parity tests load (examples/configs, examples/parameters) and the
+reference's own solver / fitter test files (tests/test_solver_*.py, tests/test_fitter_*.py, test_toolbox.py), which
+tests/test_reference_suite.py runs against the B200 classes.
 """
 
 from __future__ import annotations
@@ -58,6 +60,13 @@ def main() -> int:
         shutil.copytree(os.path.join(SRC, "src", "pyneapple"), os.path.join(DST, "pyneapple"),
                         ignore=shutil.ignore_patterns("__pycache__"))
         how = "copy of src/pyneapple (pip needs hatchling, absent here)"
+    # the reference's own solver / fitter tests: tests/test_reference_suite.py runs them against the B200 classes
+    tdst = os.path.join(DST, "tests")
+    shutil.rmtree(tdst, ignore_errors=True)
+    os.makedirs(tdst)
+    for name in sorted(os.listdir(os.path.join(SRC, "tests"))):
+        if name.startswith(("test_solver_", "test_fitter_")) or name == "test_toolbox.py":
+            shutil.copy(os.path.join(SRC, "tests", name), os.path.join(tdst, name))
     ex = os.path.join(DST, "examples")
     shutil.rmtree(ex, ignore_errors=True)
     for sub in ("configs", "parameters"):

@@ -125,23 +125,23 @@ def test_curvefit_solver_constructor_contract():
 
 def test_p0_and_bounds_packing_errors():
     s = _mono()
-    p0, lb, ub = s._validate_p0_and_bounds(None, None, 7)
+    p0, lb, ub = s._p0_and_bounds(None, None, 7)
     assert p0.shape == lb.shape == ub.shape == (2,)  # broadcast vector, not tiled
-    p0, lb, ub = s._validate_p0_and_bounds({"S0": 900.0, "D": 2e-3}, {"S0": (2.0, 10.0), "D": (0.0, 1.0)}, 7)
+    p0, lb, ub = s._p0_and_bounds({"S0": 900.0, "D": 2e-3}, {"S0": (2.0, 10.0), "D": (0.0, 1.0)}, 7)
     assert list(p0) == [900.0, 2e-3] and list(ub) == [10.0, 1.0]
     arr = np.ones((2, 7))
-    p0, lb, ub = s._validate_p0_and_bounds(arr, (arr * 0, arr * 2), 7)
+    p0, lb, ub = s._p0_and_bounds(arr, (arr * 0, arr * 2), 7)
     assert p0.shape == (2, 7)
     with pytest.raises(ValueError):
-        s._validate_p0_and_bounds(np.ones((2, 6)), None, 7)
+        s._p0_and_bounds(np.ones((2, 6)), None, 7)
     with pytest.raises(ValueError):
-        s._validate_p0_and_bounds({"S0": np.ones(7), "D": np.ones(7)}, None, 7)
+        s._p0_and_bounds({"S0": np.ones(7), "D": np.ones(7)}, None, 7)
     with pytest.raises(ValueError):
-        s._validate_p0_and_bounds([1.0, 2.0], None, 7)
+        s._p0_and_bounds([1.0, 2.0], None, 7)
     with pytest.raises(ValueError):
-        s._validate_p0_and_bounds(None, (arr, [1, 2]), 7)
+        s._p0_and_bounds(None, (arr, [1, 2]), 7)
     with pytest.raises(ValueError):
-        s._validate_p0_and_bounds(None, (np.ones((2, 3)), np.ones((2, 3))), 7)
+        s._p0_and_bounds(None, (np.ones((2, 3)), np.ones((2, 3))), 7)
     with pytest.raises(ValueError):
         V.validate_data_shapes(B, np.ones((4, 15)))
     with pytest.raises(ValueError):
@@ -290,3 +290,17 @@ def test_small_constants_are_uploaded_once(monkeypatch):
     assert a is b and c is not a and torch.equal(c, torch.tensor([1.0, 2.0, 4.0], dtype=torch.float64))
     big = engine._small_const(np.zeros(1 << 14), torch.device("cpu"))
     assert big is not engine._small_const(np.zeros(1 << 14), torch.device("cpu"))
+
+
+def test_validate_p0_and_bounds_has_the_references_contract():
+    """``_validate_p0_and_bounds`` is exercised by the reference's own tests (tests/test_solver_curvefit.py:
+    186-262): ``(p0, (lower, upper))``, each ``(n_params, n_pixels)``."""
+    s = _mono()
+    p0, (lo, hi) = s._validate_p0_and_bounds(None, None, 5)
+    assert p0.shape == lo.shape == hi.shape == (2, 5) and isinstance(p0, np.ndarray)
+    assert (p0[0] == p0[0, 0]).all()
+    arr = np.tile(np.array([900.0, 0.0012])[:, None], (1, 4))
+    got, _ = s._validate_p0_and_bounds(arr, None, 4)
+    assert np.array_equal(got, arr)
+    with pytest.raises(ValueError, match="shape"):
+        s._validate_p0_and_bounds(np.zeros((2, 3)), None, 5)
