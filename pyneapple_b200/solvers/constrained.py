@@ -237,11 +237,12 @@ class ConstrainedCurveFitSolver(CurveFitSolver):
                             max_nfev=max(4 * self.max_iter, 1000), ftol=_TIGHT, xtol=_TIGHT, gtol=_TIGHT,
                             jac_mode=engine.JAC_ANALYTIC, want_cov=False)
         ok = r2["status"] > 0
+        # a face fit that fails (iteration limit) reports its start point — the projection of the phase-1
+        # answer onto the face — so the voxel is returned feasible, with success = False, instead of keeping
+        # the violating box-bounded answer
         for j, nm in enumerate(face_names):
-            row = par[all_names.index(nm)]
-            row.index_copy_(0, idx, torch.where(ok, r2["params"][j], row.index_select(0, idx)))
-        row2 = par[i2]
-        row2.index_copy_(0, idx, torch.where(ok, 1.0 - r2["params"][j1], row2.index_select(0, idx)))
+            par[all_names.index(nm)].index_copy_(0, idx, r2["params"][j])
+        par[i2].index_copy_(0, idx, 1.0 - r2["params"][j1])
         res["nfev"].index_add_(0, idx, r2["nfev"])
         res["status"].index_copy_(0, idx, torch.where(ok, res["status"].index_select(0, idx),
                                                       torch.zeros_like(r2["status"])))

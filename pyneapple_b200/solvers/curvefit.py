@@ -15,7 +15,7 @@ import numpy as np
 from .. import engine
 from ..models import describe_model
 from .. import validation as V
-from .base import BaseSolver, PixelResults
+from .base import BaseSolver, PixelResults, _PixelFitResult
 
 log = logging.getLogger("pyneapple_b200")
 
@@ -169,6 +169,35 @@ class CurveFitSolver(BaseSolver):
                 res["cov"] = np.full(tuple(res["cov"].shape), np.nan)
         self._store(res, free_names, n_pixels)
         return self
+
+    # ------------------------------------------------------------------
+    # The reference's two internal hooks, with its signatures (curvefit.py:171-244, 246-317).  They are
+    # exercised directly by its own tests; here they run on the GPU like everything else (the class the
+    # plugin registers also derives from Pyneapple's CurveFitSolver, whose SciPy versions these override).
+    def _fit_data(self, xdata, ydata, p0, bounds, n_pixels, pixel_fixed_params=None):
+        """``(popt (n_params, n_pixels), pcov (n_pixels, n_params, n_params))``; sets ``pixel_results_``."""
+        ydata = np.asarray(ydata)
+        if ydata.ndim == 1:
+            ydata = ydata[None, :]
+        res, free_names = self._solve(np.asarray(xdata), ydata, np.asarray(p0, float), np.asarray(bounds[0], float),
+                                      np.asarray(bounds[1], float), pixel_fixed_params, n_pixels)
+        self._store(res, free_names, n_pixels)
+        popt = np.stack([np.asarray(res["params"][r]) for r in self._free_rows])
+        pcov = res["cov"]
+        pcov = np.full((n_pixels, popt.shape[0], popt.shape[0]), np.nan) if pcov is None else np.asarray(pcov)
+        return popt, pcov
+
+    def _fit_single_pixel(self, xdata, ydata, p0, bounds, pixel_idx=None, pixel_fixed=None):
+        """One voxel -> ``_PixelFitResult`` (failure: params = p0, NaN covariance, SciPy's message)."""
+        p0 = np.asarray(p0, float)
+        pf = {k: np.array([float(v)]) for k, v in pixel_fixed.items()} if pixel_fixed else None
+        keep = (self.params_, self.diagnostics_, self.pixel_results_)
+        try:
+            self._fit_data(xdata, np.asarray(ydata)[None, :], p0[:, None], (np.asarray(bounds[0], float)[:, None],
+                                                                            np.asarray(bounds[1], float)[:, None]), 1, pf)
+            return self.pixel_results_[0]
+        finally:
+            self.params_, self.diagnostics_, self.pixel_results_ = keep
 
     # ------------------------------------------------------------------
     def _solve(self, xdata, ydata, p0_m, lb_m, ub_m, pixel_fixed_params, n_pixels, max_nfev=None, method=None):

@@ -8,7 +8,7 @@ from typing import Any
 import numpy as np
 
 from .. import engine
-from .base import BaseSolver, PixelResults
+from .base import BaseSolver, PixelResults, _PixelFitResult
 
 log = logging.getLogger("pyneapple_b200")
 
@@ -71,6 +71,37 @@ class NNLSSolver(BaseSolver):
 
     def _extend_signal(self, signal: np.ndarray) -> np.ndarray:
         return np.concatenate((signal, np.zeros((signal.shape[0], self.model.n_bins))), axis=1)
+
+    # The reference's internal hooks (nnls_solver.py:129-210): they take the regularised system
+    # ``A = [basis; mu R]`` and the zero-extended signals; split back into the structured form the kernel uses.
+    def _fit_data(self, basis, signal):
+        """``(coefficients (n_pixels, n_bins), residuals (n_pixels,))``; sets ``pixel_results_``."""
+        A = np.asarray(basis, dtype=np.float64)
+        n_bins = A.shape[1]
+        n_b = A.shape[0] - n_bins
+        if n_b < 1:
+            raise ValueError(f"regularised basis must have more rows than columns, got {A.shape}")
+        y = np.asarray(signal, dtype=np.float64)
+        if y.ndim == 1:
+            y = y[None, :]
+        if np.any(y[:, n_b:] != 0.0):
+            raise NotImplementedError("the right-hand side of the regulariser rows must be zero")
+        res = engine.nnls_fit(A[:n_b], A[n_b:], np.ascontiguousarray(y[:, :n_b]), self.max_iter,
+                              device=self.device, algorithm=self.algorithm, dual_init=self.dual_init)
+        status = res["status"]
+        self.pixel_results_ = PixelResults(params=res["coefficients"], covariance=None, success=status == 1,
+                                           residual=res["residual"])
+        return res["coefficients"], res["residual"]
+
+    def _fit_single_pixel(self, basis, signal, pixel_idx=None):
+        keep = self.pixel_results_
+        try:
+            self._fit_data(basis, np.asarray(signal)[None, :])
+            pr = self.pixel_results_[0]
+        finally:
+            self.pixel_results_ = keep
+        return _PixelFitResult(params=pr.params, residual=pr.residual, success=pr.success,
+                               message=None if pr.success else "Maximum number of iterations reached.")
 
     def fit(self, xdata, signal, pixel_fixed_params=None) -> "NNLSSolver":
         self._reset_state()

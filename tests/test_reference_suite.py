@@ -20,12 +20,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SUITE = os.path.join(reference.REF_DIR, "tests")
 pytestmark = pytest.mark.skipif(not os.path.isdir(SUITE), reason="baseline/_ref/tests is missing: run scripts/install_reference.py")
 
-# Tests of the reference that assert its CPU internals rather than the solver / fitter contract:
-#  * joblib wiring (`Parallel` is mocked and expected to be called): the GPU solvers accept `multi_threading` /
-#    `n_pools` and ignore them (SURVEY.md §8b "Threading");
-#  * the per-voxel `_fit_single_pixel` hook being called / patched.
+# Tests of the reference that assert its CPU internals rather than the solver / fitter contract — they patch a
+# SciPy function inside Pyneapple's modules (`curve_fit`, `minimize`, `nnls`) and expect the solver to run into the
+# patch, or patch the per-voxel hook and expect the batch loop to call it once per voxel.  The GPU solvers make no
+# SciPy call and have no per-voxel loop.  Everything else — including the tests that call the internal hooks
+# `_fit_data` / `_fit_single_pixel` directly, which the GPU classes implement with the reference's signatures — runs.
 CPU_INTERNALS = [
-    "multi_thread", "n_pools", "parallel", "_fit_single_pixel", "joblib",
+    "test_failed_fit_returns_p0_and_nan_cov",           # curvefit / constrained: scipy curve_fit / minimize patched to raise
+    "test_failed_fit_returns_zeros_and_norm_residual",  # nnls: scipy nnls patched to raise
+    "test_failed_pixel_produces_nan_in_popt",           # `_fit_single_pixel` patched on the instance
 ]
 
 
@@ -64,4 +67,4 @@ def test_without_a_gpu_everything_that_fits_fails_with_engine_error_only(tmp_pat
 def test_the_references_own_tests_pass_on_the_gpu(tmp_path):
     r = _run(tmp_path, ["--tb=short"])
     failed, passed = _counts(r.stdout)
-    assert failed == 0 and passed and passed >= 250, r.stdout[-6000:]
+    assert failed == 0 and passed and passed >= 290, r.stdout[-6000:]
