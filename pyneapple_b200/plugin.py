@@ -60,8 +60,22 @@ def plugin_classes() -> tuple[dict, dict]:
         cls = getattr(our_fitters, name)
         f[key] = _mixed(cls, getattr(ref_fitters, name)) if ref_fitters else cls
     if ref_solvers is not None:
+        _adopt_reference_records()
         _CLASSES = (s, f)
     return s, f
+
+
+def _adopt_reference_records() -> None:
+    """Per-voxel records handed out by the B200 solvers become instances of Pyneapple's own
+    ``_PixelFitResult`` (same fields), so ``isinstance`` checks in code written against the reference hold."""
+    from pyneapple.solvers import base as ref_base
+
+    from .solvers import base as our_base
+    from .solvers import curvefit as our_curvefit
+    from .solvers import nnls as our_nnls
+
+    for mod in (our_base, our_curvefit, our_nnls):
+        mod._PixelFitResult = ref_base._PixelFitResult
 
 
 def _registries():
