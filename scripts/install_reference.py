@@ -14,7 +14,8 @@ fails in this image (the build backend ``hatchling`` is not installed and there 
 it from).  Pyneapple is pure Python with ``packages = ["src/pyneapple"]`` (pyproject.toml:108-109), so
 the wheel that install would produce is exactly the ``src/pyneapple`` tree: the fallback copies it.
 Also copied: the example TOML files the parity tests load (examples/configs, examples/parameters) and the
-reference's own solver / fitter test files (tests/test_solver_*.py, tests/test_fitter_*.py, test_toolbox.py), which
+reference's own solver / fitter / spectrum test files (tests/test_solver_*.py, tests/test_fitter_*.py,
+test_utility_spectrum.py, test_toolbox.py), which
 tests/test_reference_suite.py runs against the B200 classes.
 """
 
@@ -65,7 +66,7 @@ def main() -> int:
     shutil.rmtree(tdst, ignore_errors=True)
     os.makedirs(tdst)
     for name in sorted(os.listdir(os.path.join(SRC, "tests"))):
-        if name.startswith(("test_solver_", "test_fitter_")) or name == "test_toolbox.py":
+        if name.startswith(("test_solver_", "test_fitter_")) or name in ("test_toolbox.py", "test_utility_spectrum.py"):
             shutil.copy(os.path.join(SRC, "tests", name), os.path.join(tdst, name))
     ex = os.path.join(DST, "examples")
     shutil.rmtree(ex, ignore_errors=True)

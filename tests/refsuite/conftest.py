@@ -26,6 +26,14 @@ for _key, _name in plugin.FITTERS.items():
     setattr(pyneapple.fitters, _name, _fitters[_key])
 plugin.install()
 
+# the spectrum post-processing functions (utility/spectrum.py) likewise: same names, same arguments, on the GPU
+import pyneapple.utility.spectrum as _ref_spectrum  # noqa: E402
+
+from pyneapple_b200 import spectrum as _our_spectrum  # noqa: E402
+
+for _name in ("find_spectrum_peaks", "calculate_peak_area", "apply_cutoffs", "geometric_mean_peak"):
+    setattr(_ref_spectrum, _name, getattr(_our_spectrum, _name))
+
 
 class _Patcher:
     """The two entry points of pytest-mock's ``mocker.patch`` the reference's tests use (the plugin is not installed)."""
