@@ -131,6 +131,9 @@ int pnb_trf_fit_host(const pnb_trf_problem *prob, int device, int64_t chunk_vox)
  * n_devices DEVICE buffers, buffer i on GPU i holding its range's (n_range, n_free, n_free). */
 int pnb_trf_fit_host_multi(const pnb_trf_problem *prob, const int32_t *devices, int32_t n_devices,
                            int64_t chunk_vox, double *const *cov_per_device);
+/* voxels of the most recent pnb_trf_fit_host / _host_multi call of this process that ended with
+ * status <= 0, counted by the kernels (a pass over the status array costs the host milliseconds) */
+int64_t pnb_trf_last_failed_count(void);
 
 /*
  * Tikhonov-regularised non-negative least squares for n_vox voxels on a shared

@@ -214,6 +214,7 @@ def load():
     lib.pnb_trf_fit_host_multi.restype = C.c_int
     lib.pnb_nnls_fit_host_multi.argtypes = [C.POINTER(NnlsProblem), C.POINTER(C.c_int32), C.c_int32, C.c_int64]
     lib.pnb_nnls_fit_host_multi.restype = C.c_int
+    lib.pnb_trf_last_failed_count.restype = C.c_int64
     lib.pnb_nnls_fit_device.argtypes = [C.POINTER(NnlsProblem), C.c_void_p]
     lib.pnb_nnls_fit_device.restype = C.c_int
     lib.pnb_nnls_fit_host.argtypes = [C.POINTER(NnlsProblem), C.c_int, C.c_int64]

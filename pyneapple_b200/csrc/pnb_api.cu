@@ -269,6 +269,7 @@ extern "C" int pnb_trf_fit_device(const pnb_trf_problem *p, void *cuda_stream) {
   a.params = p->params; a.cov = p->cov; a.status = p->status; a.nfev = p->nfev;
   a.njev = p->njev; a.cost = p->cost; a.r2 = p->r_squared;
   if (int rc = next_counter(&a.counter)) return rc;
+  a.n_failed = nullptr;
   cudaError_t e = trf_launcher(p->model_id, p->t1_mode, p->method)(&a, stream);
   if (e != cudaSuccess) return cuda_fail(e, "trf kernel launch");
   g_launches.fetch_add(1);
@@ -299,8 +300,10 @@ struct Pipeline {
   Slot slots[kSlots];
   double *b = nullptr, *vec = nullptr;  // xdata, broadcast p0|lb|ub
   size_t cap_b = 0;
+  unsigned long long *n_failed = nullptr;  // voxels of the current call that ended with status <= 0
   bool init = false;
 };
+std::atomic<long long> g_last_failed{0};  // failures of the most recent host call (all devices of a multi call)
 Pipeline g_pipes[16];
 std::mutex g_pipe_mu[16];  // one host pipeline per device; different devices run concurrently
 
@@ -341,6 +344,7 @@ int trf_host_range(const pnb_trf_problem *p, int device, int64_t chunk_vox, size
       PNB_CUDA(cudaMalloc(&s.counter, sizeof(unsigned long long)));
     }
     PNB_CUDA(cudaMalloc(&P.vec, sizeof(double) * 3 * 8));
+    PNB_CUDA(cudaMalloc(&P.n_failed, sizeof(unsigned long long)));
     P.init = true;
   }
   if (int rc = grow(&P.b, &P.cap_b, (size_t)nb)) return rc;
@@ -361,6 +365,7 @@ int trf_host_range(const pnb_trf_problem *p, int device, int64_t chunk_vox, size
   }
   // shared small inputs (synchronous, tiny)
   cudaStream_t s0 = P.slots[0].stream;
+  PNB_CUDA(cudaMemsetAsync(P.n_failed, 0, sizeof(unsigned long long), s0));
   PNB_CUDA(cudaMemcpyAsync(P.b, p->xdata, sizeof(double) * nb, cudaMemcpyHostToDevice, s0));
   if (!p->p0_per_voxel)
     PNB_CUDA(cudaMemcpyAsync(P.vec, p->p0, sizeof(double) * np, cudaMemcpyHostToDevice, s0));
@@ -412,9 +417,27 @@ int trf_host_range(const pnb_trf_problem *p, int device, int64_t chunk_vox, size
     return 0;
   };
   int slot = 0;
-  for (size_t start = v0; start < v1; start += C, slot = (slot + 1) % Pipeline::kSlots) {
+  // Chunk schedule: C-sized chunks with a short ramp at both ends (C/4, C/2 ... C/2, C/4), so the first
+  // kernel starts after a quarter of a chunk's upload and only a quarter chunk's results are still on
+  // their way when the last kernel ends.
+  std::vector<size_t> sizes;
+  {
+    size_t rem = v1 - v0;
+    const size_t q = C / 4, h = C / 2;
+    const bool ramp = q >= 4096 && rem > 3 * C;
+    if (ramp) { sizes.push_back(q); sizes.push_back(h); rem -= q + h; }
+    const size_t tail = ramp ? q + h : 0;
+    while (rem > tail) {
+      const size_t n = (rem - tail < C) ? rem - tail : C;
+      sizes.push_back(n);
+      rem -= n;
+    }
+    if (ramp) { sizes.push_back(h); sizes.push_back(q); }
+  }
+  size_t start = v0;
+  for (size_t ci = 0; ci < sizes.size(); start += sizes[ci], ci++, slot = (slot + 1) % Pipeline::kSlots) {
     Slot &s = P.slots[slot];
-    const size_t n = (v1 - start < C) ? v1 - start : C;
+    const size_t n = sizes[ci];
     const double *src_y = p->ydata + start * nb, *src_p0 = p->p0 + start, *src_lb = p->lb + start,
                  *src_ub = p->ub + start;
     size_t pitch = NV * D;  // row pitch of the caller's (n_params, n_vox) arrays
@@ -461,6 +484,7 @@ int trf_host_range(const pnb_trf_problem *p, int device, int64_t chunk_vox, size
     a.njev = p->njev ? s.njev : nullptr; a.cost = p->cost ? s.cost : nullptr;
     a.r2 = p->r_squared ? s.r2 : nullptr;
     a.counter = s.counter;
+    a.n_failed = P.n_failed;
     cudaError_t e = launch(&a, s.stream);
     if (e != cudaSuccess) return cuda_fail(e, "trf kernel launch");
     g_launches.fetch_add(1);
@@ -495,6 +519,9 @@ int trf_host_range(const pnb_trf_problem *p, int device, int64_t chunk_vox, size
       if (int rc = drain(P.slots[(slot + k) % Pipeline::kSlots])) return rc;
     }
   for (auto &s : P.slots) PNB_CUDA(cudaStreamSynchronize(s.stream));
+  unsigned long long nf = 0;
+  PNB_CUDA(cudaMemcpy(&nf, P.n_failed, sizeof(nf), cudaMemcpyDeviceToHost));
+  g_last_failed.fetch_add((long long)nf);
   (void)any_cov;
   return 0;
 }
@@ -510,8 +537,11 @@ bool is_device_ptr(const void *ptr, int *dev_out) {
 }
 }  // namespace
 
+extern "C" int64_t pnb_trf_last_failed_count(void) { return (int64_t)g_last_failed.load(); }
+
 extern "C" int pnb_trf_fit_host(const pnb_trf_problem *p, int device, int64_t chunk_vox) {
   if (int rc = check_problem(p)) return rc;
+  g_last_failed.store(0);
   if (p->n_vox == 0) return 0;
   int cov_device = -1;
   double *cov_dev = is_device_ptr(p->cov, &cov_device) ? p->cov : nullptr;
@@ -526,6 +556,7 @@ extern "C" int pnb_trf_fit_host_multi(const pnb_trf_problem *p, const int32_t *d
                                       int64_t chunk_vox, double *const *cov_per_device) {
   if (int rc = check_problem(p)) return rc;
   if (n_devices < 1 || n_devices > 16) return fail(PNB_E_BADARG, "n_devices must be in [1, 16]");
+  g_last_failed.store(0);
   if (p->n_vox == 0) return 0;
   const size_t NV = (size_t)p->n_vox;
   std::vector<int> rcs(n_devices, 0);

@@ -49,6 +49,7 @@ struct TrfDeviceArgs {
   double *cost;          // (n_vox) or nullptr
   double *r2;            // (n_vox) or nullptr: 1 - SS_res / SS_tot at the returned parameters
   unsigned long long *counter;  // work counter, zeroed before launch
+  unsigned long long *n_failed; // += voxels that end with status <= 0 (failures are rare), or nullptr
 };
 
 __device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc) {
@@ -247,6 +248,7 @@ __global__ void __launch_bounds__(BLOCK, PNB_TRF_MINBLOCKS) trf_kernel(const Trf
         a.params[(long long)k * a.n_vox + vox] = ok ? S.x[k] : my_p0[k * BLOCK];
       }
       a.status[vox] = S.status;
+      if (S.status <= 0 && a.n_failed) atomicAdd(a.n_failed, 1ULL);
       a.nfev[vox] = S.nfev;
       if (a.njev) a.njev[vox] = S.njev;
       if (a.cost) a.cost[vox] = (ok || S.status == kStMaxNfev) ? S.cost : nan("");

@@ -215,7 +215,8 @@ def trf_fit(
         from ._lazy import LazyArray
 
         cov = LazyArray((n_vox, n_free, n_free), cov_parts)
-    return dict(params=params, cov=cov, status=status, nfev=nfev, njev=njev, cost=cost, r2=r2)
+    return dict(params=params, cov=cov, status=status, nfev=nfev, njev=njev, cost=cost, r2=r2,
+                n_failed=int(lib.pnb_trf_last_failed_count()))
 
 
 _CONSTS: dict = {}

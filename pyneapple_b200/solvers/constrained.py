@@ -121,9 +121,11 @@ class ConstrainedCurveFitSolver(CurveFitSolver):
                 up = lambda arr: arr if np.ndim(arr) < 2 else engine.to_device(np.ascontiguousarray(arr), y.device)  # noqa: E731
                 res = self.fit_device(xdata, y, p0=up(part(p0_m, a, z)),
                                       bounds=(up(part(lb_m, a, z)), up(part(ub_m, a, z))), pixel_fixed_params=pf)
+                n_failed = int((res["status"] <= 0).sum().item())
                 lazy_cov = res.pop("cov") if (self.want_cov is True or self.want_cov == "lazy") else None
                 host = {k_: (engine.to_host(v) if hasattr(v, "cpu") else v) for k_, v in res.items()}
                 host["cov_dev"] = lazy_cov
+                host["n_failed"] = n_failed
                 return host
 
         if len(ranges) == 1:
@@ -146,6 +148,7 @@ class ConstrainedCurveFitSolver(CurveFitSolver):
             res["cov"] = np.concatenate([p["cov"] for _, p in live], axis=0)
         else:
             res["cov"] = None
+        res["n_failed"] = int(sum(p["n_failed"] for _, p in live))
         self.n_active_ = int(sum(p["n_active"] for _, p in live))      # box-bounded minimiser violated the constraint
         self.n_released_ = int(sum(p["n_released"] for _, p in live))  # ... and left the face again in phase 3
         self._free_rows = res["free_rows"]

@@ -154,6 +154,7 @@ class CurveFitSolver(BaseSolver):
             if (self.want_cov is True or self.want_cov == "lazy") and res.get("cov") is not None and not (lm_rejected or lm_too_few):
                 cov_dev = res.pop("cov")  # stays on the GPU until somebody reads it
             res = {k: (engine.to_host(v) if v is not None else None) for k, v in res.items()}
+            res.pop("n_failed", None)
             if cov_dev is not None:
                 from .._lazy import LazyArray
 
@@ -165,6 +166,7 @@ class CurveFitSolver(BaseSolver):
             # (solvers/curvefit.py:308-317).  The single evaluation above (dogbox leaves x0 = p0 untouched)
             # only supplies R^2 at p0.
             res["status"][...] = engine.ST_LM_BOUNDED if lm_rejected else engine.ST_LM_TOO_FEW_DATA
+            res["n_failed"] = n_pixels
             if res.get("cov") is not None:
                 res["cov"] = np.full(tuple(res["cov"].shape), np.nan)
         self._store(res, free_names, n_pixels)
@@ -440,7 +442,11 @@ class CurveFitSolver(BaseSolver):
             for i, name in enumerate(free_names)
         }
         self.diagnostics_ = {"pcov": pcov[0] if n_pixels == 1 else pcov, "n_pixels": n_pixels}
-        n_fail = int(np.count_nonzero(status <= 0))
+        # the kernels count the failed voxels (host path); a pass over 4 M status words costs milliseconds
+        n_fail = res.get("n_failed")
+        if n_fail is None:
+            n_fail = int(np.count_nonzero(np.asarray(status) <= 0))
+        self.n_failed_ = int(n_fail)
         if n_fail:
             log.warning("%d of %d voxel fits failed (see pixel_results_[i].message)", n_fail, n_pixels)
 

@@ -1,6 +1,6 @@
 """The reference's OWN solver / fitter test files (baseline/_ref/tests, unmodified) run against the B200 classes.
 
-`tests/refsuite/conftest.py` swaps `pyneapple.solvers.*` / `pyneapple.fitters.*` for the plugin classes before the
+`tests/refsuite/refsuite_conftest.py` (copied next to them as conftest.py) swaps `pyneapple.solvers.*` / `pyneapple.fitters.*` for the plugin classes before the
 reference's test modules import them, so every `CurveFitSolver(...)`, `PixelWiseFitter(...)` … in those files is the
 GPU implementation.  On a box without a GPU only the tests that never fit (constructors, validation, error
 behaviour) can pass — every other one must fail with the library's `EngineError` and nothing else; on the GPU the
@@ -37,7 +37,7 @@ def _run(tmp_path, extra):
     work.mkdir()
     for name in os.listdir(SUITE):
         shutil.copy(os.path.join(SUITE, name), work / name)
-    shutil.copy(os.path.join(ROOT, "tests", "refsuite", "conftest.py"), work / "conftest.py")
+    shutil.copy(os.path.join(ROOT, "tests", "refsuite", "refsuite_conftest.py"), work / "conftest.py")
     deselect = " and ".join(f"not {k}" for k in CPU_INTERNALS)
     cmd = [sys.executable, "-m", "pytest", "-c", os.devnull, "-p", "no:cacheprovider", "-q", "-k", deselect,
            "--rootdir", str(work), str(work)] + extra
