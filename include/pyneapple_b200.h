@@ -111,7 +111,9 @@ typedef struct pnb_trf_problem {
   double *params;            /* (n_params, n_vox); fixed rows repeat the fixed value */
   double *cov;               /* (n_vox, n_free, n_free) or NULL.  pnb_trf_fit_host also accepts
                                 DEVICE memory of the fitting GPU here: the covariances then stay
-                                on the GPU (no D2H traffic) for the caller to fetch on demand  */
+                                on the GPU (no D2H traffic) for the caller to fetch on demand;
+                                they are complete when the call returns (one covariance pass
+                                over the range follows the last chunk's solver kernel)         */
   int32_t *status;           /* (n_vox)                                        */
   int32_t *nfev;             /* (n_vox) residual evaluations, SciPy's count     */
   int32_t *njev;             /* (n_vox) or NULL                                */

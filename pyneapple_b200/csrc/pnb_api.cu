@@ -287,6 +287,7 @@ struct Slot {
   double *params = nullptr, *cov = nullptr, *cost = nullptr, *r2 = nullptr;
   int *status = nullptr, *nfev = nullptr, *njev = nullptr;
   unsigned long long *counter = nullptr;
+  cudaEvent_t kernel_done = nullptr;  // after the slot's most recent solver kernel
   size_t cap_y = 0, cap_p0 = 0, cap_lb = 0, cap_ub = 0, cap_par = 0, cap_cov = 0;
   size_t cap_cost = 0, cap_r2 = 0, cap_st = 0, cap_nf = 0, cap_nj = 0;
   // page-locked staging block for pageable caller memory
@@ -301,6 +302,7 @@ struct Pipeline {
   double *b = nullptr, *vec = nullptr;  // xdata, broadcast p0|lb|ub
   size_t cap_b = 0;
   unsigned long long *n_failed = nullptr;  // voxels of the current call that ended with status <= 0
+  cudaStream_t cov_stream = nullptr;       // the one covariance pass over a device-resident covariance range
   bool init = false;
 };
 std::atomic<long long> g_last_failed{0};  // failures of the most recent host call (all devices of a multi call)
@@ -342,7 +344,9 @@ int trf_host_range(const pnb_trf_problem *p, int device, int64_t chunk_vox, size
     for (auto &s : P.slots) {
       PNB_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
       PNB_CUDA(cudaMalloc(&s.counter, sizeof(unsigned long long)));
+      PNB_CUDA(cudaEventCreateWithFlags(&s.kernel_done, cudaEventDisableTiming));
     }
+    PNB_CUDA(cudaStreamCreateWithFlags(&P.cov_stream, cudaStreamNonBlocking));
     PNB_CUDA(cudaMalloc(&P.vec, sizeof(double) * 3 * 8));
     PNB_CUDA(cudaMalloc(&P.n_failed, sizeof(unsigned long long)));
     P.init = true;
@@ -485,8 +489,13 @@ int trf_host_range(const pnb_trf_problem *p, int device, int64_t chunk_vox, size
     a.r2 = p->r_squared ? s.r2 : nullptr;
     a.counter = s.counter;
     a.n_failed = P.n_failed;
+    // covariances that stay on the GPU: the chunks only park J^T J and the cost, ONE pass over the
+    // whole range follows the last chunk instead of a small kernel queued behind every chunk (which
+    // held each chunk's downloads back while the next chunk's persistent grid owned the SMs)
+    a.defer_cov = cov_dev ? 1 : 0;
     cudaError_t e = launch(&a, s.stream);
     if (e != cudaSuccess) return cuda_fail(e, "trf kernel launch");
+    if (cov_dev) PNB_CUDA(cudaEventRecord(s.kernel_done, s.stream));
     g_launches.fetch_add(1);
     if (staged) { s.pend_start = start; s.pend_n = n; }
     if (stage_out) {
@@ -513,12 +522,20 @@ int trf_host_range(const pnb_trf_problem *p, int device, int64_t chunk_vox, size
     if (p->r_squared)
       PNB_CUDA(cudaMemcpyAsync(p->r_squared + start, s.r2, D * n, cudaMemcpyDeviceToHost, s.stream));
   }
+  if (cov_dev && nfree >= 2) {
+    const size_t n_chunks = sizes.size();
+    for (int k = 0; k < Pipeline::kSlots && (size_t)k < n_chunks; k++)
+      PNB_CUDA(cudaStreamWaitEvent(P.cov_stream, P.slots[k].kernel_done, 0));
+    cudaError_t e = pnb::trf_cov_launch(nfree, (long long)(v1 - v0), nb, nullptr, cov_dev, P.cov_stream);
+    if (e != cudaSuccess) return cuda_fail(e, "covariance kernel launch");
+  }
   if (staged)
     for (int k = 0; k < Pipeline::kSlots; k++) {
       // drain in submission order so the copies overlap the chunks still running
       if (int rc = drain(P.slots[(slot + k) % Pipeline::kSlots])) return rc;
     }
   for (auto &s : P.slots) PNB_CUDA(cudaStreamSynchronize(s.stream));
+  if (cov_dev) PNB_CUDA(cudaStreamSynchronize(P.cov_stream));
   unsigned long long nf = 0;
   PNB_CUDA(cudaMemcpy(&nf, P.n_failed, sizeof(nf), cudaMemcpyDeviceToHost));
   g_last_failed.fetch_add((long long)nf);

@@ -43,6 +43,7 @@ struct TrfDeviceArgs {
   // outputs
   double *params;        // (NP, n_vox) parameter-major, like the reference's popt
   double *cov;           // (n_vox, n_free, n_free) or nullptr
+  int defer_cov = 0;     // host pipeline: leave the slots parked, one trf_cov_launch(status = nullptr) follows
   int *status;           // (n_vox) SciPy status, <0: input rejected
   int *nfev;             // (n_vox)
   int *njev;             // (n_vox) or nullptr
@@ -319,7 +320,9 @@ __global__ void __launch_bounds__(CovTile<NF>::TV) cov_kernel(long long n_vox, i
   double *base = cov + v0 * SL;
   for (int i = threadIdx.x; i < nv * SL; i += TV) tile[(i / SL) * LDS + (i % SL)] = base[i];
   __syncthreads();
-  const bool live = (int)threadIdx.x < nv && status[v0 + threadIdx.x] > 0;
+  // status == nullptr (one pass over a whole range after the fact): a failed voxel's slot is all NaN
+  const bool live = (int)threadIdx.x < nv &&
+                    (status ? status[v0 + threadIdx.x] > 0 : tile[threadIdx.x * LDS] == tile[threadIdx.x * LDS]);
   if (live) {
     double *cv = tile + threadIdx.x * LDS;
     double A[NF][NF], C[NF][NF], L[NF][NF], dinv[NF];
@@ -423,7 +426,7 @@ template <class M, int BLOCK, int METHOD = 0> cudaError_t trf_launch(const TrfDe
   if (err != cudaSuccess) return err;
   kern<<<(unsigned)grid, BLOCK, smem, stream>>>(a);
   err = cudaGetLastError();
-  if (err != cudaSuccess || !a.cov) return err;
+  if (err != cudaSuccess || !a.cov || a.defer_cov) return err;
   int n_free = 0;
   for (int i = 0; i < M::NP; i++) n_free += ((a.opt.frozen >> i) & 1u) ? 0 : 1;
   if (n_free < 2) return err;
