@@ -128,9 +128,11 @@ std::mutex g_copy_mu;  // one parallel copy at a time (the pool has one job slot
 
 void parallel_memcpy(void *dst, const void *src, size_t bytes) {
   static const unsigned hw = std::thread::hardware_concurrency();
-  // PNB_COPY_THREADS overrides the default of min(16, cores) host threads per staging copy
+  // PNB_COPY_THREADS overrides the default of half the cores (4 .. 12) per staging copy: on the 16-core
+  // boxes 8 threads already move 35 GB/s and leave cores to the thread that drives the pipeline
+  // (end to end from pageable memory: 198 Mvoxel/s with 8, 155 with 16; profiles/r2_pageable_probe.log)
   static const unsigned want = [] { const char *e = std::getenv("PNB_COPY_THREADS"); return e ? (unsigned)std::atoi(e) : 0u; }();
-  static const unsigned nt = want ? want : (hw > 16 ? 16 : (hw ? hw : 1));
+  static const unsigned nt = want ? want : (hw >= 24 ? 12 : (hw >= 8 ? hw / 2 : (hw ? hw : 1)));
   if (bytes < (4u << 20) || nt < 2) { std::memcpy(dst, src, bytes); return; }
   static CopyPool *pool = new CopyPool(nt - 1);  // lives for the process (workers sleep on a condition variable)
   const size_t part = ((bytes / nt) + 4095) & ~(size_t)4095;

@@ -11,7 +11,7 @@ void count_launch();
 // true for ordinary (pageable) host memory: cudaMemcpyAsync on it is staged by the driver at a
 // fraction of PCIe speed and blocks the host, so the host pipelines stage it themselves
 bool is_pageable(const void *ptr);
-// memcpy split over up to 16 host threads (one thread does ~10 GB/s, PCIe 5 x16 moves ~55 GB/s)
+// memcpy split over host threads (half the cores, at most 12) (one thread does ~10 GB/s, PCIe 5 x16 moves ~55 GB/s)
 void parallel_memcpy(void *dst, const void *src, size_t bytes);
 // Makes `device` current for the lifetime of the object and restores the caller's device afterwards
 // (the host entry points must not change the calling thread's current device).

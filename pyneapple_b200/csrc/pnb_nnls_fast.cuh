@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(WARPS * 32) nnls_fast_kernel(const NnlsDeviceA
       a.iters[vox] = iter;
       if (mode == kNnlsRedo) {
         const unsigned long long slot = atomicAdd(a.redo_count, 1ULL);
-        a.redo_list[slot] = (int)vox;
+        a.redo_list[slot] = (int)vox + a.redo_base;
       }
     }
     __syncwarp();

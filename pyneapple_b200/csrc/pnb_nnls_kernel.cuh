@@ -56,6 +56,7 @@ struct NnlsDeviceArgs {
   // the robust kernel (work_list != nullptr) processes exactly work_count[0] of them
   unsigned long long *redo_count;
   int *redo_list;
+  int redo_base = 0;     // added to the voxel index an entry records (host pipeline: chunk offset)
   const int *work_list;
   const unsigned long long *work_count;
   // a work-list launch only runs when work_count lies in [work_min, work_max] (lets the host

@@ -823,7 +823,7 @@ __global__ void __launch_bounds__(PNB_V3_MAXWARPS * 32, 1) nnls_v3_kernel(const 
       a.iters[vox] = iter;
       if (mode == kNnlsRedo) {
         const unsigned long long slot = atomicAdd(a.redo_count, 1ULL);
-        a.redo_list[slot] = (int)vox;
+        a.redo_list[slot] = (int)vox + a.redo_base;
       }
     }
     __syncwarp();

@@ -35,6 +35,15 @@
 #pragma once
 #include "pnb_models.cuh"
 
+// unroll factor of the row loop of the finite-difference evaluation (1 = rolled, the default:
+// profiles/r2_trf_experiments.md)
+#ifndef PNB_TRF_ROW_UNROLL
+#define PNB_TRF_ROW_UNROLL 1
+#endif
+#define PNB_PRAGMA_(x) _Pragma(#x)
+#define PNB_PRAGMA(x) PNB_PRAGMA_(x)
+#define PNB_TRF_ROW_PRAGMA PNB_PRAGMA(unroll PNB_TRF_ROW_UNROLL)
+
 namespace pnb {
 
 struct TrfOptions {
@@ -497,6 +506,7 @@ PNB_HD void trf_evaluate(const double (&xe)[M::NP], const TrfOptions &O, int m, 
       dx[k] = (O.jac_mode == 2) ? 1.0 / h : 1.0 / (xt[k] - xk);
       M::prepare(xt, O.tr, O.tm, pk[k]);
     }
+    PNB_TRF_ROW_PRAGMA
     for (int r = 0; r < m; r++) {
       double yv, bv;
       yb(r, yv, bv);

@@ -1,23 +1,23 @@
-"""NNLS host pipeline (pinned buffers) against the chunk size (dev tool)."""
-import sys, os, time
+"""NNLS end to end (page-locked arrays) against the device-resident kernel time (dev tool)."""
+import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
-from pyneapple_b200 import synth, models, _lib
+from pyneapple_b200 import _lib, models, synth, engine
 from pyneapple_b200.solvers import NNLSSolver
-cfg = synth.CONFIGS["C3"]
-b, img, _ = synth.make_volume(cfg, 0, 64)
-y = img.reshape(-1, 16)
-pin = _lib.pinned_empty(y.shape); pin[...] = y
+
+base = synth.CONFIGS["C3"]
+b, img, _ = synth.make_volume(base)
+y = _lib.pinned_empty((img.shape[0] * img.shape[1] * img.shape[2], 16)); y[...] = img.reshape(y.shape); del img
 model = models.NNLSModel(d_range=(0.0008, 0.5), n_bins=250)
-for chunk in (0, 1 << 16, 1 << 17, 1 << 18, 1 << 19, 1 << 20):
+yd = torch.as_tensor(y).cuda()
+s = NNLSSolver(model=model, reg_order=2, mu=0.02, max_iter=250, pinned_outputs=True)
+s.fit(b, yd[:1 << 20]); torch.cuda.synchronize()
+t0 = time.perf_counter(); s.fit(b, yd); torch.cuda.synchronize(); t1 = time.perf_counter()
+print(f"device-resident fit + download: {1e3*(t1-t0):7.1f} ms", flush=True)
+for chunk in (int(c) for c in os.environ.get("CHUNKS", "262144").split(",")):
     s = NNLSSolver(model=model, reg_order=2, mu=0.02, max_iter=250, pinned_outputs=True, chunk_vox=chunk)
-    s.fit(b, pin)
-    t = time.perf_counter(); s.fit(b, pin); dt = time.perf_counter() - t
-    print(f"chunk {chunk}: {dt*1e3:.1f} ms -> {y.shape[0]/dt/1e6:.2f} Mvox/s", flush=True)
-    del s
-s = NNLSSolver(model=model, reg_order=2, mu=0.02, max_iter=250)
-cut = [(0.0008, 0.003), (0.003, 0.05), (0.05, 0.5)]
-t = time.perf_counter(); s.fit_spectrum_peaks(b, pin, cutoffs=cut); print(f'first call (page-locks the result arrays): {(time.perf_counter()-t)*1e3:.1f} ms')
-t = time.perf_counter(); r = s.fit_spectrum_peaks(b, pin, cutoffs=cut); dt = time.perf_counter() - t
-print(f"fit_spectrum_peaks (spectra stay on the device): {dt*1e3:.1f} ms -> {y.shape[0]/dt/1e6:.2f} Mvox/s; mean peaks {r['n_peaks'].mean():.2f}")
-from pyneapple_b200 import spectrum
+    s.fit(b, y); s.fit(b, y)
+    t0 = time.perf_counter()
+    s.fit(b, y)
+    dt = time.perf_counter() - t0
+    print(f"NNLS chunk {chunk:8d}: {dt*1e3:7.1f} ms  {y.shape[0]/dt/1e6:7.2f} Mvox/s  redo {_lib.load().pnb_nnls_last_redo_count(0)}", flush=True)

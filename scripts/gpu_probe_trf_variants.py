@@ -10,16 +10,18 @@ b, img, _ = synth.make_volume(cfg, 0, int(sys.argv[2]))
 y = torch.as_tensor(img.reshape(-1, 16)).cuda()
 desc = models.describe_model(models.BiExpModel(fit_s0=True)); names = list(desc.all_names)
 p0 = np.array([cfg.p0[n] for n in names]); lb = np.array([cfg.bounds[n][0] for n in names]); ub = np.array([cfg.bounds[n][1] for n in names])
-for jm in (1, 0):
+for jm in (1, 0, 1):
     f = lambda: engine.trf_fit(desc, b, y, p0, lb, ub, 0, jac_mode=jm, want_cov="eager")
-    r = f(); torch.cuda.synchronize()
+    for _ in range(5):
+        r = f()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(5):
+    for _ in range(20):
         r = f()
     e1.record(); torch.cuda.synchronize()
     digest = hashlib.sha1(r["params"].cpu().numpy().tobytes()).hexdigest()[:12]
-    print(sys.argv[1], "jac", jm, "ms", round(e0.elapsed_time(e1) / 5, 3), "nfev", round(float(r["nfev"].double().mean()), 3), "digest", digest, flush=True)
+    print(sys.argv[1], "jac", jm, "ms", round(e0.elapsed_time(e1) / 20, 3), "nfev", round(float(r["nfev"].double().mean()), 3), "digest", digest, flush=True)
 '''
 slices = sys.argv[1] if len(sys.argv) > 1 else "64"
 libs = sorted(glob.glob(os.path.join(ROOT, "pyneapple_b200", "csrc", "libpnb200_*.so")))

@@ -162,6 +162,30 @@ def test_chunked_host_pipeline_equals_single_launch():
     assert np.array_equal(one.iterations_, many.iterations_)
 
 
+def test_host_pipeline_hands_over_once_per_call():
+    """The host pipeline collects the voxels its chunks' fast kernels cannot certify in ONE list and
+    re-solves them after the last chunk from a compact copy of their signals: same bits as the device
+    path (hand-over inside the launch), for pageable and page-locked arrays, over ragged chunks."""
+    import torch
+
+    from pyneapple_b200 import _lib, synth
+
+    b, y, _ = synth.sample_voxels(synth.CONFIGS["C3"], 6000, z=5)
+    model = models.NNLSModel(d_range=(0.0008, 0.5), n_bins=250)
+    kw = dict(model=model, reg_order=2, mu=1e-3, max_iter=750)   # weak regularisation: many hand-overs
+    dev = NNLSSolver(**kw).fit(b, torch.as_tensor(y).cuda())
+    ref_coef, ref_it, ref_res = dev.params_["coefficients"].copy(), dev.iterations_.copy(), dev.diagnostics_["residual"].copy()
+    ypin = _lib.pinned_empty(y.shape); ypin[...] = y
+    for sig, pinned in ((y, False), (ypin, True)):
+        s = NNLSSolver(chunk_vox=701, pinned_outputs=pinned, **kw).fit(b, sig)
+        n_redo = _lib.load().pnb_nnls_last_redo_count(0)
+        assert 0 < n_redo < 6000
+        assert np.array_equal(s.params_["coefficients"], ref_coef)
+        assert np.array_equal(s.iterations_, ref_it) and np.array_equal(s.status_, dev.status_)
+        assert np.array_equal(s.diagnostics_["residual"], ref_res)
+        assert np.array_equal(s.r_squared_, dev.r_squared_, equal_nan=True)
+
+
 def test_single_voxel_and_device_path():
     import torch
 
