@@ -76,8 +76,8 @@ __device__ __noinline__ double pnb_exp_out_of_range(double x) { return exp(x); }
 inline double pnb_exp_out_of_range(double x) { return exp(x); }
 #endif
 
-PNB_HD double pnb_exp(double x) {
-  if (__builtin_expect(!(fabs(x) < 690.0), 0)) return pnb_exp_out_of_range(x);
+// the table path alone: valid for |x| < 690, garbage (no trap) outside
+PNB_HD double pnb_exp_core(double x) {
   const double kShift = 6755399441055744.0;  // 1.5 * 2^52: the integer lands in the low mantissa bits
   const double t = fma(x, 92.33248261689366, kShift);
   const double nf = t - kShift;
@@ -104,6 +104,11 @@ PNB_HD double pnb_exp(double x) {
   __builtin_memcpy(&out, &bits, 8);
   return out;
 #endif
+}
+
+PNB_HD double pnb_exp(double x) {
+  if (__builtin_expect(!(fabs(x) < 690.0), 0)) return pnb_exp_out_of_range(x);
+  return pnb_exp_core(x);
 }
 
 // pnb_exp as a real call, for cold paths that must not be inlined into (and if-converted with) a hot one

@@ -114,9 +114,30 @@ template <int ID, int T1MODE> struct Model {
     }
   }
 
+  // The K exponentials of a row are independent ~10-deep FP64 chains.  With the range check inside
+  // each of them every chain sits in its own branch region and the compiler cannot interleave them;
+  // here the table path runs unconditionally for all K, ONE test covers the row, and the rare row
+  // with an argument outside [-690, 690] is redone by the full pnb_exp as a call (same bits for the
+  // in-range arguments: it is the same code).
   PNB_HD static void exps(const Point &pt, double b, double (&e)[K]) {
+#if defined(PNB_EXP_PER_ELEMENT_CHECK)
 #pragma unroll
     for (int k = 0; k < K; k++) e[k] = pnb_exp(b * pt.nd[k]);
+#else
+    double x[K];
+    bool in_range = true;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      x[k] = b * pt.nd[k];
+      in_range = in_range && (fabs(x[k]) < 690.0);
+    }
+#pragma unroll
+    for (int k = 0; k < K; k++) e[k] = pnb_exp_core(x[k]);
+    if (__builtin_expect(!in_range, 0)) {
+#pragma unroll
+      for (int k = 0; k < K; k++) e[k] = pnb_exp_cold(x[k]);
+    }
+#endif
   }
   PNB_HD static double combine(const Point &pt, const double (&e)[K]) {
     double shape = 0.0;
@@ -132,25 +153,34 @@ template <int ID, int T1MODE> struct Model {
     exps(pt, b, e);
     return combine(pt, e);
   }
-  // signal at the point `pk` that differs from the point `p0` (exponentials `e0`) only in
-  // parameter j: only a changed D_k needs a new exponential, and for the ~1e-8 steps of the
-  // finite-difference Jacobian that one is e0 * exp(b * (nd' - nd)) with a 4-term series
-  // (|b dnd| < 1e-4: truncation < 5e-18 relative) instead of a second full exp()
-  template <int DUMMY>
-  PNB_HD static double value_perturbed(const Point &pk, const Point &p0, double b,
-                                       const double (&e0)[K], int j) {
-    double e[K];
+  // Finite-difference Jacobian: the point pk[j] differs from p0 (exponentials e0) only in parameter
+  // j, and only a changed D_k needs a new exponential.  For the ~1e-8 steps of the 2-point scheme
+  // that one is e0 * exp(b * (nd' - nd)) with a 4-term series (|b dnd| < 1e-4: truncation < 5e-18
+  // relative) instead of a second full exp().  As in exps(): the series of all K components run
+  // unconditionally, ONE test covers the row, the rare large step is redone as a call.
+  template <class PK>
+  PNB_HD static void perturbed_exps(const PK &pk, const Point &p0, double b, const double (&e0)[K],
+                                    double (&ep)[K]) {
+    double t[K];
+    bool small = true;
 #pragma unroll
     for (int k = 0; k < K; k++) {
-      e[k] = e0[k];
-      if (L::d(k) == j) {
-        const double t = b * (pk.nd[k] - p0.nd[k]);
-        // the second alternative is a call (never taken for finite-difference steps), so the compiler
-        // cannot turn the choice into "compute both, select one"
-        e[k] = (fabs(t) < 1e-4) ? e0[k] + e0[k] * (t * (1.0 + t * (0.5 + t * (1.0 / 6.0))))
-                                : pnb_exp_cold(b * pk.nd[k]);
-      }
+      t[k] = b * (pk[L::d(k)].nd[k] - p0.nd[k]);
+      small = small && (fabs(t[k]) < 1e-4);
     }
+#pragma unroll
+    for (int k = 0; k < K; k++) ep[k] = e0[k] + e0[k] * (t[k] * (1.0 + t[k] * (0.5 + t[k] * (1.0 / 6.0))));
+    if (__builtin_expect(!small, 0)) {
+#pragma unroll
+      for (int k = 0; k < K; k++)
+        if (!(fabs(t[k]) < 1e-4)) ep[k] = pnb_exp_cold(b * pk[L::d(k)].nd[k]);
+    }
+  }
+  // signal at pk = pk[j] from the exponentials of p0 (e0) and the perturbed ones (ep)
+  PNB_HD static double value_perturbed(const Point &pk, const double (&e0)[K], const double (&ep)[K], int j) {
+    double e[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) e[k] = (L::d(k) == j) ? ep[k] : e0[k];
     return combine(pk, e);
   }
 
@@ -158,11 +188,9 @@ template <int ID, int T1MODE> struct Model {
   PNB_HD static double value_grad(const Point &pt, double b, double (&grad)[NP]) {
     double e[K];
     double shape = 0.0;
+    exps(pt, b, e);
 #pragma unroll
-    for (int k = 0; k < K; k++) {
-      e[k] = pnb_exp(b * pt.nd[k]);
-      shape = (k == 0) ? pt.w[k] * e[k] : shape + pt.w[k] * e[k];
-    }
+    for (int k = 0; k < K; k++) shape = (k == 0) ? pt.w[k] * e[k] : shape + pt.w[k] * e[k];
 #pragma unroll
     for (int k = 0; k < K; k++) {
       grad[L::d(k)] = (L::AMP >= 0) ? -b * pt.amp * pt.w[k] * e[k] : -b * pt.w[k] * e[k];
