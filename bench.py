@@ -38,6 +38,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -688,7 +689,21 @@ def main():
     sampler = ClockSampler(0, world)
     if rank == 0:
         sampler.start()
+    wev0, wev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wev0.record()
     r = run_steps(max(1, args.warmup))
+    wev1.record()
+    torch.cuda.synchronize()
+    # A step is ~8 ms: W = 3 warm-up steps end before a GPU that idled while the host built the volume has
+    # left its idle clocks (measured on one box: 21 ms per step in the timed region against 7.7 ms for the
+    # same launches a moment later, nvidia-smi's median still 1965 MHz).  Warm up for at least half a
+    # second of device time; every rank derives the same number of extra steps from the slowest rank.
+    warm_ms = D.max(wev0.elapsed_time(wev1), dev)
+    extra_warmup = 0
+    if warm_ms < 500.0:
+        per_step = max(warm_ms / max(1, args.warmup), 1e-3)
+        extra_warmup = min(200, int(math.ceil((500.0 - warm_ms) / per_step)))
+        r = run_steps(extra_warmup)
     D.barrier()
     launches0 = _lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -868,7 +883,9 @@ def main():
                                 "the parameter fields); parameter maps gathered to rank 0 (NCCL) in the timed region on "
                                 + ("the launching stream behind each step's kernel" if serial_gather else
                                    "a high-priority side stream, overlapping the next step's kernel"),
-                   "success_rate": success, "mean_nfev": nfev_sum / n_vox},
+                   "success_rate": success, "mean_nfev": nfev_sum / n_vox,
+                   "warmup_steps_run": int(max(1, args.warmup) + extra_warmup),
+                   "warmup_note": "W steps plus as many as it takes to reach 0.5 s of device time (idle-clock ramp)"},
         "clocks": clocks,
         "e2e": {"value": n_vox * world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h_lazy), "steps": e2e_steps,

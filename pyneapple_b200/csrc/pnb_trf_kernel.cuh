@@ -61,6 +61,19 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 constexpr int kTrfClaim = 64;  // voxel indices claimed per warp-level atomicAdd
+// Batched write-out of converged lanes (see `pending` in trf_kernel).  A finished lane waits at most
+// PNB_TRF_FINISH_WAIT passes; the gate also opens when PNB_TRF_FINISH_BATCH lanes are ready (32 = never
+// by count: measured, a count trigger below 32 splits a warp into groups that drift apart and pay the
+// start / finish code separately - profiles/r2_trf_finish_batch.log) or nothing else runs.
+// BATCH 1 + WAIT 0 = every lane writes at once (the old behaviour).
+#ifndef PNB_TRF_FINISH_BATCH
+#define PNB_TRF_FINISH_BATCH 32
+#endif
+#ifndef PNB_TRF_FINISH_WAIT
+#define PNB_TRF_FINISH_WAIT 3
+#endif
+constexpr int kTrfFinishBatch = PNB_TRF_FINISH_BATCH;
+constexpr int kTrfFinishWait = PNB_TRF_FINISH_WAIT;
 
 #ifndef PNB_TRF_MINBLOCKS
 #define PNB_TRF_MINBLOCKS 1
@@ -122,6 +135,15 @@ __global__ void __launch_bounds__(BLOCK, PNB_TRF_MINBLOCKS) trf_kernel(const Trf
   long long cur = -1, nxt = -1;
   int buf = 0, nxt_buf = 0;  // which half of the double buffers holds `cur` / receives `nxt`
   bool first_eval = false;
+  // A lane whose voxel has converged does not write its results at once: the once-per-voxel code
+  // (result stores, R^2, and on the next pass the preamble of the lane's next voxel) ran with the
+  // ~4 lanes of 32 that happened to finish in a pass and took ~30 % of the kernel's warp samples
+  // (profiles/r2_trf_hotspots.txt).  Finished lanes wait until one of them has waited kTrfFinishWait
+  // passes (or nothing else is running) and go through that code together; they also start their
+  // next voxels together, and voxels that start together mostly finish within a pass or two of each
+  // other, so a warp settles into near-synchronous batches with a bounded wait for stragglers.
+  bool pending = false;
+  int waited = 0;
 
   for (;;) {
     // ---- claim + prefetch the voxel after the current one ----------------
@@ -197,7 +219,7 @@ __global__ void __launch_bounds__(BLOCK, PNB_TRF_MINBLOCKS) trf_kernel(const Trf
       } else {
         finished = true;
       }
-    } else if (cur >= 0) {
+    } else if (cur >= 0 && !pending) {
       // ---- prepare a trial step -------------------------------------------------
       bool go = true;
       if (S.need_prologue) {
@@ -239,7 +261,15 @@ __global__ void __launch_bounds__(BLOCK, PNB_TRF_MINBLOCKS) trf_kernel(const Trf
     }
     __syncwarp();
     // ---- write results ------------------------------------------------------------
-    if (finished) {
+    if (pending) waited++;
+    pending = pending || finished;
+    const unsigned pend_mask = __ballot_sync(FULL, pending);
+    const bool running_any = __any_sync(FULL, cur >= 0 && !pending);
+    const bool overdue = __any_sync(FULL, pending && waited >= kTrfFinishWait);
+    const bool open = __popc(pend_mask) >= kTrfFinishBatch || overdue || !running_any;
+    if (pending && open) {
+      pending = false;
+      waited = 0;
       const long long vox = cur;
       const bool ok = S.status > 0;
       int n_free = 0;

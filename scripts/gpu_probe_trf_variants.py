@@ -10,6 +10,11 @@ b, img, _ = synth.make_volume(cfg, 0, int(sys.argv[2]))
 y = torch.as_tensor(img.reshape(-1, 16)).cuda()
 desc = models.describe_model(models.BiExpModel(fit_s0=True)); names = list(desc.all_names)
 p0 = np.array([cfg.p0[n] for n in names]); lb = np.array([cfg.bounds[n][0] for n in names]); ub = np.array([cfg.bounds[n][1] for n in names])
+import os
+if os.environ.get("HET") == "1":
+    # heterogeneous difficulty: every other voxel gets heavy noise (its fit takes more, and more varied, evaluations)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    y[1::2] += 0.08 * y.max() * torch.randn(y[1::2].shape, generator=g, device="cuda", dtype=torch.float64)
 for jm in (1, 0, 1):
     f = lambda: engine.trf_fit(desc, b, y, p0, lb, ub, 0, jac_mode=jm, want_cov="eager")
     for _ in range(5):
