@@ -689,21 +689,20 @@ def main():
     sampler = ClockSampler(0, world)
     if rank == 0:
         sampler.start()
-    wev0, wev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    wev0.record()
     r = run_steps(max(1, args.warmup))
-    wev1.record()
-    torch.cuda.synchronize()
     # A step is ~8 ms: W = 3 warm-up steps end before a GPU that idled while the host built the volume has
     # left its idle clocks (measured on one box: 21 ms per step in the timed region against 7.7 ms for the
-    # same launches a moment later, nvidia-smi's median still 1965 MHz).  Warm up for at least half a
-    # second of device time; every rank derives the same number of extra steps from the slowest rank.
-    warm_ms = D.max(wev0.elapsed_time(wev1), dev)
-    extra_warmup = 0
-    if warm_ms < 500.0:
-        per_step = max(warm_ms / max(1, args.warmup), 1e-3)
-        extra_warmup = min(200, int(math.ceil((500.0 - warm_ms) / per_step)))
-        r = run_steps(extra_warmup)
+    # same launches a moment later, nvidia-smi's median still 1965 MHz).  Keep warming up for about
+    # 0.4 s of device time; every rank derives the same number of extra steps from the slowest rank.
+    wev0, wev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    wev0.record()
+    r = run_steps(2)
+    wev1.record()
+    torch.cuda.synchronize()
+    per_step = max(D.max(wev0.elapsed_time(wev1), dev) / 2.0, 1e-3)
+    extra_warmup = 2 + min(200, int(math.ceil(400.0 / per_step)))
+    r = run_steps(extra_warmup - 2)
     D.barrier()
     launches0 = _lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
