@@ -26,6 +26,9 @@ if what == "trf":
     lb = np.array([cfg.bounds[n][0] for n in names])
     ub = np.array([cfg.bounds[n][1] for n in names])
     jm = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+    if len(sys.argv) > 4 and sys.argv[4] == "noisy":  # heavy noise on every voxel: widely spread difficulty
+        g = torch.Generator(device="cuda").manual_seed(7)
+        y = y + 0.08 * y.max() * torch.randn(y.shape, generator=g, device="cuda", dtype=torch.float64)
     for _ in range(3):
         r = engine.trf_fit(desc, b, y, p0, lb, ub, 0, jac_mode=jm, want_cov="eager")
     torch.cuda.synchronize()
