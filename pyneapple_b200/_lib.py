@@ -340,7 +340,10 @@ def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
     block = _PinnedBlock(nbytes)
     buf = (C.c_char * nbytes).from_address(block.ptr.value)
     buf._pnb_block = block  # the ctypes buffer is the ndarray's base and keeps the block alive
-    return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+    # np.ndarray(buffer=...) and not np.frombuffer(...).reshape(...): views of the latter reference the
+    # hidden 1-D frombuffer array, not the array returned here, and the solvers decide from the returned
+    # array's reference count whether a caller still holds (a view of) the previous fit's results
+    return np.ndarray(shape=shape, dtype=dtype, buffer=buf)
 
 
 def measure_fp64_peak(device: int = 0) -> float:

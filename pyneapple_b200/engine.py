@@ -560,6 +560,21 @@ def to_host(tensor) -> np.ndarray:
     return out
 
 
+def to_host_into(tensor, out: np.ndarray) -> None:
+    """CUDA tensor -> an existing C-contiguous numpy array (or contiguous slice of one) of the same shape and
+    item size, through ``pnb_download`` on the current stream of the tensor's device."""
+    import torch
+
+    t = tensor.contiguous()
+    if not out.flags["C_CONTIGUOUS"] or tuple(out.shape) != tuple(t.shape) or out.itemsize != t.element_size():
+        raise ValueError("to_host_into needs a C-contiguous destination of the tensor's shape and item size")
+    if out.nbytes == 0:
+        return
+    with torch.cuda.device(t.device):
+        stream = torch.cuda.current_stream(t.device).cuda_stream
+        _lib.check(_lib.load().pnb_download(out.ctypes.data, t.data_ptr(), out.nbytes, C.c_void_p(stream)), "pnb_download")
+
+
 def to_device(array, device):
     """numpy array -> CUDA tensor through ``pnb_upload`` (staged like :func:`to_host`)."""
     import torch

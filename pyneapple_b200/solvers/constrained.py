@@ -107,6 +107,28 @@ class ConstrainedCurveFitSolver(CurveFitSolver):
                 return arr
             return arr[:, a:z]
 
+        # page-locked result arrays from the second fit of a shape on (CurveFitSolver._pinned_out): every GPU
+        # downloads straight into its columns; a fresh numpy array per result costs its first-touch page faults
+        n_all = len(self._desc.all_names)
+        n_free_est = n_all - len(set(self._desc.fixed) | (set(pixel_fixed_params or {}) & set(self._desc.all_names)))
+        pinned = None if on_device else self._pinned_out(n_all, n_free_est, n_pixels, ydata)
+
+        not_pinned = set()   # result keys whose shape did not match the cached block (copied the plain way)
+
+        def download(key, v, a, z):
+            if pinned is None or key not in pinned:
+                return engine.to_host(v)
+            dst = pinned[key]
+            if key == "params" and v.ndim == 2 and dst.shape[0] == v.shape[0] and v.shape[1] == z - a:
+                for r in range(v.shape[0]):          # (n_all, n): row by row into the columns a..z
+                    engine.to_host_into(v[r], dst[r, a:z])
+                return dst[:, a:z]
+            if key != "params" and tuple(dst[a:z].shape) == tuple(v.shape) and dst.itemsize == v.element_size():
+                engine.to_host_into(v, dst[a:z])
+                return dst[a:z]
+            not_pinned.add(key)
+            return engine.to_host(v)
+
         def run(k):
             (a, z), d = ranges[k], devices[k]
             if z <= a:
@@ -123,7 +145,7 @@ class ConstrainedCurveFitSolver(CurveFitSolver):
                                       bounds=(up(part(lb_m, a, z)), up(part(ub_m, a, z))), pixel_fixed_params=pf)
                 n_failed = int((res["status"] <= 0).sum().item())
                 lazy_cov = res.pop("cov") if (self.want_cov is True or self.want_cov == "lazy") else None
-                host = {k_: (engine.to_host(v) if hasattr(v, "cpu") else v) for k_, v in res.items()}
+                host = {k_: (download(k_, v, a, z) if hasattr(v, "cpu") else v) for k_, v in res.items()}
                 host["cov_dev"] = lazy_cov
                 host["n_failed"] = n_failed
                 return host
@@ -138,14 +160,18 @@ class ConstrainedCurveFitSolver(CurveFitSolver):
         res = {"free_names": first["free_names"], "free_rows": first["free_rows"]}
         for key in ("params", "status", "nfev", "njev", "cost", "r2"):
             vals = [p[key] for _, p in live]
-            res[key] = vals[0] if len(vals) == 1 else np.concatenate(vals, axis=-1)
+            if pinned is not None and key in pinned and key not in not_pinned:
+                res[key] = pinned[key]          # the parts are views of it
+            else:
+                res[key] = vals[0] if len(vals) == 1 else np.concatenate(vals, axis=-1)
         n_free = len(first["free_rows"])
         if first["cov_dev"] is not None:
             from .._lazy import LazyArray
 
             res["cov"] = LazyArray((n_pixels, n_free, n_free), [(a, z, p["cov_dev"]) for (a, z), p in live])
         elif first.get("cov") is not None:
-            res["cov"] = np.concatenate([p["cov"] for _, p in live], axis=0)
+            res["cov"] = (pinned["cov"] if pinned is not None and "cov" in pinned and "cov" not in not_pinned
+                          else np.concatenate([p["cov"] for _, p in live], axis=0))
         else:
             res["cov"] = None
         res["n_failed"] = int(sum(p["n_failed"] for _, p in live))

@@ -135,6 +135,33 @@ def test_device_resident_call_equals_the_host_call_and_uses_no_host_arrays():
         assert np.array_equal(arr.params_[n_], host.params_[n_])
 
 
+def test_page_locked_results_from_the_second_fit_on():
+    """`pinned_outputs="auto"`: the first fit of a shape downloads into fresh numpy arrays, later ones into the
+    solver's page-locked block — same values, and arrays a caller still holds are never overwritten."""
+    from pyneapple_b200 import synth
+
+    cfg = synth.CONFIGS["C5"]
+    b, img, _ = synth.make_volume(cfg, 0, 1)
+    y = np.ascontiguousarray(img.reshape(-1, img.shape[3]))
+    assert y.shape[0] >= 65536
+    s = ConstrainedCurveFitSolver(model=models.TriExpModel(), max_iter=250, tol=1e-8, p0=cfg.p0, bounds=cfg.bounds,
+                                  fraction_constraint=True)
+    s.fit(b, y)
+    first = {n: s.params_[n].copy() for n in NAMES}
+    nfev = s.nfev_.copy()
+    assert s._out_cache is None                    # fresh numpy arrays
+    s.fit(b, y)                                    # second fit of the shape: the page-locked block
+    held = s.params_["D1"]
+    assert np.shares_memory(held, s._out_cache[1]["params"])
+    for n in NAMES:
+        assert np.array_equal(s.params_[n], first[n]), n
+    assert np.array_equal(s.nfev_, nfev)
+    y2 = y * 1.01
+    s.fit(b, y2)                                   # `held` is still referenced: this fit must not touch it
+    assert np.array_equal(held, first["D1"])
+    assert not np.shares_memory(s.params_["D1"], held)
+
+
 def test_constructor_contract():
     with pytest.raises(ValueError):
         ConstrainedCurveFitSolver(model=models.TriExpModel(fit_reduced=False), max_iter=10, tol=1e-8,

@@ -186,6 +186,22 @@ def test_host_pipeline_hands_over_once_per_call():
         assert np.array_equal(s.r_squared_, dev.r_squared_, equal_nan=True)
 
 
+def test_page_locked_spectra_are_never_overwritten_while_a_caller_holds_them():
+    from pyneapple_b200 import synth
+
+    b, y, _ = synth.sample_voxels(synth.CONFIGS["C3"], 16384, z=9)
+    model = models.NNLSModel(d_range=(0.0008, 0.5), n_bins=250)
+    s = NNLSSolver(model=model, reg_order=2, mu=0.02, max_iter=250)
+    first = s.fit(b, y).params_["coefficients"].copy()
+    s.fit(b, y)                                   # second fit of the shape: the page-locked block
+    block = s._out_cache[1]["coefficients"]
+    held = s.params_["coefficients"][:100]        # a view
+    assert np.shares_memory(held, block)
+    s.fit(b, 2.0 * y)
+    assert np.array_equal(held, first[:100]) and not np.shares_memory(s.params_["coefficients"], block)
+    assert np.allclose(s.params_["coefficients"], 2.0 * first, rtol=1e-9, atol=1e-9)
+
+
 def test_single_voxel_and_device_path():
     import torch
 

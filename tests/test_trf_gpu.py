@@ -242,3 +242,29 @@ def test_device_pointer_path_matches_host_path():
     solver.fit(P["b"], torch.as_tensor(P["y"]).cuda())
     dev = np.stack([solver.params_[n] for n in P["free_names"]], axis=1)
     assert np.array_equal(host, dev)
+
+
+def test_page_locked_results_are_never_overwritten_while_a_caller_holds_them():
+    """`pinned_outputs="auto"`: from the second fit of a shape on the results live in the solver's
+    page-locked block.  A caller that still holds an array of the previous fit — or a VIEW of one, like
+    `solver.params_["D1"]` — must keep its values: the next fit takes a fresh block."""
+    from pyneapple_b200 import _lib, synth
+
+    a = _lib.pinned_empty((4, 10))
+    assert a[1].base is a and a[:, 2:5].base is a      # views reference the array the solver counts on
+    cfg = synth.CONFIGS["C2"]
+    b, y, _ = synth.sample_voxels(cfg, 65536, z=3)
+    s = CurveFitSolver(model=models.BiExpModel(fit_s0=True), max_iter=250, tol=1e-8, p0=cfg.p0, bounds=cfg.bounds)
+    s.fit(b, y)
+    first = s.params_["D1"].copy()
+    s.fit(b, y)                                  # page-locked block from here on
+    block = s._out_cache[1]["params"]
+    held = s.params_["D1"]                       # a view of the block's parameter array
+    assert np.shares_memory(held, block) and np.array_equal(held, first)
+    s.fit(b, y * 1.5)                            # S0 scales with the signal; `held` is still referenced
+    assert np.array_equal(held, first)
+    assert not np.shares_memory(s.params_["S0"], block)
+    del held
+    s.fit(b, y)                                  # nobody holds the previous arrays: the block is reused
+    s.fit(b, y)
+    assert np.array_equal(s.params_["D1"], first)
