@@ -574,10 +574,12 @@ def bench_c5(args, D, dev, cpu):
         hy = _lib.pinned_empty((himg.shape[0] * himg.shape[1] * zs, hb.shape[0]))
         hy[...] = himg.reshape(hy.shape)
         del himg
-        t = _time_host(lambda: solver.fit(hb, hy), 1, D, dev)
+        solver.fit(hb, hy)  # first fit of the shape (pinned_outputs="auto": the page-locked result block is set up by the second)
+        t = _time_host(lambda: solver.fit(hb, hy), 2, D, dev)
         e2e = {"value": hy.shape[0] / t, "unit": UNIT, "voxels": int(hy.shape[0]),
                "h2d_bytes_per_step": int(hy.nbytes), "d2h_bytes_per_step": int(hy.shape[0] * (5 * 8 + 4 * 3 + 8 * 2)),
-               "api": "ConstrainedCurveFitSolver.fit(page-locked numpy): upload, both phases on the GPU, download"}
+               "api": "ConstrainedCurveFitSolver.fit(page-locked numpy): upload, both phases on the GPU, download into the "
+                      "solver's page-locked result block (third and fourth fit of the shape)"}
         del hy
     if rank != 0:
         return None
