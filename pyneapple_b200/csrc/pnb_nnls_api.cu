@@ -409,37 +409,36 @@ int nnls_host_range(const pnb_nnls_problem *p, int device, int64_t chunk_vox, si
   const size_t R = (size_t)n_redo;
   std::vector<int> idx(R);
   PNBI_CUDA(cudaMemcpy(idx.data(), C.defer_list, R * I, cudaMemcpyDeviceToHost));
-  std::vector<double> ybuf(R * m), cbuf(R * n), rnbuf(R), r2buf(p->r_squared ? R : 0);
-  std::vector<int> stbuf(R), itbuf(R);
-  for (size_t q = 0; q < R; q++)
-    std::memcpy(&ybuf[q * m], p->signal + (v0 + (size_t)idx[q]) * m, m * D);
-  // slot 0's buffers are free again; they hold a chunk, the list can be longer than that
-  if (int rc = grow(&C.y[0], &C.cap_y[0], R * m)) return rc;
-  if (int rc = grow(&C.coef[0], &C.cap_coef[0], R * n)) return rc;
-  if (int rc = grow(&C.rn[0], &C.cap_rn[0], R)) return rc;
-  if (int rc = grow(&C.r2[0], &C.cap_r2[0], R)) return rc;
-  if (int rc = grow(&C.st[0], &C.cap_st[0], R)) return rc;
-  if (int rc = grow(&C.it[0], &C.cap_it[0], R)) return rc;
+  // in batches of at most one chunk: slot 0's buffers are free again and hold exactly that (a weakly
+  // regularised problem can hand over most of its voxels)
+  const size_t batch = R < Cn ? R : Cn;
+  std::vector<double> ybuf(batch * m), cbuf(batch * n), rnbuf(batch), r2buf(p->r_squared ? batch : 0);
+  std::vector<int> stbuf(batch), itbuf(batch);
   cudaStream_t st0 = C.streams[0];
-  PNBI_CUDA(cudaMemcpyAsync(C.y[0], ybuf.data(), R * m * D, cudaMemcpyHostToDevice, st0));
-  if (int rc = launch(C, p, C.B, C.rtr, C.y[0], (long long)R, C.coef[0], C.rn[0], C.st[0], C.it[0],
-                      p->r_squared ? C.r2[0] : nullptr, st0, 0, nullptr, 2))
-    return rc;
-  C.last_redo = C.defer_count;  // what pnb_nnls_last_redo_count reports for this call
-  PNBI_CUDA(cudaMemcpyAsync(cbuf.data(), C.coef[0], R * n * D, cudaMemcpyDeviceToHost, st0));
-  PNBI_CUDA(cudaMemcpyAsync(rnbuf.data(), C.rn[0], R * D, cudaMemcpyDeviceToHost, st0));
-  if (p->r_squared) PNBI_CUDA(cudaMemcpyAsync(r2buf.data(), C.r2[0], R * D, cudaMemcpyDeviceToHost, st0));
-  PNBI_CUDA(cudaMemcpyAsync(stbuf.data(), C.st[0], R * I, cudaMemcpyDeviceToHost, st0));
-  PNBI_CUDA(cudaMemcpyAsync(itbuf.data(), C.it[0], R * I, cudaMemcpyDeviceToHost, st0));
-  PNBI_CUDA(cudaStreamSynchronize(st0));
-  for (size_t q = 0; q < R; q++) {
-    const size_t v = v0 + (size_t)idx[q];
-    std::memcpy(p->coefficients + v * n, &cbuf[q * n], n * D);
-    p->residual[v] = rnbuf[q];
-    if (p->r_squared) p->r_squared[v] = r2buf[q];
-    p->status[v] = stbuf[q];
-    p->iterations[v] = itbuf[q];
+  for (size_t q0 = 0; q0 < R; q0 += batch) {
+    const size_t nb = (R - q0 < batch) ? R - q0 : batch;
+    for (size_t q = 0; q < nb; q++)
+      std::memcpy(&ybuf[q * m], p->signal + (v0 + (size_t)idx[q0 + q]) * m, m * D);
+    PNBI_CUDA(cudaMemcpyAsync(C.y[0], ybuf.data(), nb * m * D, cudaMemcpyHostToDevice, st0));
+    if (int rc = launch(C, p, C.B, C.rtr, C.y[0], (long long)nb, C.coef[0], C.rn[0], C.st[0], C.it[0],
+                        p->r_squared ? C.r2[0] : nullptr, st0, 0, nullptr, 2))
+      return rc;
+    PNBI_CUDA(cudaMemcpyAsync(cbuf.data(), C.coef[0], nb * n * D, cudaMemcpyDeviceToHost, st0));
+    PNBI_CUDA(cudaMemcpyAsync(rnbuf.data(), C.rn[0], nb * D, cudaMemcpyDeviceToHost, st0));
+    if (p->r_squared) PNBI_CUDA(cudaMemcpyAsync(r2buf.data(), C.r2[0], nb * D, cudaMemcpyDeviceToHost, st0));
+    PNBI_CUDA(cudaMemcpyAsync(stbuf.data(), C.st[0], nb * I, cudaMemcpyDeviceToHost, st0));
+    PNBI_CUDA(cudaMemcpyAsync(itbuf.data(), C.it[0], nb * I, cudaMemcpyDeviceToHost, st0));
+    PNBI_CUDA(cudaStreamSynchronize(st0));
+    for (size_t q = 0; q < nb; q++) {
+      const size_t v = v0 + (size_t)idx[q0 + q];
+      std::memcpy(p->coefficients + v * n, &cbuf[q * n], n * D);
+      p->residual[v] = rnbuf[q];
+      if (p->r_squared) p->r_squared[v] = r2buf[q];
+      p->status[v] = stbuf[q];
+      p->iterations[v] = itbuf[q];
+    }
   }
+  C.last_redo = C.defer_count;  // what pnb_nnls_last_redo_count reports for this call
   return 0;
 }
 }  // namespace
