@@ -392,7 +392,10 @@ class CurveFitSolver(BaseSolver):
 
         eager = bool(self.want_cov) and self.want_cov is not True and self.want_cov != "lazy"
         key = (n_all, n_free, n_pixels, eager)
-        if self.pinned_outputs == "auto" and self._last_out_key != key:
+        nbytes = n_pixels * (8 * n_all + 28 + (8 * n_free * n_free if eager else 0))
+        if self.pinned_outputs == "auto" and (self._last_out_key != key or nbytes > (1 << 30)):
+            # first fit of a shape, or a block so large that locking its pages (~0.6 s per GB) never pays
+            # for itself: plain numpy arrays
             self._last_out_key = key
             return None
         self._last_out_key = key

@@ -13,6 +13,10 @@ from .base import BaseSolver, PixelResults, _PixelFitResult
 log = logging.getLogger("pyneapple_b200")
 
 
+# "auto" page-locks result blocks up to this many bytes (see NNLSSolver.fit)
+_AUTO_PIN_LIMIT = 1 << 30
+
+
 def regularization_matrix(n_bins: int, order: int, mu: float = 1.0) -> np.ndarray:
     """Tikhonov matrix, orders 0-3 (behaviour of model_functions/nnls.py:46-85).
 
@@ -117,9 +121,13 @@ class NNLSSolver(BaseSolver):
         out = None
         self.status_ = self.iterations_ = self.r_squared_ = None
         key = (self.n_pixels, basis.shape[1])
-        use_pinned = bool(self.pinned_outputs) and not on_device and self.n_pixels >= 16384
-        if use_pinned and self.pinned_outputs == "auto" and self._last_out_key != key:
-            use_pinned = False  # first fit of this shape: locking the pages costs more than one staged download
+        use_pinned = bool(self.pinned_outputs) and self.n_pixels >= 16384
+        if use_pinned and self.pinned_outputs == "auto" and (
+                self._last_out_key != key or self.n_pixels * (basis.shape[1] + 4) * 8 > _AUTO_PIN_LIMIT):
+            # first fit of this shape: locking the pages costs more than one staged download.  Large blocks
+            # never pay for themselves in "auto" mode: page-locking takes ~0.6 s per GB (5 s for the 8.4 GB of
+            # spectra of a 4.19 M voxel volume) and saves ~0.03 s per GB and fit; pinned_outputs=True asks for it
+            use_pinned = False
         self._last_out_key = key
         if use_pinned:
             from .. import _lib
@@ -137,8 +145,15 @@ class NNLSSolver(BaseSolver):
                     r2=_lib.pinned_empty((self.n_pixels,)))
                 self._out_cache = (key, out)
         res = engine.nnls_fit(basis, reg, signal, self.max_iter, device=self.device,
-                              chunk_vox=self.chunk_vox, out=out, algorithm=self.algorithm, dual_init=self.dual_init)
-        if on_device:
+                              chunk_vox=self.chunk_vox, out=None if on_device else out, algorithm=self.algorithm,
+                              dual_init=self.dual_init)
+        if on_device and out is not None:
+            # device-resident signal, host results: straight into the page-locked block (the 8.4 GB of
+            # spectra of a 4.19 M voxel volume take 0.15 s that way, 0.46 s into a fresh numpy array)
+            for k, v in res.items():
+                engine.to_host_into(v, out[k])
+            res = dict(out)
+        elif on_device:
             res = {k: engine.to_host(v) for k, v in res.items()}
         status = res["status"]
         self.status_, self.iterations_ = status, res["iterations"]

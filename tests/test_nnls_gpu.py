@@ -200,6 +200,16 @@ def test_page_locked_spectra_are_never_overwritten_while_a_caller_holds_them():
     s.fit(b, 2.0 * y)
     assert np.array_equal(held, first[:100]) and not np.shares_memory(s.params_["coefficients"], block)
     assert np.allclose(s.params_["coefficients"], 2.0 * first, rtol=1e-9, atol=1e-9)
+    # a device-resident signal downloads into the page-locked block too
+    import torch
+
+    del held
+    s2 = NNLSSolver(model=model, reg_order=2, mu=0.02, max_iter=250)
+    yd = torch.as_tensor(y).cuda()
+    s2.fit(b, yd)
+    s2.fit(b, yd)
+    assert np.shares_memory(s2.params_["coefficients"], s2._out_cache[1]["coefficients"])
+    assert np.array_equal(s2.params_["coefficients"], first) and np.array_equal(s2.status_, np.ones(16384, np.int32))
 
 
 def test_single_voxel_and_device_path():
