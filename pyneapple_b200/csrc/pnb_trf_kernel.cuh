@@ -220,27 +220,18 @@ __global__ void __launch_bounds__(BLOCK, PNB_TRF_MINBLOCKS) trf_kernel(const Trf
         finished = true;
       }
     } else if (cur >= 0 && !pending) {
-      // ---- prepare a trial step -------------------------------------------------
-      bool go = true;
-      if (S.need_prologue) {
-        go = (METHOD == 2) ? lm_prologue<M>(S, LM, O)
-             : (METHOD == 1) ? dbx_prologue<M>(S, DB, O) : trf_prologue<M>(S, O, my_lb, my_ub, BLOCK);
-        S.need_prologue = false;
-      }
-      if (go) {
-        if (METHOD == 2) {
-          lm_trial<M>(S, LM, O);
-        } else if (METHOD == 1) {
-          dbx_trial<M>(S, DB, O, my_lb, my_ub, BLOCK);
-        } else {
-          double p_h[N];
-          trf_solve_tr<M>(S, p_h);
-          trf_select_step<M>(S, p_h, my_lb, my_ub, BLOCK, O.frozen);
-        }
-        do_eval = true;
+      // ---- prepare a trial step (the prologue of this outer iteration ran at the end of the
+      // previous pass, see below) -------------------------------------------------
+      if (METHOD == 2) {
+        lm_trial<M>(S, LM, O);
+      } else if (METHOD == 1) {
+        dbx_trial<M>(S, DB, O, my_lb, my_ub, BLOCK);
       } else {
-        finished = true;
+        double p_h[N];
+        trf_solve_tr<M>(S, p_h);
+        trf_select_step<M>(S, p_h, my_lb, my_ub, BLOCK, O.frozen);
       }
+      do_eval = true;
     }
     __syncwarp();
     // ---- model, Jacobian and normal equations at x_new --------------------------
@@ -257,6 +248,15 @@ __global__ void __launch_bounds__(BLOCK, PNB_TRF_MINBLOCKS) trf_kernel(const Trf
         S.need_prologue = (METHOD == 2) ? lm_after_trial<M>(S, LM, O, c, g, A)
                           : (METHOD == 1) ? dbx_after_trial<M>(S, DB, O, c, g, A, my_lb, my_ub, BLOCK)
                                           : trf_after_trial<M>(S, O, c, g, A);
+      }
+      // The head of the next outer iteration (scaling vector, termination tests, trust-region model)
+      // runs in THIS pass, right after the step has been accepted: a converged voxel is recognised in
+      // the pass of its last evaluation instead of spending one more pass to find out.
+      if (!finished && S.need_prologue) {
+        const bool go = (METHOD == 2) ? lm_prologue<M>(S, LM, O)
+                        : (METHOD == 1) ? dbx_prologue<M>(S, DB, O) : trf_prologue<M>(S, O, my_lb, my_ub, BLOCK);
+        S.need_prologue = false;
+        if (!go) finished = true;
       }
     }
     __syncwarp();
