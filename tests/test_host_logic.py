@@ -250,6 +250,42 @@ def test_pinned_output_blocks_are_only_reused_when_nobody_else_holds_them():
     del held
 
 
+def test_page_locked_block_policy(monkeypatch):
+    """`pinned_outputs="auto"`: nothing on the first fit of a shape, the cached block from the second on, a fresh
+    block while a caller holds the old arrays OR A VIEW of one, and never for blocks above 1 GB.  The page-locked
+    allocator is replaced by one that builds its arrays the same way (`np.ndarray(buffer=...)`) from plain memory."""
+    import ctypes
+
+    from pyneapple_b200 import _lib, models
+    from pyneapple_b200.solvers import CurveFitSolver
+
+    def fake_pinned(shape, dtype=np.float64):
+        shape = tuple(int(v) for v in np.atleast_1d(shape))
+        dtype = np.dtype(dtype)
+        if int(np.prod(shape)) * dtype.itemsize > (1 << 26):
+            raise AssertionError("the policy asked for a page-locked block it should not want")
+        buf = (ctypes.c_char * max(1, int(np.prod(shape)) * dtype.itemsize))()
+        return np.ndarray(shape=shape, dtype=dtype, buffer=buf)
+
+    monkeypatch.setattr(_lib, "pinned_empty", fake_pinned)
+    s = CurveFitSolver(model=models.BiExpModel(fit_s0=True), max_iter=250, tol=1e-8,
+                       p0={"f1": 0.2, "D1": 1e-3, "D2": 0.02, "S0": 1000.0},
+                       bounds={"f1": (0.01, 0.99), "D1": (1e-5, 3e-3), "D2": (3e-3, 0.3), "S0": (1.0, 5e3)})
+    y = np.zeros((70000, 16))
+    assert s._pinned_out(4, 4, 70000, y) is None                 # first fit of the shape
+    blk = s._pinned_out(4, 4, 70000, y)
+    assert blk is not None and blk["params"].shape == (4, 70000) and "cov" not in blk
+    assert s._pinned_out(4, 4, 70000, y) is blk                  # nobody holds anything: reused
+    row = blk["params"][1]                                        # what solver.params_["D1"] is
+    assert row.base is blk["params"]
+    fresh = s._pinned_out(4, 4, 70000, y)
+    assert fresh is not blk and not np.shares_memory(fresh["params"], row)
+    del row, blk, fresh
+    assert s._pinned_out(4, 4, 1000, y[:1000]) is None            # small problems stay pageable
+    assert s._pinned_out(4, 4, 40_000_000, np.zeros((1, 16))) is None  # first fit of that shape ...
+    assert s._pinned_out(4, 4, 40_000_000, np.zeros((1, 16))) is None  # ... and 2.4 GB is above the limit of "auto"
+
+
 def test_device_argument_forms():
     from pyneapple_b200 import _lib
 
