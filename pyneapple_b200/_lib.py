@@ -51,7 +51,7 @@ class TrfProblem(C.Structure):
         ("jac_mode", C.c_int32),
         ("x_scale_jac", C.c_int32),
         ("method", C.c_int32),
-        ("reserved", C.c_int32),
+        ("finish_wait", C.c_int32),
         ("x_scale", C.c_double * 8),
         ("params", C.c_void_p),
         ("cov", C.c_void_p),

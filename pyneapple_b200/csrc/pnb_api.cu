@@ -209,6 +209,7 @@ pnb::TrfOptions make_options(const pnb_trf_problem *p) {
   o.frozen = p->frozen_mask & ((1u << p->n_params) - 1u);
   for (int i = 0; i < 8; i++) o.x_scale[i] = (p->x_scale[i] > 0.0) ? p->x_scale[i] : 1.0;
   o.tr = p->repetition_time; o.tm = p->mixing_time;
+  o.finish_wait = (p->finish_wait > 0 && p->finish_wait <= 64) ? p->finish_wait : pnb::kTrfFinishWait;
   return o;
 }
 

@@ -55,6 +55,7 @@ struct TrfOptions {
   unsigned frozen;   // bit j set: parameter j is fixed at its p0 value
   double x_scale[8];
   double tr, tm;     // repetition / mixing time of the T1 variants
+  int finish_wait = 3;  // kernel scheduling only (trf_kernel: passes a converged lane waits for its warp)
 };
 
 enum TrfStatus {

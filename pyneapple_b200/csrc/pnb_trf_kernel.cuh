@@ -62,7 +62,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 constexpr int kTrfClaim = 64;  // voxel indices claimed per warp-level atomicAdd
 // Batched write-out of converged lanes (see `pending` in trf_kernel).  A finished lane waits at most
-// PNB_TRF_FINISH_WAIT passes; the gate also opens when PNB_TRF_FINISH_BATCH lanes are ready (32 = never
+// PNB_TRF_FINISH_WAIT passes (the default of pnb_trf_problem.finish_wait / TrfOptions::finish_wait); the gate also opens when PNB_TRF_FINISH_BATCH lanes are ready (32 = never
 // by count: measured, a count trigger below 32 splits a warp into groups that drift apart and pay the
 // start / finish code separately - profiles/r2_trf_finish_batch.log) or nothing else runs.
 // BATCH 1 + WAIT 0 = every lane writes at once (the old behaviour).
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(BLOCK, PNB_TRF_MINBLOCKS) trf_kernel(const Trf
     pending = pending || finished;
     const unsigned pend_mask = __ballot_sync(FULL, pending);
     const bool running_any = __any_sync(FULL, cur >= 0 && !pending);
-    const bool overdue = __any_sync(FULL, pending && waited >= kTrfFinishWait);
+    const bool overdue = __any_sync(FULL, pending && waited >= O.finish_wait);
     const bool open = __popc(pend_mask) >= kTrfFinishBatch || overdue || !running_any;
     if (pending && open) {
       pending = false;

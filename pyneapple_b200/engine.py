@@ -105,6 +105,7 @@ def trf_fit(
     chunk_vox: int = 0,
     out: dict | None = None,
     method: str = "trf",
+    finish_wait: int = 0,
 ):
     """Fit all voxels.  ``p0``/``lb``/``ub``: ``(n_all,)`` or ``(n_all, n_vox)`` over
     ``desc.all_names`` (frozen rows of ``p0`` carry the fixed values).
@@ -136,6 +137,7 @@ def trf_fit(
     if method not in METHODS:
         raise NotImplementedError(f"method={method!r}: SciPy's 'trf', 'dogbox' and 'lm' have a B200 implementation")
     prob.method = METHODS[method]
+    prob.finish_wait = int(finish_wait)  # kernel scheduling hint (pnb_trf_problem.finish_wait), 0 = default
     xs = np.ones(8)
     if x_scale is not None:
         xs[:n_all] = np.broadcast_to(np.asarray(x_scale, float), (n_all,))

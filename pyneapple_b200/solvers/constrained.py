@@ -39,6 +39,9 @@ log = logging.getLogger("pyneapple_b200")
 # (TRF stops on the first criterion met): 1e-13 leaves max 1e-5 / median 2e-8 relative in the parameters at 13.8
 # evaluations per voxel, 1e-11 max 9e-5 at 11.9 — too close to the 1e-4 of the contract to buy 14 % of speed with
 _TIGHT = 1e-13
+# tight tolerances mean ~14 evaluations per voxel, spread widely: converged lanes of the TRF kernel wait longer for
+# their warp before the once-per-voxel code runs (pnb_trf_problem.finish_wait; 48.9 -> 45.7 ms per 4.19 M voxel slab)
+_FINISH_WAIT = 6
 
 
 class ConstrainedCurveFitSolver(CurveFitSolver):
@@ -200,11 +203,13 @@ class ConstrainedCurveFitSolver(CurveFitSolver):
         self.solver_kwargs.update(xtol=_TIGHT, gtol=_TIGHT)
         self.max_iter = max(4 * saved[1], 1000)
         self.jac = "analytic"
+        self._finish_wait = _FINISH_WAIT
         try:
             res = super().fit_device(xdata, y_dev, p0=p0, bounds=bounds, pixel_fixed_params=pixel_fixed_params,
                                      want_cov=want_cov)
         finally:
             self.tol, self.max_iter, self.solver_kwargs, self.jac = saved
+            self._finish_wait = 0
         res["n_active"] = 0
         res["n_released"] = 0
         free_names = res["free_names"]
@@ -264,7 +269,7 @@ class ConstrainedCurveFitSolver(CurveFitSolver):
         r2 = engine.trf_fit(face_desc, np.asarray(xdata, float), y_dev.index_select(0, idx),
                             torch.stack(P0), torch.stack(LB), torch.stack(UB), frozen,
                             max_nfev=max(4 * self.max_iter, 1000), ftol=_TIGHT, xtol=_TIGHT, gtol=_TIGHT,
-                            jac_mode=engine.JAC_ANALYTIC, want_cov=False)
+                            jac_mode=engine.JAC_ANALYTIC, finish_wait=_FINISH_WAIT, want_cov=False)
         ok = r2["status"] > 0
         # a face fit that fails (iteration limit) reports its start point — the projection of the phase-1
         # answer onto the face — so the voxel is returned feasible, with success = False, instead of keeping
@@ -357,7 +362,7 @@ class ConstrainedCurveFitSolver(CurveFitSolver):
         frozen = engine.frozen_mask(desc, fixed_names)
         r3 = engine.trf_fit(desc, np.asarray(xdata, float), y_dev.index_select(0, vox), P0, LB, UB, frozen,
                             max_nfev=max(4 * self.max_iter, 1000), ftol=_TIGHT, xtol=_TIGHT, gtol=_TIGHT,
-                            jac_mode=engine.JAC_ANALYTIC, want_cov=res["cov"] is not None)
+                            jac_mode=engine.JAC_ANALYTIC, finish_wait=_FINISH_WAIT, want_cov=res["cov"] is not None)
         i1, i2 = all_names.index("f1"), all_names.index("f2")
         better = ((r3["status"] > 0) & (r3["params"][i1] + r3["params"][i2] <= 1.0)
                   & (r3["cost"] < res["cost"].index_select(0, vox)))

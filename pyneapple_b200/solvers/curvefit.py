@@ -256,7 +256,7 @@ class CurveFitSolver(BaseSolver):
             jac_mode=jac_mode, x_scale=xs_full, x_scale_jac=x_scale_jac,
             want_cov=self.want_cov, device=self.device, chunk_vox=self.chunk_vox,
             out=self._pinned_out(len(all_names), len(all_names) - len(fixed_names), n_pixels, ydata),
-            method=method or self._ls_method(),
+            method=method or self._ls_method(), finish_wait=getattr(self, "_finish_wait", 0),
         )
         self._free_rows = [all_names.index(n) for n in free_names]
         return res, free_names
@@ -357,7 +357,7 @@ class CurveFitSolver(BaseSolver):
             gtol=gtol, jac_mode=jac_mode,
             x_scale=xs_full, x_scale_jac=x_scale_jac,
             want_cov=self.want_cov if want_cov is None else want_cov, device=self.primary_device,
-            method=self._ls_method(),
+            method=self._ls_method(), finish_wait=getattr(self, "_finish_wait", 0),
         )
         res["free_names"] = free_names
         res["free_rows"] = [all_names.index(n) for n in free_names]
