@@ -1,31 +1,24 @@
-"""Print the headline metrics of an .ncu-rep (dev tool): ncu_summary.py <rep>"""
-import csv, subprocess, sys, io
-rep = sys.argv[1]
+"""Key counters of the last launch matching <kernel substring> in an .ncu-rep, one per line (dev tool):
+
+    python scripts/ncu_summary.py <rep> <kernel substring> > profiles/<name>_ncu_summary.txt
+"""
+import csv, io, subprocess, sys
+
+rep, kern = sys.argv[1], sys.argv[2]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, data = rows[0], rows[1], rows[2:]
+row = [r for r in data if kern in r[hdr.index("Kernel Name")]][-1]
 want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__registers_per_thread",
         "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__thread_inst_executed_per_inst_executed.ratio",
         "smsp__warps_eligible.avg.per_cycle_active", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__inst_executed.sum", "sm__cycles_elapsed.max",
-        "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
-        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_membar_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_selected_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_sleeping_per_issue_active.ratio"]
-for w in want:
-    if w in hdr:
-        i = hdr.index(w)
-        print(f"{w:85s} {units[i]:14s} {[r[i] for r in data]}")
+        "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct"]
+want += [h for h in hdr if h.startswith("smsp__average_warps_issue_stalled") and h.endswith("_per_issue_active.ratio")]
+print(f"# {row[hdr.index('Kernel Name')]}   ({rep.split('/')[-1]})")
+for k in want:
+    if k in hdr:
+        i = hdr.index(k)
+        print(f"{k:85s} {units[i]:14s} {row[i]}")
