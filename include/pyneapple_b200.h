@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PNB_ABI_VERSION 3
+#define PNB_ABI_VERSION 4
 
 /* model_id: parameter order is the reference's `_all_param_names`
  * (models/monoexp.py:91-105, models/biexp.py:103-126, models/triexp.py:103-128) */
@@ -53,6 +53,9 @@ enum { PNB_METHOD_TRF = 0, PNB_METHOD_DOGBOX = 1,
         * 2 ftol, 3 xtol, 4 both (success); 0 maxfev reached, -6 / -7 / -8 = leastsq's info 6 / 7 / 8
         * ("ftol / xtol / gtol is too small"): failures, params = p0 */
        PNB_METHOD_LM = 2 };
+/* least_squares(loss=...) (scipy/optimize/_lsq/least_squares.py: soft_l1, huber, cauchy, arctan), forwarded by the
+ * reference from solver_kwargs (solvers/curvefit.py:70-73, 305) */
+enum { PNB_LOSS_LINEAR = 0, PNB_LOSS_SOFT_L1 = 1, PNB_LOSS_HUBER = 2, PNB_LOSS_CAUCHY = 3, PNB_LOSS_ARCTAN = 4 };
 
 enum {
   PNB_E_BADARG = -1,      /* inconsistent sizes / null pointers */
@@ -111,6 +114,15 @@ typedef struct pnb_trf_problem {
                                 many evaluations per voxel, like the tight tolerances of the constrained
                                 solver, run ~6 % faster with 6)                                   */
   double x_scale[8];         /* per parameter, 1.0 = SciPy default             */
+  /* curve_fit extras (same forwarding): any of weights / loss / diff_step selects a separate kernel instantiation,
+     built for method trf without a T1 parameter; PNB_E_UNSUPPORTED otherwise */
+  const double *weights;     /* (n_b) 1 / sigma of curve_fit(sigma=<1-D>), or NULL; host memory for the
+                                _host entry points, device memory for _device          */
+  double diff_step[8];       /* relative step of the 2-point Jacobian per parameter (least_squares
+                                diff_step), 0 = SciPy's default sqrt(eps) max(1, |x|)    */
+  int32_t loss;              /* PNB_LOSS_*                                      */
+  int32_t absolute_sigma;    /* curve_fit(absolute_sigma=True): cov not scaled by 2 cost / (m - n) */
+  double f_scale;            /* least_squares f_scale (soft margin of the robust losses), > 0; 0 = 1.0 */
   /* outputs */
   double *params;            /* (n_params, n_vox); fixed rows repeat the fixed value */
   double *cov;               /* (n_vox, n_free, n_free) or NULL.  pnb_trf_fit_host also accepts

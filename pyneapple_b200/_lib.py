@@ -53,6 +53,11 @@ class TrfProblem(C.Structure):
         ("method", C.c_int32),
         ("finish_wait", C.c_int32),
         ("x_scale", C.c_double * 8),
+        ("weights", C.c_void_p),
+        ("diff_step", C.c_double * 8),
+        ("loss", C.c_int32),
+        ("absolute_sigma", C.c_int32),
+        ("f_scale", C.c_double),
         ("params", C.c_void_p),
         ("cov", C.c_void_p),
         ("status", C.c_void_p),

@@ -39,11 +39,12 @@ using LaunchFn = cudaError_t (*)(const pnb::TrfDeviceArgs *, cudaStream_t);
 }  // namespace
 
 namespace pnb {
-cudaError_t trf_cov_launch(int n_free, long long n_vox, int m, const int *status, double *cov, cudaStream_t stream) {
+cudaError_t trf_cov_launch(int n_free, long long n_vox, int m, const int *status, double *cov, cudaStream_t stream,
+                           int absolute_sigma) {
 #define PNB_COV_CASE(nf)                                                                           \
   case nf: {                                                                                       \
     constexpr int TV = pnb::CovTile<nf>::TV;                                                       \
-    cov_kernel<nf><<<(unsigned)((n_vox + TV - 1) / TV), TV, 0, stream>>>(n_vox, m, status, cov);   \
+    cov_kernel<nf><<<(unsigned)((n_vox + TV - 1) / TV), TV, 0, stream>>>(n_vox, m, status, cov, absolute_sigma);   \
   } break;
   switch (n_free) {
     PNB_COV_CASE(2) PNB_COV_CASE(3) PNB_COV_CASE(4) PNB_COV_CASE(5) PNB_COV_CASE(6) PNB_COV_CASE(7)
@@ -147,6 +148,9 @@ void parallel_memcpy(void *dst, const void *src, size_t bytes) {
   extern "C" cudaError_t pnb_dogbox_launch_##id##_##t1(const pnb::TrfDeviceArgs *, cudaStream_t);  \
   extern "C" cudaError_t pnb_lm_launch_##id##_##t1(const pnb::TrfDeviceArgs *, cudaStream_t);
 PNB_DECL(0, 0) PNB_DECL(1, 0) PNB_DECL(2, 0) PNB_DECL(3, 0) PNB_DECL(4, 0) PNB_DECL(5, 0) PNB_DECL(6, 0)
+// the EXTRAS instantiations (curve_fit sigma / robust loss): method trf, no T1 parameter
+#define PNB_DECLX(id) extern "C" cudaError_t pnb_trfx_launch_##id##_0(const pnb::TrfDeviceArgs *, cudaStream_t);
+PNB_DECLX(0) PNB_DECLX(1) PNB_DECLX(2) PNB_DECLX(3) PNB_DECLX(4) PNB_DECLX(5) PNB_DECLX(6)
 #ifdef PNB_WITH_T1
 PNB_DECL(0, 1) PNB_DECL(1, 1) PNB_DECL(2, 1) PNB_DECL(3, 1) PNB_DECL(4, 1) PNB_DECL(5, 1) PNB_DECL(6, 1)
 PNB_DECL(0, 2) PNB_DECL(1, 2) PNB_DECL(2, 2) PNB_DECL(3, 2) PNB_DECL(4, 2) PNB_DECL(5, 2) PNB_DECL(6, 2)
@@ -156,7 +160,12 @@ namespace {
 
 #define PNB_ROW(name, t1) {name##_0_##t1, name##_1_##t1, name##_2_##t1, name##_3_##t1, name##_4_##t1, name##_5_##t1, name##_6_##t1}
 #define PNB_NOROW {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}
-LaunchFn trf_launcher(int model_id, int t1_mode, int method = 0) {
+LaunchFn trf_launcher(int model_id, int t1_mode, int method = 0, bool extras = false) {
+  if (extras) {
+    static const LaunchFn xtable[7] = PNB_ROW(pnb_trfx_launch, 0);
+    if (model_id < 0 || model_id > 6 || t1_mode != 0 || method != 0) return nullptr;
+    return xtable[model_id];
+  }
   static const LaunchFn table[3][3][7] = {
 #ifdef PNB_WITH_T1
       {PNB_ROW(pnb_trf_launch, 0), PNB_ROW(pnb_trf_launch, 1), PNB_ROW(pnb_trf_launch, 2)},
@@ -172,6 +181,13 @@ LaunchFn trf_launcher(int model_id, int t1_mode, int method = 0) {
   return table[method][t1_mode][model_id];
 }
 
+// weights or a robust loss need the EXTRAS kernel
+bool wants_extras(const pnb_trf_problem *p) {
+  bool steps = false;
+  for (int i = 0; i < 8; i++) steps = steps || p->diff_step[i] > 0.0;
+  return p->weights != nullptr || p->loss != PNB_LOSS_LINEAR || steps;
+}
+
 int model_n_params(int model_id, int t1_mode) {
   static const int base[7] = {2, 3, 4, 4, 5, 6, 6};
   return base[model_id] + (t1_mode ? 1 : 0);
@@ -185,6 +201,11 @@ int check_problem(const pnb_trf_problem *p) {
     return fail(PNB_E_UNSUPPORTED, "method must be PNB_METHOD_TRF, PNB_METHOD_DOGBOX or PNB_METHOD_LM");
   if (!trf_launcher(p->model_id, p->t1_mode, p->method))
     return fail(PNB_E_UNSUPPORTED, "this build has no kernel for the requested model / T1 mode");
+  if (p->loss < PNB_LOSS_LINEAR || p->loss > PNB_LOSS_ARCTAN) return fail(PNB_E_BADARG, "loss must be one of PNB_LOSS_*");
+  if (wants_extras(p) && !trf_launcher(p->model_id, p->t1_mode, p->method, true))
+    return fail(PNB_E_UNSUPPORTED, "sigma / loss / diff_step are built for method trf without a T1 parameter");
+  if (p->loss != PNB_LOSS_LINEAR && p->method == PNB_METHOD_LM)
+    return fail(PNB_E_BADARG, "method='lm' supports only 'linear' loss function.");
   if (p->n_params != model_n_params(p->model_id, p->t1_mode))
     return fail(PNB_E_BADARG, "n_params does not match the model");
   if (p->n_b < 1 || p->n_b > 512) return fail(PNB_E_BADARG, "n_b must be in [1, 512]");
@@ -210,6 +231,10 @@ pnb::TrfOptions make_options(const pnb_trf_problem *p) {
   for (int i = 0; i < 8; i++) o.x_scale[i] = (p->x_scale[i] > 0.0) ? p->x_scale[i] : 1.0;
   o.tr = p->repetition_time; o.tm = p->mixing_time;
   o.finish_wait = (p->finish_wait > 0 && p->finish_wait <= 64) ? p->finish_wait : pnb::kTrfFinishWait;
+  for (int i = 0; i < 8; i++) o.diff_step[i] = (p->diff_step[i] > 0.0) ? p->diff_step[i] : 0.0;
+  o.loss = p->loss;
+  o.f_scale = (p->f_scale > 0.0) ? p->f_scale : 1.0;
+  o.absolute_sigma = p->absolute_sigma ? 1 : 0;
   return o;
 }
 
@@ -273,7 +298,8 @@ extern "C" int pnb_trf_fit_device(const pnb_trf_problem *p, void *cuda_stream) {
   a.njev = p->njev; a.cost = p->cost; a.r2 = p->r_squared;
   if (int rc = next_counter(&a.counter)) return rc;
   a.n_failed = nullptr;
-  cudaError_t e = trf_launcher(p->model_id, p->t1_mode, p->method)(&a, stream);
+  a.w = p->weights;
+  cudaError_t e = trf_launcher(p->model_id, p->t1_mode, p->method, wants_extras(p))(&a, stream);
   if (e != cudaSuccess) return cuda_fail(e, "trf kernel launch");
   g_launches.fetch_add(1);
   return 0;
@@ -303,7 +329,8 @@ struct Pipeline {
   static constexpr int kSlots = 3;
   Slot slots[kSlots];
   double *b = nullptr, *vec = nullptr;  // xdata, broadcast p0|lb|ub
-  size_t cap_b = 0;
+  double *w = nullptr;                  // weights (1 / sigma), when the problem has them
+  size_t cap_b = 0, cap_w = 0;
   unsigned long long *n_failed = nullptr;  // voxels of the current call that ended with status <= 0
   cudaStream_t cov_stream = nullptr;       // the one covariance pass over a device-resident covariance range
   bool init = false;
@@ -355,6 +382,8 @@ int trf_host_range(const pnb_trf_problem *p, int device, int64_t chunk_vox, size
     P.init = true;
   }
   if (int rc = grow(&P.b, &P.cap_b, (size_t)nb)) return rc;
+  if (p->weights)
+    if (int rc = grow(&P.w, &P.cap_w, (size_t)nb)) return rc;
   for (auto &s : P.slots) {
     if (int rc = grow(&s.y, &s.cap_y, C * nb)) return rc;
     const size_t need_p = C * np;
@@ -374,6 +403,7 @@ int trf_host_range(const pnb_trf_problem *p, int device, int64_t chunk_vox, size
   cudaStream_t s0 = P.slots[0].stream;
   PNB_CUDA(cudaMemsetAsync(P.n_failed, 0, sizeof(unsigned long long), s0));
   PNB_CUDA(cudaMemcpyAsync(P.b, p->xdata, sizeof(double) * nb, cudaMemcpyHostToDevice, s0));
+  if (p->weights) PNB_CUDA(cudaMemcpyAsync(P.w, p->weights, sizeof(double) * nb, cudaMemcpyHostToDevice, s0));
   if (!p->p0_per_voxel)
     PNB_CUDA(cudaMemcpyAsync(P.vec, p->p0, sizeof(double) * np, cudaMemcpyHostToDevice, s0));
   if (!p->bounds_per_voxel) {
@@ -383,7 +413,7 @@ int trf_host_range(const pnb_trf_problem *p, int device, int64_t chunk_vox, size
   PNB_CUDA(cudaStreamSynchronize(s0));
 
   const pnb::TrfOptions opt = make_options(p);
-  LaunchFn launch = trf_launcher(p->model_id, p->t1_mode, p->method);
+  LaunchFn launch = trf_launcher(p->model_id, p->t1_mode, p->method, wants_extras(p));
   const size_t NV = (size_t)p->n_vox;
   // pageable caller memory is staged through page-locked blocks with multi-threaded host copies;
   // inputs and outputs independently (a caller may hold pageable images and page-locked result arrays)
@@ -478,6 +508,7 @@ int trf_host_range(const pnb_trf_problem *p, int device, int64_t chunk_vox, size
     }
     pnb::TrfDeviceArgs a;
     a.n_b = nb; a.n_vox = (long long)n; a.b = P.b; a.y = s.y;
+    a.w = p->weights ? P.w : nullptr;
     a.p0 = p->p0_per_voxel ? s.p0 : P.vec;
     a.lb = p->bounds_per_voxel ? s.lb : P.vec + 8;
     a.ub = p->bounds_per_voxel ? s.ub : P.vec + 16;
@@ -529,7 +560,8 @@ int trf_host_range(const pnb_trf_problem *p, int device, int64_t chunk_vox, size
     const size_t n_chunks = sizes.size();
     for (int k = 0; k < Pipeline::kSlots && (size_t)k < n_chunks; k++)
       PNB_CUDA(cudaStreamWaitEvent(P.cov_stream, P.slots[k].kernel_done, 0));
-    cudaError_t e = pnb::trf_cov_launch(nfree, (long long)(v1 - v0), nb, nullptr, cov_dev, P.cov_stream);
+    cudaError_t e = pnb::trf_cov_launch(nfree, (long long)(v1 - v0), nb, nullptr, cov_dev, P.cov_stream,
+                                        opt.absolute_sigma);
     if (e != cudaSuccess) return cuda_fail(e, "covariance kernel launch");
   }
   if (staged)

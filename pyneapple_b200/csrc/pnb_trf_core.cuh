@@ -56,7 +56,37 @@ struct TrfOptions {
   double x_scale[8];
   double tr, tm;     // repetition / mixing time of the T1 variants
   int finish_wait = 3;  // kernel scheduling only (trf_kernel: passes a converged lane waits for its warp)
+  // curve_fit / least_squares extras (solvers/curvefit.py:305 forwards them)
+  double diff_step[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // relative 2-point step per parameter, 0 = SciPy's default
+  int loss = 0;            // 0 linear, 1 soft_l1, 2 huber, 3 cauchy, 4 arctan (EXTRAS evaluation only)
+  double f_scale = 1.0;    // soft margin of the robust losses
+  int absolute_sigma = 0;  // curve_fit(absolute_sigma=True): the covariance is not scaled by 2 cost / (m - n)
 };
+
+// least_squares' robust losses (scipy/optimize/_lsq/least_squares.py: soft_l1, huber, cauchy, arctan and
+// construct_loss_function): rho(z), rho'(z), rho''(z) at z = (f / f_scale)^2, with rho scaled by
+// f_scale^2 and rho'' by 1 / f_scale^2.
+PNB_HD void trf_rho(int loss, double f, double f_scale, double &r0, double &r1, double &r2) {
+  const double q = f / f_scale;
+  const double z = q * q;
+  if (loss == 1) {
+    const double t = 1.0 + z, st = sqrt(t);
+    r0 = 2.0 * (st - 1.0); r1 = 1.0 / st; r2 = -0.5 / (t * st);
+  } else if (loss == 2) {
+    if (z <= 1.0) { r0 = z; r1 = 1.0; r2 = 0.0; }
+    else { const double sz = sqrt(z); r0 = 2.0 * sz - 1.0; r1 = 1.0 / sz; r2 = -0.5 / (z * sz); }
+  } else if (loss == 3) {
+    const double t = 1.0 + z;
+    r0 = log1p(z); r1 = 1.0 / t; r2 = -1.0 / (t * t);
+  } else if (loss == 4) {
+    const double t = 1.0 + z * z;
+    r0 = atan(z); r1 = 1.0 / t; r2 = -2.0 * z / (t * t);
+  } else {
+    r0 = z; r1 = 1.0; r2 = 0.0;
+  }
+  r0 *= f_scale * f_scale;
+  r2 /= f_scale * f_scale;
+}
 
 enum TrfStatus {
   kStRunning = -99,
@@ -450,10 +480,14 @@ PNB_HD void trf_select_step(TrfLane<M> &S, double (&p_h)[M::NP], const double *l
 // yb(i) -> (y_i, b_i).  jac_mode 1 reproduces SciPy's 2-point differences
 // (_numdiff.py: h = sqrt(eps) * sign(x) * max(1, |x|), flipped / shrunk at the
 // bounds by _adjust_scheme_to_bounds, column = (f(x + h e_k) - f(x)) / dx).
-template <class M, class RowFn>
+// EXTRAS (a separate instantiation, the plain one stays as it is): `w` = 1 / sigma of curve_fit per
+// row (or nullptr) scales residual and Jacobian rows (_wrap_func / _wrap_jac), and a robust loss
+// rescales them as scale_for_robust_loss_function does: with J_s = max(rho' + 2 rho'' f^2, eps),
+// J^T J -> sum J_s row row^T, J^T f -> sum rho' f row, cost -> 0.5 sum rho.
+template <class M, bool EXTRAS = false, class RowFn>
 PNB_HD void trf_evaluate(const double (&xe)[M::NP], const TrfOptions &O, int m, RowFn yb,
                          const double *lb, const double *ub, int lbs, double &cost,
-                         double (&g)[M::NP], double (&A)[M::NP][M::NP]) {
+                         double (&g)[M::NP], double (&A)[M::NP][M::NP], const double *w = nullptr) {
   constexpr int N = M::NP;
   typename M::Point pt;
   M::prepare(xe, O.tr, O.tm, pt);
@@ -469,7 +503,25 @@ PNB_HD void trf_evaluate(const double (&xe)[M::NP], const TrfOptions &O, int m, 
       double yv, bv;
       yb(r, yv, bv);
       double gr[N];
-      const double f = M::value_grad(pt, bv, gr) - yv;
+      double f = M::value_grad(pt, bv, gr) - yv;
+      if (EXTRAS) {
+        const double wv = w ? w[r] : 1.0;
+        f *= wv;
+        double r0, r1, r2;
+        trf_rho(O.loss, f, O.f_scale, r0, r1, r2);
+        double js = r1 + 2.0 * r2 * f * f;
+        if (js < kEps) js = kEps;
+        c += r0;
+        const double fs = f * r1;
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+          gr[i] = ((O.frozen >> i) & 1u) ? 0.0 : gr[i] * wv;
+          g[i] += gr[i] * fs;
+#pragma unroll
+          for (int j = 0; j <= i; j++) A[i][j] += js * (gr[i] * gr[j]);
+        }
+        continue;
+      }
       c += f * f;
 #pragma unroll
       for (int i = 0; i < N; i++) {
@@ -487,6 +539,12 @@ PNB_HD void trf_evaluate(const double (&xe)[M::NP], const TrfOptions &O, int m, 
     for (int k = 0; k < N; k++) {
       const double xk = xe[k];
       double h = rstep * (xk >= 0.0 ? 1.0 : -1.0) * dmax(1.0, fabs(xk));
+      if (EXTRAS && O.diff_step[k] > 0.0) {
+        // _numdiff.py: _compute_absolute_step with rel_step: rel_step * sign(x) * |x|, the default where
+        // that step vanishes in floating point
+        const double hr = O.diff_step[k] * (xk >= 0.0 ? 1.0 : -1.0) * fabs(xk);
+        if ((xk + hr) - xk != 0.0) h = hr;
+      }
       const double l = lb[k * lbs], u = ub[k * lbs];
       const double lower = xk - l, upper = u - xk;
       const double xh = xk + h;
@@ -513,6 +571,31 @@ PNB_HD void trf_evaluate(const double (&xe)[M::NP], const TrfOptions &O, int m, 
       yb(r, yv, bv);
       double e[M::K];
       M::exps(pt, bv, e);
+      if (EXTRAS) {
+        double gr[N], ep[M::K];
+        M::perturbed_exps(pk, pt, bv, e, ep);
+        const double wv = w ? w[r] : 1.0;
+        const double f = (M::combine(pt, e) - yv) * wv;
+        double r0, r1, r2;
+        trf_rho(O.loss, f, O.f_scale, r0, r1, r2);
+        double js = r1 + 2.0 * r2 * f * f;
+        if (js < kEps) js = kEps;
+        c += r0;
+        const double fs = f * r1;
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+          gr[k] = 0.0;
+          if (!((O.frozen >> k) & 1u))
+            gr[k] = (((M::value_perturbed(pk[k], e, ep, k) - yv) * wv) - f) * dx[k];
+        }
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+          g[i] += gr[i] * fs;
+#pragma unroll
+          for (int j = 0; j <= i; j++) A[i][j] += js * (gr[i] * gr[j]);
+        }
+        continue;
+      }
       const double f = M::combine(pt, e) - yv;
       c += f * f;
       double gr[N], ep[M::K];
@@ -746,13 +829,13 @@ PNB_HD void trf_covariance(const TrfLane<M> &S, const TrfOptions &O, int m, doub
   }
   double C[N][N];
   double L[N][N], dinv[N];
-  if (m <= n_free) {
+  if (m <= n_free && !O.absolute_sigma) {
 #pragma unroll
     for (int i = 0; i < N; i++)
 #pragma unroll
       for (int j = 0; j < N; j++) C[i][j] = kInf;
   } else {
-    const double s_sq = 2.0 * S.cost / (double)(m - n_free);
+    const double s_sq = O.absolute_sigma ? 1.0 : 2.0 * S.cost / (double)(m - n_free);
     if (ldlt<N>(Af, 0.0, L, dinv)) {
 #pragma unroll
       for (int c = 0; c < N; c++) {

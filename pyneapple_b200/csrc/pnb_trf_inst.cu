@@ -1,5 +1,6 @@
 // One translation unit per (model, T1 mode, method): compiled with
 //   -DPNB_MODEL_ID=<0..6> -DPNB_T1MODE=<0..2> [-DPNB_METHOD=1 for dogbox, 2 for lm]
+//   [-DPNB_EXTRAS=1: the trf kernel that honours curve_fit's sigma / least_squares' robust loss]
 // so the seven-plus register-heavy kernels build in parallel.
 #include "pnb_trf_kernel.cuh"
 
@@ -13,7 +14,12 @@
 #ifndef PNB_METHOD
 #define PNB_METHOD 0
 #endif
-#if PNB_METHOD == 2
+#ifndef PNB_EXTRAS
+#define PNB_EXTRAS 0
+#endif
+#if PNB_EXTRAS
+#define PNB_CAT_(a, b, c) pnb_trfx_launch_##a##_##b
+#elif PNB_METHOD == 2
 #define PNB_CAT_(a, b, c) pnb_lm_launch_##a##_##b
 #elif PNB_METHOD == 1
 #define PNB_CAT_(a, b, c) pnb_dogbox_launch_##a##_##b
@@ -24,5 +30,5 @@
 
 extern "C" cudaError_t PNB_CAT(PNB_MODEL_ID, PNB_T1MODE)(const pnb::TrfDeviceArgs *a,
                                                           cudaStream_t stream) {
-  return pnb::trf_launch<pnb::Model<PNB_MODEL_ID, PNB_T1MODE>, PNB_TRF_BLOCK, PNB_METHOD>(*a, stream);
+  return pnb::trf_launch<pnb::Model<PNB_MODEL_ID, PNB_T1MODE>, PNB_TRF_BLOCK, PNB_METHOD, (PNB_EXTRAS != 0)>(*a, stream);
 }

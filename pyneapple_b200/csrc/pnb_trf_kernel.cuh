@@ -35,6 +35,7 @@ struct TrfDeviceArgs {
   long long n_vox;
   const double *b;       // (n_b)
   const double *y;       // (n_vox, n_b) voxel-major
+  const double *w = nullptr;  // (n_b) 1 / sigma of curve_fit, or nullptr (EXTRAS kernels only)
   // p0 / lb / ub over ALL model parameters: element (k, v) at ptr[k * row_stride + v * vox_stride]
   const double *p0, *lb, *ub;
   long long p0_row_stride, p0_vox_stride;
@@ -79,7 +80,9 @@ constexpr int kTrfFinishWait = PNB_TRF_FINISH_WAIT;
 #define PNB_TRF_MINBLOCKS 1
 #endif
 
-template <class M, int BLOCK, int METHOD = 0>
+// EXTRAS: the instantiation that honours curve_fit's `sigma` (a.w) and least_squares' robust `loss`
+// (trf_evaluate<M, true>); the plain kernels do not carry that code.
+template <class M, int BLOCK, int METHOD = 0, bool EXTRAS = false>
 __global__ void __launch_bounds__(BLOCK, PNB_TRF_MINBLOCKS) trf_kernel(const TrfDeviceArgs a) {
   constexpr int N = M::NP;
   constexpr unsigned FULL = 0xffffffffu;
@@ -89,14 +92,17 @@ __global__ void __launch_bounds__(BLOCK, PNB_TRF_MINBLOCKS) trf_kernel(const Trf
   const unsigned lane = tid & 31;
   const bool pv_p0 = a.p0_vox_stride != 0;
   const bool pv_bd = a.bd_vox_stride != 0;
-  // layout: b[m'] | y[2][m][BLOCK] | lb[2][N][BLOCK] | ub[2][N][BLOCK] | p0[2][N][BLOCK]
+  // layout: b[m'] | (EXTRAS: w[m']) | y[2][m][BLOCK] | lb[2][N][BLOCK] | ub[2][N][BLOCK] | p0[2][N][BLOCK]
   double *b_s = smem;
-  double *y_s = b_s + ((m + 1) & ~1);
+  double *w_s = b_s + ((m + 1) & ~1);
+  double *y_s = w_s + (EXTRAS ? ((m + 1) & ~1) : 0);
   double *lb_s = y_s + (size_t)2 * m * BLOCK;
   double *ub_s = lb_s + 2 * N * BLOCK;
   double *p0_s = ub_s + 2 * N * BLOCK;
   exp_tab_init(tid, BLOCK);
   for (int i = tid; i < m; i += BLOCK) b_s[i] = a.b[i];
+  if (EXTRAS)
+    for (int i = tid; i < m; i += BLOCK) w_s[i] = a.w ? a.w[i] : 1.0;
   if (!pv_bd) {
 #pragma unroll
     for (int k = 0; k < N; k++) {
@@ -237,7 +243,7 @@ __global__ void __launch_bounds__(BLOCK, PNB_TRF_MINBLOCKS) trf_kernel(const Trf
     // ---- model, Jacobian and normal equations at x_new --------------------------
     if (do_eval) {
       double c, g[N], A[N][N];
-      trf_evaluate<M>(S.x_new, O, m, yb, my_lb, my_ub, BLOCK, c, g, A);
+      trf_evaluate<M, EXTRAS>(S.x_new, O, m, yb, my_lb, my_ub, BLOCK, c, g, A, EXTRAS ? w_s : nullptr);
       if (first_eval) {
         first_eval = false;
         const bool ok0 = (METHOD == 2) ? lm_after_first_eval<M>(S, LM, O, c, g, A)
@@ -291,10 +297,12 @@ __global__ void __launch_bounds__(BLOCK, PNB_TRF_MINBLOCKS) trf_kernel(const Trf
         double ss_tot = 0.0;
         for (int r = 0; r < m; r++) { const double d = my_y[r * BLOCK] - mean; ss_tot += d * d; }
         double ss_res = 2.0 * S.cost;
-        if (!ok) {  // the returned parameters are p0: evaluate the model there
+        if (!ok || EXTRAS) {
+          // the returned parameters are p0: evaluate the model there.  EXTRAS: S.cost is the weighted /
+          // robust cost, R^2 wants the plain residuals at the solution
           double p0v[N], c0, g0[N], A0[N][N];
 #pragma unroll
-          for (int k = 0; k < N; k++) p0v[k] = my_p0[k * BLOCK];
+          for (int k = 0; k < N; k++) p0v[k] = ok ? S.x[k] : my_p0[k * BLOCK];
           TrfOptions O2 = O;
           O2.jac_mode = 0;
           trf_evaluate<M>(p0v, O2, m, yb, my_lb, my_ub, BLOCK, c0, g0, A0);
@@ -339,7 +347,7 @@ template <int NF> struct CovTile { static constexpr int TV = NF <= 4 ? 256 : 64;
 
 template <int NF>
 __global__ void __launch_bounds__(CovTile<NF>::TV) cov_kernel(long long n_vox, int m, const int *__restrict__ status,
-                                                              double *__restrict__ cov) {
+                                                              double *__restrict__ cov, int absolute_sigma) {
   constexpr int TV = CovTile<NF>::TV;
   // a tile of TV voxel slots goes through shared memory so that global memory is read and written
   // with consecutive lanes on consecutive doubles (each thread's slot is NF^2 doubles long)
@@ -362,13 +370,13 @@ __global__ void __launch_bounds__(CovTile<NF>::TV) cov_kernel(long long n_vox, i
 #pragma unroll
       for (int j = 0; j <= i; j++) A[i][j] = cv[q++];
     const double cost = cv[q];
-    if (m <= NF) {
+    if (m <= NF && !absolute_sigma) {
 #pragma unroll
       for (int i = 0; i < NF; i++)
 #pragma unroll
         for (int j = 0; j < NF; j++) C[i][j] = kInf;
     } else {
-      const double s_sq = 2.0 * cost / (double)(m - NF);
+      const double s_sq = absolute_sigma ? 1.0 : 2.0 * cost / (double)(m - NF);
       if (ldlt<NF>(A, 0.0, L, dinv)) {
 #pragma unroll
         for (int c = 0; c < NF; c++) {
@@ -414,16 +422,18 @@ __global__ void __launch_bounds__(CovTile<NF>::TV) cov_kernel(long long n_vox, i
 }
 
 // defined once in pnb_api.cu (six small instantiations)
-cudaError_t trf_cov_launch(int n_free, long long n_vox, int m, const int *status, double *cov, cudaStream_t stream);
+cudaError_t trf_cov_launch(int n_free, long long n_vox, int m, const int *status, double *cov, cudaStream_t stream,
+                           int absolute_sigma = 0);
 
-template <class M, int BLOCK> size_t trf_smem_bytes(int n_b) {
-  return sizeof(double) * (((n_b + 1) & ~1) + (size_t)2 * n_b * BLOCK + 6 * M::NP * BLOCK);
+template <class M, int BLOCK> size_t trf_smem_bytes(int n_b, bool extras = false) {
+  return sizeof(double) * ((extras ? 2 : 1) * ((n_b + 1) & ~1) + (size_t)2 * n_b * BLOCK + 6 * M::NP * BLOCK);
 }
 
 // Launch configuration: persistent grid, as many CTAs as are resident.
-template <class M, int BLOCK, int METHOD = 0> cudaError_t trf_launch(const TrfDeviceArgs &a, cudaStream_t stream) {
-  const size_t smem = trf_smem_bytes<M, BLOCK>(a.n_b);
-  auto kern = trf_kernel<M, BLOCK, METHOD>;
+template <class M, int BLOCK, int METHOD = 0, bool EXTRAS = false>
+cudaError_t trf_launch(const TrfDeviceArgs &a, cudaStream_t stream) {
+  const size_t smem = trf_smem_bytes<M, BLOCK>(a.n_b, EXTRAS);
+  auto kern = trf_kernel<M, BLOCK, METHOD, EXTRAS>;
   // per thread: the multi-GPU host entry drives one device from each of its threads
   static thread_local int blocks_per_sm_cache = -1;
   static thread_local size_t smem_cache = 0;
@@ -460,7 +470,7 @@ template <class M, int BLOCK, int METHOD = 0> cudaError_t trf_launch(const TrfDe
   int n_free = 0;
   for (int i = 0; i < M::NP; i++) n_free += ((a.opt.frozen >> i) & 1u) ? 0 : 1;
   if (n_free < 2) return err;
-  return trf_cov_launch(n_free, a.n_vox, a.n_b, a.status, a.cov, stream);
+  return trf_cov_launch(n_free, a.n_vox, a.n_b, a.status, a.cov, stream, a.opt.absolute_sigma);
 }
 
 }  // namespace pnb

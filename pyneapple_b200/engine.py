@@ -38,6 +38,7 @@ JAC_TWO_POINT = 1
 JAC_MINPACK_FORWARD = 2  # fdjac2 of MINPACK's lmdif (method "lm" without an analytic Jacobian)
 # PNB_METHOD_*: scipy.optimize.least_squares(method=...) for "trf" / "dogbox", MINPACK through leastsq for "lm"
 METHODS = {"trf": 0, "dogbox": 1, "lm": 2}
+LOSSES = {"linear": 0, "soft_l1": 1, "huber": 2, "cauchy": 3, "arctan": 4}  # least_squares(loss=...), PNB_LOSS_*
 ST_LM_TOO_FEW_DATA = -9  # not a kernel status: method='lm' with more parameters than measurements
 # leastsq's xtol / gtol defaults (curve_fit(method="lm") does not override them)
 LM_XTOL, LM_GTOL = 1.49012e-8, 0.0
@@ -106,6 +107,11 @@ def trf_fit(
     out: dict | None = None,
     method: str = "trf",
     finish_wait: int = 0,
+    weights=None,
+    loss: str = "linear",
+    f_scale: float = 1.0,
+    diff_step=None,
+    absolute_sigma: bool = False,
 ):
     """Fit all voxels.  ``p0``/``lb``/``ub``: ``(n_all,)`` or ``(n_all, n_vox)`` over
     ``desc.all_names`` (frozen rows of ``p0`` carry the fixed values).
@@ -138,6 +144,29 @@ def trf_fit(
         raise NotImplementedError(f"method={method!r}: SciPy's 'trf', 'dogbox' and 'lm' have a B200 implementation")
     prob.method = METHODS[method]
     prob.finish_wait = int(finish_wait)  # kernel scheduling hint (pnb_trf_problem.finish_wait), 0 = default
+    # curve_fit extras (`weights` = 1 / sigma per b-value; `diff_step` over desc.all_names)
+    if loss not in LOSSES:
+        raise ValueError(f"`loss` must be one of {sorted(LOSSES)} (callables have no B200 implementation).")
+    if loss != "linear" and method == "lm":
+        raise ValueError("method='lm' supports only 'linear' loss function.")
+    if not float(f_scale) > 0.0:
+        raise ValueError("`f_scale` must be positive.")
+    prob.loss, prob.f_scale, prob.absolute_sigma = LOSSES[loss], float(f_scale), int(bool(absolute_sigma))
+    ds = np.zeros(8)
+    if diff_step is not None:
+        ds[:n_all] = np.broadcast_to(np.asarray(diff_step, float), (n_all,))
+        if not np.all(np.isfinite(ds)) or np.any(ds < 0):
+            raise ValueError("`diff_step` must be non-negative and finite.")
+    for i in range(8):
+        prob.diff_step[i] = ds[i]
+    w_host = None
+    if weights is not None:
+        w_host = np.ascontiguousarray(np.asarray(weights, np.float64))
+        if w_host.ndim != 1 or not np.all(np.isfinite(w_host)):
+            raise ValueError("weights (1 / sigma) must be a finite vector over the b-values")
+    extras = w_host is not None or loss != "linear" or bool(np.any(ds > 0))
+    if extras and (method != "trf" or desc.t1_mode != 0):
+        raise NotImplementedError("sigma / loss / diff_step are implemented for method='trf' on models without a T1 parameter")
     xs = np.ones(8)
     if x_scale is not None:
         xs[:n_all] = np.broadcast_to(np.asarray(x_scale, float), (n_all,))
@@ -145,6 +174,11 @@ def trf_fit(
         prob.x_scale[i] = xs[i]
 
     if _is_torch_cuda(ydata):
+        if w_host is not None:
+            if w_host.shape != (int(ydata.shape[1]),):
+                raise ValueError("`sigma` has incorrect shape.")
+            w_dev = _small_const(w_host, ydata.device)
+            prob.weights = w_dev.data_ptr()
         return _trf_fit_device(lib, prob, desc, xdata, ydata, p0, lb, ub, n_free, want_cov)
 
     y = _as_f64(ydata)
@@ -193,7 +227,11 @@ def trf_fit(
     njev = o.get("njev") if o.get("njev") is not None else np.empty(n_vox, np.int32)
     cost = o.get("cost") if o.get("cost") is not None else np.empty(n_vox)
     r2 = o.get("r2") if o.get("r2") is not None else np.empty(n_vox)
-    keep = (b, y, p0, lb, ub, params, cov, status, nfev, njev, cost, r2)
+    if w_host is not None:
+        if w_host.shape != (n_b,):
+            raise ValueError("`sigma` has incorrect shape.")
+        prob.weights = w_host.ctypes.data
+    keep = (b, y, p0, lb, ub, params, cov, status, nfev, njev, cost, r2, w_host)
     prob.xdata, prob.ydata = b.ctypes.data, y.ctypes.data
     prob.p0, prob.lb, prob.ub = p0.ctypes.data, lb.ctypes.data, ub.ctypes.data
     prob.params = params.ctypes.data

@@ -21,7 +21,7 @@ log = logging.getLogger("pyneapple_b200")
 
 # extra keyword arguments the reference would splat into curve_fit /
 # least_squares (curvefit.py:70-73, 305) and that the device solver honours
-_HONOURED_KWARGS = {"xtol", "gtol", "x_scale"}
+_HONOURED_KWARGS = {"xtol", "gtol", "x_scale", "sigma", "absolute_sigma", "loss", "f_scale", "diff_step"}
 # accepted for TOML compatibility, meaningless on the GPU
 _IGNORED_KWARGS = {"n_pools"}
 
@@ -257,6 +257,7 @@ class CurveFitSolver(BaseSolver):
             want_cov=self.want_cov, device=self.device, chunk_vox=self.chunk_vox,
             out=self._pinned_out(len(all_names), len(all_names) - len(fixed_names), n_pixels, ydata),
             method=method or self._ls_method(), finish_wait=getattr(self, "_finish_wait", 0),
+            **self._extras_for(all_names, model_names, int(np.asarray(xdata).shape[0])),
         )
         self._free_rows = [all_names.index(n) for n in free_names]
         return res, free_names
@@ -291,6 +292,44 @@ class CurveFitSolver(BaseSolver):
             for i, n in enumerate(model_names):
                 xs_full[all_names.index(n)] = xs[i]
         return xs_full, x_scale_jac
+
+    def _extras_for(self, all_names, model_names, n_b):
+        out = self._extras_args(all_names, model_names)
+        w = out.get("weights")
+        if w is not None and np.ndim(w) == 0:
+            out["weights"] = np.full(n_b, 1.0 / float(w))   # scalar sigma
+        return out
+
+    def _extras_args(self, all_names, model_names):
+        """``sigma`` / ``absolute_sigma`` of ``curve_fit`` and ``loss`` / ``f_scale`` / ``diff_step`` of
+        ``least_squares`` (all forwarded by the reference, curvefit.py:70-73, 305) as engine arguments.  The same
+        values apply to every voxel, as in the reference's loop."""
+        kw = self.solver_kwargs
+        out = {}
+        sigma = kw.get("sigma")
+        if sigma is not None:
+            sigma = np.asarray(sigma, float)
+            if sigma.ndim == 2:
+                raise NotImplementedError("a 2-D `sigma` (covariance matrix of the data) has no B200 implementation")
+            # scipy/optimize/_minpack_py.py: transform = 1.0 / sigma (a scalar sigma applies to every point)
+            out["weights"] = 1.0 / sigma if sigma.ndim == 1 else sigma.reshape(())
+        if kw.get("absolute_sigma"):
+            out["absolute_sigma"] = True
+        loss = kw.get("loss", "linear")
+        if callable(loss):
+            raise NotImplementedError("a callable `loss` has no B200 implementation")
+        if loss != "linear":
+            out["loss"] = loss
+        if "f_scale" in kw:
+            out["f_scale"] = float(kw["f_scale"])
+        ds = kw.get("diff_step")
+        if ds is not None:
+            ds = np.broadcast_to(np.asarray(ds, float), (len(model_names),))
+            full = np.zeros(len(all_names))
+            for i, n in enumerate(model_names):
+                full[all_names.index(n)] = ds[i]
+            out["diff_step"] = full
+        return out
 
     # ------------------------------------------------------------------
     def fit_device(self, xdata, y_dev, p0=None, bounds=None, pixel_fixed_params=None, want_cov=None):
@@ -358,6 +397,7 @@ class CurveFitSolver(BaseSolver):
             x_scale=xs_full, x_scale_jac=x_scale_jac,
             want_cov=self.want_cov if want_cov is None else want_cov, device=self.primary_device,
             method=self._ls_method(), finish_wait=getattr(self, "_finish_wait", 0),
+            **self._extras_for(all_names, model_names, int(np.asarray(xdata).shape[0])),
         )
         res["free_names"] = free_names
         res["free_rows"] = [all_names.index(n) for n in free_names]

@@ -71,6 +71,31 @@ def trf_fit(model_id, b, y, p0, lb, ub, frozen=None, t1_mode=0, tr=0.0, tm=0.0, 
     return dict(params=params, cov=cov, status=status, nfev=nfev, cost=cost)
 
 
+def trf_fit_extras(model_id, b, y, p0, lb, ub, ftol=1e-8, xtol=1e-8, gtol=1e-8, max_nfev=250, jac_mode=1, method=0,
+                   weights=None, loss=0, f_scale=1.0, diff_step=None, absolute_sigma=False, extras_kernel=True):
+    """The core with the curve_fit extras (``weights`` = 1 / sigma per b-value)."""
+    b = np.ascontiguousarray(b, np.float64)
+    y = np.ascontiguousarray(np.atleast_2d(y), np.float64)
+    n_vox, nb = y.shape
+    p0, lb, ub = (np.ascontiguousarray(a, np.float64) for a in (p0, lb, ub))
+    na = p0.shape[1]
+    params = np.empty((n_vox, na)); cov = np.empty((n_vox, na, na))
+    status = np.empty(n_vox, np.int32); nfev = np.empty(n_vox, np.int32); cost = np.empty(n_vox)
+    w = None if weights is None else np.ascontiguousarray(np.broadcast_to(np.asarray(weights, float), (nb,)))
+    ds = None
+    if diff_step is not None:
+        ds = np.zeros(8); ds[:na] = np.broadcast_to(np.asarray(diff_step, float), (na,))
+    rc = lib().pnbh_trf_fit_extras(
+        C.c_int(model_id), C.c_int(nb), _p(b), C.c_long(n_vox), _p(y), _p(p0), _p(lb), _p(ub), C.c_double(ftol),
+        C.c_double(xtol), C.c_double(gtol), C.c_int(max_nfev), C.c_int(jac_mode), C.c_int(method),
+        None if w is None else _p(w), C.c_int(loss), C.c_double(f_scale), None if ds is None else _p(ds),
+        C.c_int(int(absolute_sigma)), C.c_int(int(extras_kernel)), _p(params), _p(cov), _p(status, C.c_int),
+        _p(nfev, C.c_int), _p(cost))
+    if rc != 0:
+        raise RuntimeError(f"hostsim: unsupported model {model_id}")
+    return dict(params=params, cov=cov, status=status, nfev=nfev, cost=cost)
+
+
 def exp(x):
     """``pnb_exp`` of pnb_hd.cuh (host build of the same code the kernel runs)."""
     x = np.ascontiguousarray(x, np.float64)

@@ -23,7 +23,7 @@ def test_exports_every_declared_symbol(lib):
 
 
 def test_abi_version(lib):
-    assert lib.pnb_abi_version() == 3
+    assert lib.pnb_abi_version() == 4
 
 
 def test_struct_layout_matches_header(lib):

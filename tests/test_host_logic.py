@@ -116,7 +116,16 @@ def test_curvefit_solver_constructor_contract():
     with pytest.raises(ValueError):  # p0 list
         CurveFitSolver(models.MonoExpModel(), 250, 1e-8, {"S0": [1.0], "D": [1e-3]}, {"S0": (1, 2), "D": (0, 1)})
     with pytest.raises(NotImplementedError):  # curve_fit kwargs without a device implementation
-        _mono(loss="huber")
+        _mono(check_finite=False)
+    x = _mono(loss="huber", f_scale=2.0, sigma=np.array([1.0, 2.0, 4.0]), absolute_sigma=True, diff_step=1e-6)
+    args = x._extras_for(["D", "S0"], list(x.model.param_names), 3)   # curve_fit's extras as engine arguments
+    assert args["loss"] == "huber" and args["f_scale"] == 2.0 and args["absolute_sigma"] is True
+    assert np.array_equal(args["weights"], [1.0, 0.5, 0.25]) and np.array_equal(args["diff_step"], [1e-6, 1e-6])
+    assert np.array_equal(_mono(sigma=4.0)._extras_for(["D", "S0"], ["S0", "D"], 3)["weights"], [0.25] * 3)
+    with pytest.raises(NotImplementedError):  # full covariance matrix of the data
+        _mono(sigma=np.eye(3))._extras_for(["D", "S0"], ["S0", "D"], 3)
+    with pytest.raises(NotImplementedError):
+        _mono(loss=lambda z: z)._extras_for(["D", "S0"], ["S0", "D"], 3)
     assert get_solver("curvefit", model=models.MonoExpModel(), max_iter=5, tol=1e-3, p0=s.p0,
                       bounds=s.bounds).max_iter == 5
     with pytest.raises(ValueError):

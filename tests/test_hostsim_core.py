@@ -229,3 +229,55 @@ def test_lm_core_matches_reference(name):
         assert np.median(err) < 1e-6
         cerr = rel_err(r["cov"][ok], P["ref_pcov"][ok]).reshape(int(ok.sum()), -1).max(axis=1)
         assert np.nanmedian(cerr) < 1e-3
+
+
+# --------------------------------------------------------------------------- curve_fit extras
+_EXTRA_CASES = {
+    "sigma": (dict(sigma="S"), dict(weights="W")),
+    "sigma_absolute": (dict(sigma="S", absolute_sigma=True), dict(weights="W", absolute_sigma=True)),
+    "diff_step": (dict(diff_step=1e-6), dict(diff_step=1e-6)),
+    "soft_l1": (dict(loss="soft_l1", f_scale=20.0), dict(loss=1, f_scale=20.0)),
+    "huber": (dict(loss="huber", f_scale=20.0), dict(loss=2, f_scale=20.0)),
+    "cauchy": (dict(loss="cauchy", f_scale=30.0), dict(loss=3, f_scale=30.0)),
+    "arctan": (dict(loss="arctan", f_scale=60.0), dict(loss=4, f_scale=60.0)),
+    "sigma_huber": (dict(sigma="S", loss="huber", f_scale=1.5), dict(weights="W", loss=2, f_scale=1.5)),
+}
+
+
+def extras_problem(n=48, seed=3):
+    """Bi-exponential (S0) voxels with 2 % noise and a planted outlier on every seventh voxel."""
+    rng = np.random.default_rng(seed)
+    b = np.array([0, 5, 10, 20, 30, 40, 50, 75, 100, 150, 200, 300, 400, 500, 650, 800.0])
+    P = np.stack([rng.uniform(0.1, 0.4, n), rng.uniform(5e-4, 2e-3, n), rng.uniform(0.01, 0.08, n),
+                  rng.uniform(500, 1500, n)], 1)
+    y = np.stack([p[3] * (p[0] * np.exp(-b * p[1]) + (1 - p[0]) * np.exp(-b * p[2])) for p in P])
+    y *= 1 + 0.02 * rng.standard_normal(y.shape)
+    y[::7, 5] *= 1.6
+    return b, y, np.array([0.2, 1e-3, 0.02, 1000.0]), np.array([0.01, 1e-5, 3e-3, 1.0]), np.array([0.99, 3e-3, 0.3, 5e3]), \
+        np.linspace(5, 40, 16)
+
+
+def scipy_extras(b, y, p0, lb, ub, kw):
+    from scipy.optimize import curve_fit
+
+    f = lambda b_, f1, D1, D2, S0: S0 * (f1 * np.exp(-b_ * D1) + (1 - f1) * np.exp(-b_ * D2))  # noqa: E731
+    fits = [curve_fit(f, b, yi, p0=p0, bounds=(lb, ub), method="trf", maxfev=250, ftol=1e-8, **kw) for yi in y]
+    return np.array([p for p, _ in fits]), np.array([c for _, c in fits])
+
+
+@pytest.mark.parametrize("case", sorted(_EXTRA_CASES))
+def test_curve_fit_extras_core_equals_scipy(case):
+    """`sigma` / `absolute_sigma` (curve_fit) and `loss` / `f_scale` / `diff_step` (least_squares), which the
+    reference forwards from its solver kwargs (solvers/curvefit.py:70-73, 305): the EXTRAS instantiation of the
+    device core, compiled for the host, against SciPy itself."""
+    b, y, p0, lb, ub, sigma = extras_problem()
+    kw_scipy, kw_core = _EXTRA_CASES[case]
+    kw_scipy = {k: (sigma if isinstance(v, str) and v == "S" else v) for k, v in kw_scipy.items()}
+    kw_core = {k: (1.0 / sigma if isinstance(v, str) and v == "W" else v) for k, v in kw_core.items()}
+    ref_p, ref_c = scipy_extras(b, y, p0, lb, ub, kw_scipy)
+    n = y.shape[0]
+    r = hostsim.trf_fit_extras(3, b, y, np.tile(p0, (n, 1)), np.tile(lb, (n, 1)), np.tile(ub, (n, 1)), **kw_core)
+    assert (r["status"] > 0).all()
+    assert (np.abs(r["params"] - ref_p) / np.abs(ref_p)).max() <= 1e-4
+    d = np.sqrt(np.einsum("vii->vi", ref_c))
+    assert (np.abs(r["cov"] - ref_c) / (d[:, :, None] * d[:, None, :])).max() <= 1e-4   # on the scale of the variances

@@ -268,3 +268,49 @@ def test_page_locked_results_are_never_overwritten_while_a_caller_holds_them():
     s.fit(b, y)                                  # nobody holds the previous arrays: the block is reused
     s.fit(b, y)
     assert np.array_equal(s.params_["D1"], first)
+
+
+@pytest.mark.parametrize("case", ["sigma", "sigma_absolute", "diff_step", "soft_l1", "huber", "cauchy", "arctan", "sigma_huber"])
+def test_curve_fit_extras_equal_scipy(case):
+    """`sigma`, `absolute_sigma`, `loss`, `f_scale`, `diff_step` in the solver kwargs — forwarded to `curve_fit`
+    by the reference (solvers/curvefit.py:70-73, 305) — through CurveFitSolver on the GPU (host and device
+    pointer paths) against SciPy with the same keywords."""
+    import torch
+
+    from test_hostsim_core import _EXTRA_CASES, extras_problem, scipy_extras
+
+    b, y, p0, lb, ub, sigma = extras_problem()
+    kw = {k: (sigma if isinstance(v, str) and v == "S" else v) for k, v in _EXTRA_CASES[case][0].items()}
+    ref_p, ref_c = scipy_extras(b, y, p0, lb, ub, kw)
+    names = ["f1", "D1", "D2", "S0"]
+    mk = lambda: CurveFitSolver(model=models.BiExpModel(fit_s0=True), max_iter=250, tol=1e-8,  # noqa: E731
+                                p0=dict(zip(names, p0)), bounds={n: (l, u) for n, l, u in zip(names, lb, ub)},
+                                want_cov="eager", **kw)
+    s = mk().fit(b, y)
+    got = np.stack([s.params_[n] for n in names], 1)
+    assert np.asarray(s.pixel_results_.success).all()
+    assert (np.abs(got - ref_p) / np.abs(ref_p)).max() <= 1e-4
+    d = np.sqrt(np.einsum("vii->vi", ref_c))
+    assert (np.abs(np.asarray(s.diagnostics_["pcov"]) - ref_c) / (d[:, :, None] * d[:, None, :])).max() <= 1e-4
+    dev = mk().fit(b, torch.as_tensor(y).cuda())
+    for n in names:
+        assert np.array_equal(dev.params_[n], s.params_[n]), n
+    # R^2 is that of the plain residuals (fitters/base.py:142-186), whatever the loss or the weights
+    f1, D1, D2, S0 = (got[:, i][:, None] for i in range(4))
+    pred = S0 * (f1 * np.exp(-b * D1) + (1 - f1) * np.exp(-b * D2))
+    r2 = 1 - ((y - pred) ** 2).sum(1) / ((y - y.mean(1, keepdims=True)) ** 2).sum(1)
+    assert np.allclose(s.r_squared_, r2, rtol=0, atol=1e-9)
+
+
+def test_curve_fit_extras_are_refused_where_they_are_not_built():
+    kw = dict(model=models.BiExpModel(fit_s0=True), max_iter=250, tol=1e-8,
+              p0={"f1": 0.2, "D1": 1e-3, "D2": 0.02, "S0": 1000.0},
+              bounds={"f1": (0.01, 0.99), "D1": (1e-5, 3e-3), "D2": (3e-3, 0.3), "S0": (1.0, 5e3)})
+    b = np.linspace(0, 800, 16)
+    y = np.full((4, 16), 500.0)
+    with pytest.raises(NotImplementedError):
+        CurveFitSolver(method="dogbox", loss="huber", **kw).fit(b, y)
+    with pytest.raises(ValueError):
+        CurveFitSolver(sigma=np.ones(7), **kw).fit(b, y)
+    with pytest.raises(ValueError):
+        CurveFitSolver(loss="nope", **kw).fit(b, y)
