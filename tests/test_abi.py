@@ -41,6 +41,29 @@ def test_bad_arguments_are_rejected_without_a_device(lib):
     assert b"model" in lib.pnb_last_error()
 
 
+def test_curve_fit_extras_are_validated_by_the_library(lib):
+    """`loss` outside PNB_LOSS_*, extras with a method / T1 mode they are not built for, `lm` with a robust loss:
+    rejected by the argument check (before any CUDA call)."""
+    def problem(**kw):
+        prob = _lib.TrfProblem()
+        prob.model_id, prob.n_params, prob.n_b, prob.n_vox, prob.max_nfev, prob.jac_mode = 3, 4, 16, 0, 250, 1
+        for k, v in kw.items():
+            setattr(prob, k, v)
+        return prob
+
+    assert lib.pnb_trf_fit_host(ctypes.byref(problem()), 0, 0) == 0          # n_vox = 0: nothing to do
+    assert lib.pnb_trf_fit_host(ctypes.byref(problem(loss=2, f_scale=1.5)), 0, 0) == 0
+    assert lib.pnb_trf_fit_host(ctypes.byref(problem(loss=9)), 0, 0) == -1
+    assert b"PNB_LOSS" in lib.pnb_last_error()
+    assert lib.pnb_trf_fit_host(ctypes.byref(problem(loss=2, method=1)), 0, 0) == -2      # dogbox + robust loss
+    assert b"method trf" in lib.pnb_last_error()
+    t1 = problem(loss=1, t1_mode=1, n_params=5)
+    assert lib.pnb_trf_fit_host(ctypes.byref(t1), 0, 0) == -2
+    step = problem(method=1)
+    step.diff_step[0] = 1e-6
+    assert lib.pnb_trf_fit_host(ctypes.byref(step), 0, 0) == -2
+
+
 def test_no_cpu_fallback():
     import numpy as np
     from pyneapple_b200 import models
