@@ -125,7 +125,7 @@ extern "C" int pnbh_trf_fit(int model_id, int t1_mode, double tr, double tm, int
 }
 
 // the same with the curve_fit extras: weights = 1 / sigma per row (or null), robust loss, relative
-// finite-difference steps, absolute_sigma; bi-exponential S0 and mono-exponential S0 models
+// finite-difference steps, absolute_sigma; mono-exponential, bi-exponential S0 and reduced tri-exponential models
 extern "C" int pnbh_trf_fit_extras(int model_id, int nb, const double *b, long n_vox, const double *y, const double *p0,
                                    const double *lb, const double *ub, double ftol, double xtol, double gtol,
                                    int max_nfev, int jac_mode, int method, const double *w, int loss, double f_scale,
@@ -137,7 +137,7 @@ extern "C" int pnbh_trf_fit_extras(int model_id, int nb, const double *b, long n
   for (int i = 0; i < 8; i++) { O.x_scale[i] = 1.0; O.diff_step[i] = diff_step ? diff_step[i] : 0.0; }
   O.loss = loss; O.f_scale = f_scale; O.absolute_sigma = absolute_sigma;
 #define XCASE(ID) if (model_id == ID) { run_all<Model<ID, 0>>(O, nb, b, n_vox, y, p0, lb, ub, params, cov, status, nfev, cost, w, use_extras_kernel != 0); return 0; }
-  XCASE(1) XCASE(3) XCASE(4)
+  XCASE(0) XCASE(3) XCASE(4)
   return -1;
 }
 

@@ -281,3 +281,42 @@ def test_curve_fit_extras_core_equals_scipy(case):
     assert (np.abs(r["params"] - ref_p) / np.abs(ref_p)).max() <= 1e-4
     d = np.sqrt(np.einsum("vii->vi", ref_c))
     assert (np.abs(r["cov"] - ref_c) / (d[:, :, None] * d[:, None, :])).max() <= 1e-4   # on the scale of the variances
+
+
+@pytest.mark.parametrize("model_id,case", [(0, "sigma_huber"), (0, "diff_step"), (4, "huber"), (4, "sigma")])
+def test_curve_fit_extras_core_other_models(model_id, case):
+    """The EXTRAS evaluation is a template over the model: mono-exponential [S0, D] (id 0) and the reduced
+    tri-exponential (id 4) against SciPy, like the bi-exponential above."""
+    from scipy.optimize import curve_fit
+
+    rng = np.random.default_rng(11)
+    b = np.array([0, 5, 10, 20, 30, 40, 50, 75, 100, 150, 200, 300, 400, 500, 650, 800.0])
+    n = 24
+    if model_id == 0:   # [S0, D]
+        f = lambda b_, S0, D: S0 * np.exp(-b_ * D)  # noqa: E731
+        P = np.stack([rng.uniform(500, 1500, n), rng.uniform(5e-4, 3e-3, n)], 1)
+        p0, lb, ub = np.array([1000.0, 1e-3]), np.array([1.0, 1e-5]), np.array([5e3, 0.1])
+        scale = 1000.0
+    else:               # [f1, D1, f2, D2, D3]
+        f = lambda b_, f1, D1, f2, D2, D3: f1 * np.exp(-b_ * D1) + f2 * np.exp(-b_ * D2) + (1 - f1 - f2) * np.exp(-b_ * D3)  # noqa: E731
+        P = np.stack([rng.uniform(0.3, 0.5, n), rng.uniform(5e-4, 1.5e-3, n), rng.uniform(0.2, 0.3, n),
+                      rng.uniform(5e-3, 1e-2, n), rng.uniform(0.05, 0.15, n)], 1)
+        p0 = np.array([0.4, 1e-3, 0.25, 8e-3, 0.1])
+        lb, ub = np.array([0.01, 1e-4, 0.01, 3e-3, 0.03]), np.array([0.9, 3e-3, 0.9, 3e-2, 0.5])
+        scale = 1.0
+    y = np.stack([f(b, *p) for p in P]) * (1 + 0.01 * rng.standard_normal((n, 16)))
+    y[::5, 4] *= 1.3
+    sigma = np.linspace(0.005, 0.04, 16) * scale
+    kw_scipy, kw_core = _EXTRA_CASES[case]
+    fs = {"f_scale": 0.02 * scale} if "loss" in kw_scipy and "sigma" not in kw_scipy else {}
+    kw_scipy = {**{k: (sigma if isinstance(v, str) and v == "S" else v) for k, v in kw_scipy.items()}, **fs}
+    kw_core = {**{k: (1.0 / sigma if isinstance(v, str) and v == "W" else v) for k, v in kw_core.items()}, **fs}
+    fits = [curve_fit(f, b, yi, p0=p0, bounds=(lb, ub), method="trf", maxfev=250, ftol=1e-8, **kw_scipy) for yi in y]
+    ref = np.array([p for p, _ in fits])
+    r = hostsim.trf_fit_extras(model_id, b, y, np.tile(p0, (n, 1)), np.tile(lb, (n, 1)), np.tile(ub, (n, 1)), **kw_core)
+    ok = r["status"] > 0
+    assert ok.all()
+    # residual norms agree; parameters agree wherever the minimiser is well determined
+    res = lambda P_: np.array([np.linalg.norm(f(b, *p) - yi) for p, yi in zip(P_, y)])  # noqa: E731
+    assert np.allclose(res(r["params"]), res(ref), rtol=1e-6)
+    assert np.median(np.abs(r["params"] - ref) / np.abs(ref)) <= 1e-6
